@@ -1,0 +1,171 @@
+/*
+ * fdpt.h — C ABI of libfdpt.so, the B200 (sm_100a) sampler hot path of framedipt_b200.
+ *
+ * The reference (instadeepai/FrameDiPT) has no FFI: its boundary for this path is a Python call
+ * surface.  Each entry point below names the reference interface it replaces (paths relative to
+ * the reference repository root).  The Python shims in framedipt_b200/ bind these with ctypes
+ * (see INTEGRATION.md); no torch types cross this boundary — only raw pointers and sizes.
+ *
+ * Conventions
+ *   - one context per GPU, not thread-safe (one host thread per context);
+ *   - all tensor pointers are DEVICE pointers to contiguous row-major arrays unless stated;
+ *   - every call enqueues on the caller's `stream` (a cudaStream_t passed as void*) and returns
+ *     0 on success or a negative fdpt_status; fdpt_last_error(ctx) gives the message;
+ *   - no exception crosses the ABI;  dtypes: f32 unless stated, i32 indices, f64 where the
+ *     reference computes in float64 (IGSO(3) score, reverse SDE step).
+ */
+#ifndef FDPT_H
+#define FDPT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdpt_ctx fdpt_ctx;
+
+typedef enum {
+  FDPT_OK = 0,
+  FDPT_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  FDPT_ERR_CUDA = -2,      /* CUDA runtime error */
+  FDPT_ERR_PARAM = -3,     /* unknown / missing / mis-shaped parameter */
+  FDPT_ERR_STATE = -4      /* call order (params not finalised, no schedule ...) */
+} fdpt_status;
+
+/* Model + diffuser hyper-parameters: config/base.yaml:33-79 of the reference
+ * (model_conf.*, model_conf.embed.*, model_conf.ipa.*, diffuser.r3.*, diffuser.so3.*). */
+typedef struct {
+  int32_t c_s, c_z, c_hidden, c_skip;
+  int32_t no_heads, no_qk_points, no_v_points, num_blocks;
+  int32_t index_embed_size, num_bins;
+  float min_bin, max_bin;
+  int32_t seq_tfmr_num_heads, seq_tfmr_num_layers;
+  float coordinate_scaling;
+  int32_t with_aatype;      /* 1: node features carry the 21-way aatype one-hot (inpainting / input_aatype) */
+  double r3_min_b, r3_max_b;
+} fdpt_config;
+
+/* Per-step schedule row (doubles), filled on the host with the reference's numpy expressions
+ * (so3_diffuser.py:288-323, r3_diffuser.py:48-96, experiments/utils.py:166-190). */
+enum {
+  FDPT_SCHED_T32 = 0,        /* t rounded through float32 (feats["t"]) */
+  FDPT_SCHED_SIGMA = 1,      /* discrete_sigma[t_to_idx(t)] */
+  FDPT_SCHED_SO3_G2DT = 2,   /* g(t)^2 * dt */
+  FDPT_SCHED_SO3_NOISE = 3,  /* g(t) * sqrt(dt) * noise_scale */
+  FDPT_SCHED_R3_BT = 4,      /* b_t */
+  FDPT_SCHED_DT = 5,         /* dt */
+  FDPT_SCHED_R3_NOISE = 6,   /* sqrt(b_t) * sqrt(dt) * noise_scale */
+  FDPT_SCHED_SPARE = 7,
+  FDPT_SCHED_COLS = 8
+};
+
+/* Input features of one forward = the feature dict of experiments/sampler.py:69-111, 267-354. */
+typedef struct {
+  const float* rigids_t;     /* [B,N,7] quat (w,x,y,z) + translation in Angstrom */
+  const float* sc_ca_t;      /* [B,N,3] self-conditioning CA (Angstrom) */
+  const float* res_mask;     /* [B,N] */
+  const float* fixed_mask;   /* [B,N] */
+  const int32_t* seq_idx;    /* [B,N] */
+  const int32_t* aatype;     /* [B,N] after preprocess_aatype (framedipt/data/utils.py:565-610); NULL if with_aatype=0 */
+  const float* gt_psi;       /* [B,N,2] torsion_angles_sin_cos[...,2,:] */
+  const float* idx_emb;      /* [B,N,E] get_index_embedding(seq_idx), host-evaluated (score_network.py:17-38) */
+  const float* rel_emb;      /* [R,E]   get_index_embedding(r) for r = rel_min .. rel_min+R-1 */
+  int32_t rel_min, rel_count;
+  const float* t_emb;        /* [B,E]   get_timestep_embedding(t)    (score_network.py:41-64), host-evaluated */
+  const float* t_emb_eps;    /* [E]     get_timestep_embedding(1e-5) */
+  const float* t32;          /* [B]     feats["t"] */
+  const double* sigma;       /* [B]     discrete_sigma[t_to_idx(t)] */
+} fdpt_feats;
+
+/* Outputs of one forward = ScoreNetwork.forward's dict (score_network.py:262-275). Any pointer may be NULL. */
+typedef struct {
+  float* rigids;       /* [B,N,7] predicted x0 frames (quat + trans, Angstrom) */
+  double* rot_score;   /* [B,N,3] float64 like the reference */
+  float* trans_score;  /* [B,N,3] */
+  float* psi;          /* [B,N,2] */
+  float* atom37_bb;    /* [B,N,5,3] atom37 slots 0..4 (N,CA,C,CB,O) of the predicted frames; other 32 slots are zero */
+} fdpt_out;
+
+/* Trajectory buffers of fdpt_sample = the dict returned by inference_fn (experiments/utils.py:610-626).
+ * Index 0 of each trajectory is the FINAL sample (the reference flips).  Any pointer may be NULL. */
+typedef struct {
+  float* prot_traj;     /* [T,B,N,5,3]  backbone of x_{t-1} (atom37 slots 0..4) */
+  float* rigid_traj;    /* [T+1,B,N,7]  */
+  float* trans_traj;    /* [T,B,N,3]    */
+  float* rigid_0_traj;  /* [T,B,N,5,3]  backbone of the x0 prediction */
+  float* psi_pred;      /* [B,N,2]      last step */
+  int32_t final_only;   /* 1: only slot 0 (final sample) of prot_traj / rigid_traj / ... is written ([1,...] buffers) */
+} fdpt_traj;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* replaces: ScoreNetwork.__init__ / SE3Diffuser.__init__ (score_network.py:200-216, se3_diffuser.py:39-49) */
+int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out);
+int fdpt_destroy(fdpt_ctx* ctx);
+const char* fdpt_last_error(const fdpt_ctx* ctx);
+const char* fdpt_version(void);
+
+/* replaces: nn.Module.load_state_dict (experiments/inference.py:149-161).  `data` may be a host or device
+ * pointer to float32; key/shape are those of the reference state_dict. */
+int fdpt_load_param(fdpt_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim);
+int fdpt_finalize_params(fdpt_ctx* ctx);
+int fdpt_num_params_expected(const fdpt_ctx* ctx);
+
+/* Reserve workspace for problems up to (B,N); optional (forward grows it lazily, which synchronises). */
+int fdpt_reserve(fdpt_ctx* ctx, int B, int N);
+int64_t fdpt_workspace_bytes(const fdpt_ctx* ctx);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* replaces: ScoreNetwork.forward (score_network.py:218-275) incl. Embedder (129-197), IpaScore.forward
+ * (ipa_pytorch.py:509-572), calc_rot_score / calc_trans_score (se3_diffuser.py:269-292). */
+int fdpt_forward(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_out* out, void* stream);
+
+/* replaces: SE3Diffuser.reverse (se3_diffuser.py:346-401) + Rigid.to_tensor_7 (rigid_utils.py:1200-1212).
+ * sched_row: host pointer to FDPT_SCHED_COLS doubles.  z_rot/z_trans: N(0,1) draws [B,N,3] float64 (device).
+ * rigids_out may alias rigids_t. */
+int fdpt_reverse(fdpt_ctx* ctx, int B, int N, const float* rigids_t, const double* rot_score, const float* trans_score,
+                 const float* diffuse_mask, const double* z_rot, const double* z_trans, const double* sched_row,
+                 int center, int diffuse_rot, int diffuse_trans, float* rigids_out, void* stream);
+
+/* replaces: all_atom.compute_backbone (framedipt/protein/all_atom.py:147-176) as used by
+ * get_atom_positions_from_rigids (experiments/utils.py:415-438).  aatype may be NULL (ALA). out [B,N,5,3]. */
+int fdpt_backbone(fdpt_ctx* ctx, int B, int N, const float* rigids, const float* psi, const int32_t* aatype,
+                  float* atom37_bb, void* stream);
+
+/* replaces: SE3Diffuser.calc_rot_score / calc_trans_score as standalone calls */
+int fdpt_rot_score(fdpt_ctx* ctx, int B, int N, const float* quats_t, const float* quats_0, const double* sigma,
+                   const float* mask, double* out, void* stream);
+int fdpt_trans_score(fdpt_ctx* ctx, int B, int N, const float* trans_t, const float* trans_0, const float* t32,
+                     const float* mask, int scale, float* out, void* stream);
+
+/* replaces: experiments.utils.inference_fn's loop (experiments/utils.py:557-626): one self-conditioning forward
+ * at the first t, then num_t x (forward -> reverse | take x0 at the last step -> backbone).
+ *   sched      host [num_t, FDPT_SCHED_COLS] doubles, step 0 = t=1.0 ... last = min_t
+ *   t_emb_tab  device [num_t, E] timestep embeddings per step; feats->t_emb / t32 / sigma are ignored
+ *   noise      device float64 [num_t-1, 2, B, N, 3] standard normals (rot then trans), reference draw order
+ *   feats->rigids_t is read as x_T and not modified; feats->sc_ca_t is the initial self-conditioning (zeros). */
+int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t, const double* sched,
+                const float* t_emb_tab, const double* noise, int self_condition, int center,
+                int diffuse_rot, int diffuse_trans, const fdpt_traj* out, void* stream);
+
+/* number of kernel launches enqueued by this context since creation (bench.py's gpu_launches) */
+int64_t fdpt_launch_count(const fdpt_ctx* ctx);
+
+/* ---- unit entry points (parity tests per kernel; same kernels the hot path launches) ---------- */
+/* y[M,N] = act(x[M,K] @ w[N,K]^T + bias) ; act: 0 none, 1 relu */
+int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act,
+                float* y, void* stream);
+/* InvariantPointAttention.forward (ipa_pytorch.py:170-329) of block `blk` on given s [B,N,c_s], z [B,N,N,c_z],
+ * frames (quats [B,N,4], trans in 0.1 A units [B,N,3]), mask [B,N] -> out [B,N,c_s] (linear_out applied, not masked) */
+int fdpt_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z, const float* quats,
+             const float* trans, const float* mask, float* out, void* stream);
+/* EdgeTransition.forward (ipa_pytorch.py:84-102) of block `blk`, followed by *edge_mask: z_out may alias z_in */
+int fdpt_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* z_in,
+                         const float* mask, float* z_out, void* stream);
+/* Embedder.forward (score_network.py:129-197) incl. the mask multiply of score_network.py:252-253 */
+int fdpt_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, float* edge_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDPT_H */
