@@ -1,0 +1,782 @@
+// fdpt_api.cu — context, parameters, workspace, forward orchestration, sampling loop and the C ABI of libfdpt.so.
+// Reference interfaces replaced by each entry point are listed in include/fdpt.h.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fdpt.h"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels_diffusion.cuh"
+#include "kernels_ipa.cuh"
+#include "kernels_misc.cuh"
+#include "backbone_tables.inc"
+
+using namespace fdpt;
+
+namespace {
+
+struct ParamSpec {
+  std::vector<int64_t> shape;
+  float* dev = nullptr;
+};
+
+struct BlockParams {
+  const float *head_w, *Wq, *bq, *Wkv, *bkv, *Wqp, *bqp, *Wkvp, *bkvp, *Wb, *bb, *Wd, *bd, *Wout, *bout;
+  const float *ln_g, *ln_b, *Wskip, *bskip;
+  struct TfLayer {
+    const float *Win, *bin, *Wo, *bo, *W1, *b1, *W2, *b2, *n1g, *n1b, *n2g, *n2b;
+  } tf[TF_LAYERS];
+  const float *Wpost, *bpost;
+  const float *Wt1, *bt1, *Wt2, *bt2, *Wt3, *bt3, *tln_g, *tln_b;
+  const float *Wbb, *bbb;
+  // edge transition (blocks 0..2)
+  const float *Wie, *bie, *We1, *be1, *We2, *be2, *Wef, *bef, *eln_g, *eln_b;
+};
+
+struct Workspace {
+  char* base = nullptr;
+  size_t bytes = 0;
+  int capB = 0, capN = 0;
+  long long pair_chunk = 0;
+  // node side
+  float *node_feat, *feat1d, *node0, *node, *tmpA, *tmpB, *tmpC;  // tmp: [M,320]-capable
+  float *PA, *PB, *RelProj;
+  float *q, *kv, *qp_raw, *kvp_raw, *q_pts, *k_pts, *v_pts, *cat;
+  float *tf_x, *qkv, *att_o;
+  float *upd, *quats, *trans, *dmask;
+  float *n_emb, *U, *V, *Pf, *Qf;
+  float *tors_u;
+  // pair side
+  float *z, *S, *h1, *h2, *ho;
+  // outputs / sampling state
+  float *pred_rigids, *trans_score, *psi, *rig_cur, *rig_next, *sc_ca, *t_emb_b, *t32_b, *bb_tmp;
+  double *rot_score, *sigma_b, *sched_dev;
+};
+
+}  // namespace
+
+struct fdpt_ctx {
+  fdpt_config cfg;
+  int device = 0;
+  std::string err;
+  std::map<std::string, ParamSpec> params;
+  bool finalized = false;
+  BlockParams blk[NBLK];
+  struct {
+    const float *nW0, *nb0, *nW2, *nb2, *nW4, *nb4, *nln_g, *nln_b;
+    const float *eW0, *eb0, *eW2, *eb2, *eW4, *eb4, *eln_g, *eln_b;
+    const float *tW1, *tb1, *tW2, *tb2, *tWf, *tbf;
+  } top;
+  float *bin_lower = nullptr, *ideal = nullptr, *psi_frame = nullptr, *atom_mask = nullptr;
+  Workspace ws;
+  int64_t launches = 0;
+  int max_smem_optin = 0;
+};
+
+namespace {
+
+int fail(fdpt_ctx* c, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                                   \
+  do {                                                                                                             \
+    cudaError_t e__ = (call);                                                                                      \
+    if (e__ != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define LAUNCH_CHECK()   \
+  do {                   \
+    ctx->launches++;     \
+    CK(cudaGetLastError()); \
+  } while (0)
+
+int f1_dim(const fdpt_ctx* c) { return c->cfg.with_aatype ? 54 : 33; }
+
+std::vector<std::pair<std::string, std::vector<int64_t>>> expected_params(const fdpt_ctx* c) {
+  std::vector<std::pair<std::string, std::vector<int64_t>>> v;
+  auto lin = [&](const std::string& n, int64_t o, int64_t i) {
+    v.push_back({n + ".weight", {o, i}});
+    v.push_back({n + ".bias", {o}});
+  };
+  auto ln = [&](const std::string& n, int64_t cdim) {
+    v.push_back({n + ".weight", {cdim}});
+    v.push_back({n + ".bias", {cdim}});
+  };
+  const int f1 = f1_dim(c);
+  const std::string ne = "embedding_layer.node_embedder", ee = "embedding_layer.edge_embedder";
+  lin(ne + ".0", C_S, f1 + EMB); lin(ne + ".2", C_S, C_S); lin(ne + ".4", C_S, C_S); ln(ne + ".5", C_S);
+  lin(ee + ".0", C_Z, 2 * f1 + EMB + NBINS); lin(ee + ".2", C_Z, C_Z); lin(ee + ".4", C_Z, C_Z); ln(ee + ".5", C_Z);
+  const std::string t = "score_model.trunk.";
+  for (int b = 0; b < NBLK; ++b) {
+    const std::string bs = std::to_string(b), p = t + "ipa_" + bs;
+    v.push_back({p + ".head_weights", {NH}});
+    lin(p + ".linear_q", NH * C_HID, C_S); lin(p + ".linear_kv", 2 * NH * C_HID, C_S);
+    lin(p + ".linear_q_points", NH * PQ * 3, C_S); lin(p + ".linear_kv_points", NH * (PQ + PV) * 3, C_S);
+    lin(p + ".linear_b", NH, C_Z); lin(p + ".down_z", C_Z / 4, C_Z); lin(p + ".linear_out", C_S, CAT);
+    ln(t + "ipa_ln_" + bs, C_S);
+    lin(t + "skip_embed_" + bs, C_SKIP, C_S);
+    for (int l = 0; l < TF_LAYERS; ++l) {
+      const std::string q = t + "seq_tfmr_" + bs + ".layers." + std::to_string(l);
+      v.push_back({q + ".self_attn.in_proj_weight", {3 * TF_D, TF_D}});
+      v.push_back({q + ".self_attn.in_proj_bias", {3 * TF_D}});
+      lin(q + ".self_attn.out_proj", TF_D, TF_D); lin(q + ".linear1", TF_D, TF_D); lin(q + ".linear2", TF_D, TF_D);
+      ln(q + ".norm1", TF_D); ln(q + ".norm2", TF_D);
+    }
+    lin(t + "post_tfmr_" + bs, C_S, TF_D);
+    const std::string nt = t + "node_transition_" + bs;
+    lin(nt + ".linear_1", C_S, C_S); lin(nt + ".linear_2", C_S, C_S); lin(nt + ".linear_3", C_S, C_S); ln(nt + ".ln", C_S);
+    lin(t + "bb_update_" + bs + ".linear", 6, C_S);
+    if (b < NBLK - 1) {
+      const std::string et = t + "edge_transition_" + bs;
+      lin(et + ".initial_embed", C_S / 2, C_S); lin(et + ".trunk.0", ET_HID, ET_HID); lin(et + ".trunk.2", ET_HID, ET_HID);
+      lin(et + ".final_layer", C_Z, ET_HID); ln(et + ".layer_norm", C_Z);
+    }
+  }
+  const std::string tp = "score_model.torsion_pred";
+  lin(tp + ".linear_1", C_S, C_S); lin(tp + ".linear_2", C_S, C_S); lin(tp + ".linear_final", 2, C_S);
+  return v;
+}
+
+// keys that exist in the reference state_dict but are never used by the forward pass
+bool is_unused_key(const std::string& k) {
+  return k.find(".linear_rbf.") != std::string::npos || k.find("torsion_pred.linear_3.") != std::string::npos;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------------
+template <typename T>
+T* carve(char*& p, size_t n) {
+  T* r = reinterpret_cast<T*>(p);
+  p += ((n * sizeof(T) + 255) / 256) * 256;
+  return r;
+}
+
+int reserve_ws(fdpt_ctx* ctx, int B, int N) {
+  Workspace& w = ctx->ws;
+  if (w.base && B <= w.capB && N <= w.capN && (long long)B * N <= (long long)w.capB * w.capN) return FDPT_OK;
+  CK(cudaDeviceSynchronize());
+  if (w.base) CK(cudaFree(w.base));
+  w = Workspace();
+  const size_t M = (size_t)B * N, P = M * N;
+  const long long chunk = (long long)std::min<size_t>(P, (size_t)1 << 20);
+  const int R = 4 * 4096;  // capacity of the relative-offset table
+  for (int pass = 0; pass < 2; ++pass) {
+    char* p = pass ? w.base : nullptr;
+    w.node_feat = carve<float>(p, M * 96); w.feat1d = carve<float>(p, M * 64);
+    w.node0 = carve<float>(p, M * C_S); w.node = carve<float>(p, M * C_S);
+    w.tmpA = carve<float>(p, M * ET_HID); w.tmpB = carve<float>(p, M * ET_HID); w.tmpC = carve<float>(p, M * ET_HID);
+    w.PA = carve<float>(p, M * C_Z); w.PB = carve<float>(p, M * C_Z); w.RelProj = carve<float>(p, (size_t)R * C_Z);
+    w.q = carve<float>(p, M * NH * C_HID); w.kv = carve<float>(p, M * 2 * NH * C_HID);
+    w.qp_raw = carve<float>(p, M * NH * PQ * 3); w.kvp_raw = carve<float>(p, M * NH * (PQ + PV) * 3);
+    w.q_pts = carve<float>(p, M * NH * PQ * 3); w.k_pts = carve<float>(p, M * NH * PQ * 3); w.v_pts = carve<float>(p, M * NH * PV * 3);
+    w.cat = carve<float>(p, M * CAT);
+    w.tf_x = carve<float>(p, M * TF_D); w.qkv = carve<float>(p, M * 3 * TF_D); w.att_o = carve<float>(p, M * TF_D);
+    w.upd = carve<float>(p, M * 8); w.quats = carve<float>(p, M * 4); w.trans = carve<float>(p, M * 4); w.dmask = carve<float>(p, M);
+    w.n_emb = carve<float>(p, M * C_Z); w.U = carve<float>(p, M * ET_HID); w.V = carve<float>(p, M * ET_HID);
+    w.Pf = carve<float>(p, M * C_Z); w.Qf = carve<float>(p, M * C_Z); w.tors_u = carve<float>(p, M * 2);
+    w.z = carve<float>(p, P * C_Z); w.S = carve<float>(p, P * NH);
+    w.h1 = carve<float>(p, (size_t)chunk * ET_HID); w.h2 = carve<float>(p, (size_t)chunk * ET_HID); w.ho = carve<float>(p, (size_t)chunk * C_Z);
+    w.pred_rigids = carve<float>(p, M * 7); w.trans_score = carve<float>(p, M * 3); w.psi = carve<float>(p, M * 2);
+    w.rig_cur = carve<float>(p, M * 7); w.rig_next = carve<float>(p, M * 7); w.sc_ca = carve<float>(p, M * 3);
+    w.t_emb_b = carve<float>(p, (size_t)B * EMB); w.t32_b = carve<float>(p, B); w.bb_tmp = carve<float>(p, M * 15);
+    w.rot_score = carve<double>(p, M * 3); w.sigma_b = carve<double>(p, B); w.sched_dev = carve<double>(p, 4096 * FDPT_SCHED_COLS);
+    if (!pass) {
+      w.bytes = (size_t)(p - (char*)nullptr);
+      CK(cudaMalloc(&w.base, w.bytes));
+    }
+  }
+  w.capB = B; w.capN = N; w.pair_chunk = chunk;
+  return FDPT_OK;
+}
+
+// ---- small launch helpers ------------------------------------------------------------------------------
+struct Lin {
+  fdpt_ctx* ctx;
+  cudaStream_t st;
+  // y[M,N] (ldc) = epi(x[M,K] (lda) @ W[N,K]^T (ldb))
+  int operator()(const float* x, int lda, const float* W, int ldb, const float* bias, float* y, int ldc, long long M, int N, int K,
+                 int relu = 0, const float* residual = nullptr, int ldr = 0, const float* rowmask = nullptr, int accumulate = 0) const {
+    GemmArgs g;
+    g.A = x; g.lda = lda; g.B = W; g.ldb = ldb; g.C = y; g.ldc = ldc; g.M = (int)M; g.N = N; g.K = K;
+    g.bias = bias; g.relu = relu; g.residual = residual; g.ldr = ldr; g.rowmask = rowmask; g.accumulate = accumulate;
+    cudaError_t e = launch_gemm(g, true, 1, st);
+    ctx->launches++;
+    if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+    return FDPT_OK;
+  }
+};
+
+#define RET(x)                 \
+  do {                         \
+    int r__ = (x);             \
+    if (r__ != FDPT_OK) return r__; \
+  } while (0)
+
+template <int C>
+int layernorm(fdpt_ctx* ctx, cudaStream_t st, const float* x, float* y, const float* g, const float* b, long long rows,
+              const float* rowmask, const float* pairmask = nullptr, int nres = 0, long long row0 = 0) {
+  if (rows <= 0) return FDPT_OK;
+  layernorm_kernel<C><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, y, g, b, rows, rowmask, pairmask, nres, row0);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+
+// ---- embedder -------------------------------------------------------------------------------------------
+int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, float* z_out, cudaStream_t st) {
+  Workspace& w = ctx->ws;
+  const long long M = (long long)B * N, P = M * N;
+  const int F1 = f1_dim(ctx), FN = F1 + EMB, EIN = 2 * F1 + EMB + NBINS;
+  Lin lin{ctx, st};
+  if (in->rel_count <= 0 || in->rel_count > 4 * 4096) return fail(ctx, FDPT_ERR_INVALID, "rel_count %d out of range", in->rel_count);
+  {
+    dim3 blk(32, 8);
+    node_feats_kernel<<<(unsigned)((M + 7) / 8), blk, 0, st>>>((int)M, N, ctx->cfg.with_aatype, in->aatype, in->fixed_mask, in->t_emb,
+                                                                 in->t_emb_eps, in->idx_emb, w.feat1d, w.node_feat);
+    LAUNCH_CHECK();
+  }
+  auto& T = ctx->top;
+  // node MLP
+  RET(lin(w.node_feat, FN, T.nW0, FN, T.nb0, w.tmpA, C_S, M, C_S, FN, 1));
+  RET(lin(w.tmpA, C_S, T.nW2, C_S, T.nb2, w.tmpB, C_S, M, C_S, C_S, 1));
+  RET(lin(w.tmpB, C_S, T.nW4, C_S, T.nb4, w.tmpA, C_S, M, C_S, C_S, 0));
+  RET(layernorm<C_S>(ctx, st, w.tmpA, node_out, T.nln_g, T.nln_b, M, in->res_mask));
+  // edge layer-1 partials: W0 = [A (F1) | B (F1) | C (32) | D (22)]
+  RET(lin(w.feat1d, F1, T.eW0, EIN, T.eb0, w.PA, C_Z, M, C_Z, F1, 0));
+  RET(lin(w.feat1d, F1, T.eW0 + F1, EIN, nullptr, w.PB, C_Z, M, C_Z, F1, 0));
+  RET(lin(in->rel_emb, EMB, T.eW0 + 2 * F1, EIN, nullptr, w.RelProj, C_Z, in->rel_count, C_Z, EMB, 0));
+  for (long long r0 = 0; r0 < P; r0 += w.pair_chunk) {
+    const long long rows = std::min<long long>(w.pair_chunk, P - r0);
+    edge_l1_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(r0, rows, N, w.PA, w.PB, w.RelProj, in->seq_idx, in->rel_min, in->rel_count,
+                                                                in->sc_ca_t, ctx->bin_lower, T.eW0, EIN, 2 * F1 + EMB, w.h1);
+    LAUNCH_CHECK();
+    RET(lin(w.h1, C_Z, T.eW2, C_Z, T.eb2, w.h2, C_Z, rows, C_Z, C_Z, 1));
+    RET(lin(w.h2, C_Z, T.eW4, C_Z, T.eb4, w.ho, C_Z, rows, C_Z, C_Z, 0));
+    RET(layernorm<C_Z>(ctx, st, w.ho, z_out + r0 * C_Z, T.eln_g, T.eln_b, rows, nullptr, in->res_mask, N, r0));
+  }
+  return FDPT_OK;
+}
+
+// ---- IPA ---------------------------------------------------------------------------------------------------
+int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z, const float* quats, const float* trans,
+            const float* mask, float* out, int ldo, const float* residual, const float* outmask, cudaStream_t st) {
+  Workspace& w = ctx->ws;
+  const BlockParams& p = ctx->blk[blk];
+  const long long M = (long long)B * N;
+  Lin lin{ctx, st};
+  RET(lin(s, C_S, p.Wq, C_S, p.bq, w.q, NH * C_HID, M, NH * C_HID, C_S));
+  RET(lin(s, C_S, p.Wkv, C_S, p.bkv, w.kv, 2 * NH * C_HID, M, 2 * NH * C_HID, C_S));
+  RET(lin(s, C_S, p.Wqp, C_S, p.bqp, w.qp_raw, NH * PQ * 3, M, NH * PQ * 3, C_S));
+  RET(lin(s, C_S, p.Wkvp, C_S, p.bkvp, w.kvp_raw, NH * (PQ + PV) * 3, M, NH * (PQ + PV) * 3, C_S));
+  ipa_points_kernel<<<(unsigned)M, 128, 0, st>>>((int)M, w.qp_raw, w.kvp_raw, quats, trans, w.q_pts, w.k_pts, w.v_pts);
+  LAUNCH_CHECK();
+  {  // S[b,h] = Q_h K_h^T
+    GemmArgs g;
+    g.A = w.q; g.lda = NH * C_HID; g.sA1 = (long long)N * NH * C_HID; g.sA2 = C_HID;
+    g.B = w.kv; g.ldb = 2 * NH * C_HID; g.sB1 = (long long)N * 2 * NH * C_HID; g.sB2 = 2 * C_HID;
+    g.C = w.S; g.ldc = N; g.sC1 = (long long)NH * N * N; g.sC2 = (long long)N * N;
+    g.M = N; g.N = N; g.K = C_HID; g.batch2 = NH;
+    CK(launch_gemm(g, true, B * NH, st));
+    ctx->launches++;
+  }
+  {
+    IpaCoreArgs a;
+    a.B = B; a.N = N; a.S = w.S; a.z = z; a.q_pts = w.q_pts; a.k_pts = w.k_pts; a.v_pts = w.v_pts; a.quats = quats; a.trans = trans;
+    a.mask = mask; a.Wb = p.Wb; a.bb = p.bb; a.head_w = p.head_w; a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat;
+    const size_t smem = ipa_core_smem_bytes(N);
+    if ((int)smem > ctx->max_smem_optin) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs %zu B of shared memory in ipa_core", N, smem);
+    ipa_core_kernel<<<dim3(N, B), 256, smem, st>>>(a);
+    LAUNCH_CHECK();
+  }
+  {  // o[b,:,h,:] = A_h V_h  -> cat[:, h*256 : (h+1)*256]
+    GemmArgs g;
+    g.A = w.S; g.lda = N; g.sA1 = (long long)NH * N * N; g.sA2 = (long long)N * N;
+    g.B = w.kv + C_HID; g.ldb = 2 * NH * C_HID; g.sB1 = (long long)N * 2 * NH * C_HID; g.sB2 = 2 * C_HID;
+    g.C = w.cat; g.ldc = CAT; g.sC1 = (long long)N * CAT; g.sC2 = C_HID;
+    g.M = N; g.N = C_HID; g.K = N; g.batch2 = NH;
+    CK(launch_gemm(g, false, B * NH, st));
+    ctx->launches++;
+  }
+  // linear_out (+ mask, + residual)
+  RET(lin(w.cat, CAT, p.Wout, CAT, p.bout, out, ldo, M, C_S, CAT, 0, residual, C_S, outmask));
+  return FDPT_OK;
+}
+
+// ---- edge transition -----------------------------------------------------------------------------------------
+int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* z_in, const float* mask, float* z_out,
+                        cudaStream_t st) {
+  Workspace& w = ctx->ws;
+  const BlockParams& p = ctx->blk[blk];
+  const long long M = (long long)B * N, P = M * N;
+  Lin lin{ctx, st};
+  RET(lin(node, C_S, p.Wie, C_S, p.bie, w.n_emb, C_Z, M, C_Z, C_S));
+  // x = [z | n_i | n_j]; trunk.0 and final_layer are split column-wise so the node parts are per-residue
+  RET(lin(w.n_emb, C_Z, p.We1 + C_Z, ET_HID, p.be1, w.U, ET_HID, M, ET_HID, C_Z));
+  RET(lin(w.n_emb, C_Z, p.We1 + 2 * C_Z, ET_HID, nullptr, w.V, ET_HID, M, ET_HID, C_Z));
+  RET(lin(w.n_emb, C_Z, p.Wef + C_Z, ET_HID, p.bef, w.Pf, C_Z, M, C_Z, C_Z));
+  RET(lin(w.n_emb, C_Z, p.Wef + 2 * C_Z, ET_HID, nullptr, w.Qf, C_Z, M, C_Z, C_Z));
+  for (long long r0 = 0; r0 < P; r0 += w.pair_chunk) {
+    const long long rows = std::min<long long>(w.pair_chunk, P - r0);
+    const float* zc = z_in + r0 * C_Z;
+    {  // h1 = relu(W1z z + U_i + V_j)
+      GemmArgs g;
+      g.A = zc; g.lda = C_Z; g.B = p.We1; g.ldb = ET_HID; g.C = w.h1; g.ldc = ET_HID; g.M = (int)rows; g.N = ET_HID; g.K = C_Z;
+      g.U = w.U; g.V = w.V; g.lduv = ET_HID; g.nres = N; g.row0 = r0; g.relu = 1;
+      CK(launch_gemm(g, true, 1, st));
+      ctx->launches++;
+    }
+    RET(lin(w.h1, ET_HID, p.We2, ET_HID, p.be2, w.h2, ET_HID, rows, ET_HID, ET_HID, 1));
+    {  // o = Wf r2 + P_i + Q_j  (+ Wf[:, :128] z below)
+      GemmArgs g;
+      g.A = w.h2; g.lda = ET_HID; g.B = p.Wef; g.ldb = ET_HID; g.C = w.ho; g.ldc = C_Z; g.M = (int)rows; g.N = C_Z; g.K = ET_HID;
+      g.U = w.Pf; g.V = w.Qf; g.lduv = C_Z; g.nres = N; g.row0 = r0;
+      CK(launch_gemm(g, true, 1, st));
+      ctx->launches++;
+    }
+    RET(lin(zc, C_Z, p.Wef, ET_HID, nullptr, w.ho, C_Z, rows, C_Z, C_Z, 0, nullptr, 0, nullptr, 1));
+    RET(layernorm<C_Z>(ctx, st, w.ho, z_out + r0 * C_Z, p.eln_g, p.eln_b, rows, nullptr, mask, N, r0));
+  }
+  return FDPT_OK;
+}
+
+// ---- sequence transformer (post-norm encoder, ipa_pytorch.py:433-443, 533-539) ------------------------------------
+int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaStream_t st) {
+  Workspace& w = ctx->ws;
+  const BlockParams& p = ctx->blk[blk];
+  const long long M = (long long)B * N;
+  Lin lin{ctx, st};
+  // x = [node | skip_embed(init_node)]
+  copy_cols_kernel<<<(unsigned)((M * C_S + 255) / 256), 256, 0, st>>>(M, C_S, w.node, C_S, w.tf_x, TF_D, 0, nullptr);
+  LAUNCH_CHECK();
+  RET(lin(w.node0, C_S, p.Wskip, C_S, p.bskip, w.tf_x + C_S, TF_D, M, C_SKIP, C_S));
+  for (int l = 0; l < TF_LAYERS; ++l) {
+    const auto& L = p.tf[l];
+    RET(lin(w.tf_x, TF_D, L.Win, TF_D, L.bin, w.qkv, 3 * TF_D, M, 3 * TF_D, TF_D));
+    {
+      GemmArgs g;  // S[b,h] = Q K^T
+      g.A = w.qkv; g.lda = 3 * TF_D; g.sA1 = (long long)N * 3 * TF_D; g.sA2 = TF_DH;
+      g.B = w.qkv + TF_D; g.ldb = 3 * TF_D; g.sB1 = (long long)N * 3 * TF_D; g.sB2 = TF_DH;
+      g.C = w.S; g.ldc = N; g.sC1 = (long long)TF_H * N * N; g.sC2 = (long long)N * N;
+      g.M = N; g.N = N; g.K = TF_DH; g.batch2 = TF_H;
+      CK(launch_gemm(g, true, B * TF_H, st));
+      ctx->launches++;
+    }
+    {
+      const long long rows = (long long)B * TF_H * N;
+      softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.S, rows, N, TF_H * N, 1.0f / sqrtf((float)TF_DH), mask);
+      LAUNCH_CHECK();
+    }
+    {
+      GemmArgs g;  // O = P V
+      g.A = w.S; g.lda = N; g.sA1 = (long long)TF_H * N * N; g.sA2 = (long long)N * N;
+      g.B = w.qkv + 2 * TF_D; g.ldb = 3 * TF_D; g.sB1 = (long long)N * 3 * TF_D; g.sB2 = TF_DH;
+      g.C = w.att_o; g.ldc = TF_D; g.sC1 = (long long)N * TF_D; g.sC2 = TF_DH;
+      g.M = N; g.N = TF_DH; g.K = N; g.batch2 = TF_H;
+      CK(launch_gemm(g, false, B * TF_H, st));
+      ctx->launches++;
+    }
+    RET(lin(w.att_o, TF_D, L.Wo, TF_D, L.bo, w.tmpA, TF_D, M, TF_D, TF_D, 0, w.tf_x, TF_D));
+    RET(layernorm<TF_D>(ctx, st, w.tmpA, w.tf_x, L.n1g, L.n1b, M, nullptr));
+    RET(lin(w.tf_x, TF_D, L.W1, TF_D, L.b1, w.tmpA, TF_D, M, TF_D, TF_D, 1));
+    RET(lin(w.tmpA, TF_D, L.W2, TF_D, L.b2, w.tmpB, TF_D, M, TF_D, TF_D, 0, w.tf_x, TF_D));
+    RET(layernorm<TF_D>(ctx, st, w.tmpB, w.tf_x, L.n2g, L.n2b, M, nullptr));
+  }
+  // node = node + post_tfmr(x)
+  RET(lin(w.tf_x, TF_D, p.Wpost, TF_D, p.bpost, w.node, C_S, M, C_S, TF_D, 0, w.node, C_S));
+  return FDPT_OK;
+}
+
+// ---- full forward -------------------------------------------------------------------------------------------------
+int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_out* out, cudaStream_t st) {
+  if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
+  if (B <= 0 || N <= 0) return fail(ctx, FDPT_ERR_INVALID, "bad B=%d N=%d", B, N);
+  RET(reserve_ws(ctx, B, N));
+  Workspace& w = ctx->ws;
+  const long long M = (long long)B * N;
+  Lin lin{ctx, st};
+  const float cs = ctx->cfg.coordinate_scaling;
+  RET(run_embed(ctx, B, N, in, w.node0, w.z, st));
+  CK(cudaMemcpyAsync(w.node, w.node0, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
+  init_frames_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, in->rigids_t, cs, in->res_mask, in->fixed_mask, w.quats, w.trans,
+                                                                  w.dmask);
+  LAUNCH_CHECK();
+  for (int b = 0; b < NBLK; ++b) {
+    const BlockParams& p = ctx->blk[b];
+    // node = LN(node + ipa(node) * mask)
+    RET(run_ipa(ctx, b, B, N, w.node, w.z, w.quats, w.trans, in->res_mask, w.tmpC, C_S, w.node, in->res_mask, st));
+    RET(layernorm<C_S>(ctx, st, w.tmpC, w.node, p.ln_g, p.ln_b, M, nullptr));
+    RET(run_seq_tfmr(ctx, b, B, N, in->res_mask, st));
+    // node transition
+    RET(lin(w.node, C_S, p.Wt1, C_S, p.bt1, w.tmpA, C_S, M, C_S, C_S, 1));
+    RET(lin(w.tmpA, C_S, p.Wt2, C_S, p.bt2, w.tmpB, C_S, M, C_S, C_S, 1));
+    RET(lin(w.tmpB, C_S, p.Wt3, C_S, p.bt3, w.tmpA, C_S, M, C_S, C_S, 0, w.node, C_S));
+    RET(layernorm<C_S>(ctx, st, w.tmpA, w.node, p.tln_g, p.tln_b, M, in->res_mask));
+    // backbone update
+    RET(lin(w.node, C_S, p.Wbb, C_S, p.bbb, w.upd, 6, M, 6, C_S));
+    compose_update_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, w.upd, w.dmask, w.quats, w.trans);
+    LAUNCH_CHECK();
+    if (b < NBLK - 1) RET(run_edge_transition(ctx, b, B, N, w.node, w.z, in->res_mask, w.z, st));
+  }
+  // heads
+  float* rig = (out && out->rigids) ? out->rigids : w.pred_rigids;
+  finish_frames_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, w.quats, w.trans, cs, rig);
+  LAUNCH_CHECK();
+  double* rs = (out && out->rot_score) ? out->rot_score : w.rot_score;
+  rot_score_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>((int)M, N, in->rigids_t, 7, w.quats, 4, in->sigma, in->res_mask, rs);
+  LAUNCH_CHECK();
+  float* ts = (out && out->trans_score) ? out->trans_score : w.trans_score;
+  trans_score_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, N, in->rigids_t + 4, 7, rig + 4, 7, 1.0f, in->t32,
+                                                                  (float)ctx->cfg.r3_min_b, (float)ctx->cfg.r3_max_b, cs, 1, in->res_mask, ts);
+  LAUNCH_CHECK();
+  // torsion head (ipa_pytorch.py:347-363)
+  auto& T = ctx->top;
+  RET(lin(w.node, C_S, T.tW1, C_S, T.tb1, w.tmpA, C_S, M, C_S, C_S, 1));
+  RET(lin(w.tmpA, C_S, T.tW2, C_S, T.tb2, w.tmpB, C_S, M, C_S, C_S, 0, w.node, C_S));
+  RET(lin(w.tmpB, C_S, T.tWf, C_S, T.tbf, w.tors_u, 2, M, 2, C_S));
+  float* psi = (out && out->psi) ? out->psi : w.psi;
+  psi_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, w.tors_u, in->fixed_mask, in->gt_psi, psi);
+  LAUNCH_CHECK();
+  if (out && out->atom37_bb) {
+    backbone_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, rig, psi, ctx->cfg.with_aatype ? in->aatype : nullptr, ctx->ideal,
+                                                                 ctx->psi_frame, ctx->atom_mask, out->atom37_bb);
+    LAUNCH_CHECK();
+  }
+  return FDPT_OK;
+}
+
+__global__ void set_step_kernel(int B, int step, const float* __restrict__ t_emb_tab, const double* __restrict__ sched,
+                                float* __restrict__ t_emb_b, float* __restrict__ t32_b, double* __restrict__ sigma_b) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < B * EMB) t_emb_b[idx] = t_emb_tab[step * EMB + (idx % EMB)];
+  if (idx < B) {
+    t32_b[idx] = (float)sched[step * FDPT_SCHED_COLS + FDPT_SCHED_T32];
+    sigma_b[idx] = sched[step * FDPT_SCHED_COLS + FDPT_SCHED_SIGMA];
+  }
+}
+
+__global__ void copy_trans_kernel(int M, const float* __restrict__ rig, float* __restrict__ ca) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < M * 3) ca[idx] = rig[(idx / 3) * 7 + 4 + idx % 3];
+}
+
+}  // namespace
+
+// =======================================================================================================
+// C ABI
+// =======================================================================================================
+extern "C" {
+
+const char* fdpt_version(void) { return "framedipt_b200 libfdpt 0.1 (sm_100a)"; }
+
+const char* fdpt_last_error(const fdpt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
+  if (!cfg || !out) return FDPT_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->c_s != C_S || cfg->c_z != C_Z || cfg->c_hidden != C_HID || cfg->c_skip != C_SKIP || cfg->no_heads != NH ||
+      cfg->no_qk_points != PQ || cfg->no_v_points != PV || cfg->num_blocks != NBLK || cfg->index_embed_size != EMB ||
+      cfg->num_bins != NBINS || cfg->seq_tfmr_num_heads != TF_H || cfg->seq_tfmr_num_layers != TF_LAYERS)
+    return FDPT_ERR_INVALID;  // kernels are specialised for the reference's default dims (config/base.yaml:55-79)
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return FDPT_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return FDPT_ERR_CUDA;
+  fdpt_ctx* ctx = new fdpt_ctx();
+  ctx->cfg = *cfg;
+  ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
+  float lower[NBINS];
+  {
+    // torch.linspace (CPU, float32): step = (end - start) / (steps - 1); first half start + i*step, second half end - (steps-1-i)*step
+    const float start = cfg->min_bin, end = cfg->max_bin;
+    const float step = (end - start) / (float)(NBINS - 1);
+    for (int i = 0; i < NBINS; ++i) lower[i] = (i < NBINS / 2) ? start + step * (float)i : end - step * (float)(NBINS - 1 - i);
+  }
+  bool ok = cudaMalloc(&ctx->bin_lower, sizeof(lower)) == cudaSuccess && cudaMalloc(&ctx->ideal, sizeof(kIdealBB)) == cudaSuccess &&
+            cudaMalloc(&ctx->psi_frame, sizeof(kPsiFrame)) == cudaSuccess && cudaMalloc(&ctx->atom_mask, sizeof(kAtomMask)) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->bin_lower, lower, sizeof(lower), cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(ctx->ideal, kIdealBB, sizeof(kIdealBB), cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(ctx->psi_frame, kPsiFrame, sizeof(kPsiFrame), cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(ctx->atom_mask, kAtomMask, sizeof(kAtomMask), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) {
+    delete ctx;
+    return FDPT_ERR_CUDA;
+  }
+  *out = ctx;
+  return FDPT_OK;
+}
+
+int fdpt_destroy(fdpt_ctx* ctx) {
+  if (!ctx) return FDPT_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->params) cudaFree(kv.second.dev);
+  cudaFree(ctx->ws.base);
+  cudaFree(ctx->bin_lower);
+  cudaFree(ctx->ideal);
+  cudaFree(ctx->psi_frame);
+  cudaFree(ctx->atom_mask);
+  delete ctx;
+  return FDPT_OK;
+}
+
+int fdpt_num_params_expected(const fdpt_ctx* ctx) { return ctx ? (int)expected_params(ctx).size() : 0; }
+
+int fdpt_load_param(fdpt_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!ctx || !key || !data || !shape) return FDPT_ERR_INVALID;
+  const std::string k(key);
+  if (is_unused_key(k)) return FDPT_OK;  // accepted and ignored, like dead parameters in the reference
+  bool found = false;
+  for (auto& e : expected_params(ctx)) {
+    if (e.first != k) continue;
+    found = true;
+    if ((int)e.second.size() != ndim) return fail(ctx, FDPT_ERR_PARAM, "size mismatch for %s: expected %zu dims, got %d", key, e.second.size(), ndim);
+    for (int i = 0; i < ndim; ++i)
+      if (e.second[i] != shape[i]) return fail(ctx, FDPT_ERR_PARAM, "size mismatch for %s: dim %d expected %lld, got %lld", key, i, (long long)e.second[i], (long long)shape[i]);
+  }
+  if (!found) return fail(ctx, FDPT_ERR_PARAM, "Unexpected key(s) in state_dict: %s", key);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+  ParamSpec& ps = ctx->params[k];
+  if (!ps.dev) CK(cudaMalloc(&ps.dev, n * sizeof(float) + 64));
+  ps.shape.assign(shape, shape + ndim);
+  CK(cudaMemcpy(ps.dev, data, n * sizeof(float), cudaMemcpyDefault));
+  ctx->finalized = false;
+  return FDPT_OK;
+}
+
+int fdpt_finalize_params(fdpt_ctx* ctx) {
+  if (!ctx) return FDPT_ERR_INVALID;
+  std::string missing;
+  for (auto& e : expected_params(ctx))
+    if (!ctx->params.count(e.first)) missing += (missing.empty() ? "" : ", ") + e.first;
+  if (!missing.empty()) return fail(ctx, FDPT_ERR_PARAM, "Missing key(s) in state_dict: %s", missing.substr(0, 900).c_str());
+  auto P = [&](const std::string& k) -> const float* { return ctx->params.at(k).dev; };
+  const std::string ne = "embedding_layer.node_embedder", ee = "embedding_layer.edge_embedder", t = "score_model.trunk.";
+  auto& T = ctx->top;
+  T.nW0 = P(ne + ".0.weight"); T.nb0 = P(ne + ".0.bias"); T.nW2 = P(ne + ".2.weight"); T.nb2 = P(ne + ".2.bias");
+  T.nW4 = P(ne + ".4.weight"); T.nb4 = P(ne + ".4.bias"); T.nln_g = P(ne + ".5.weight"); T.nln_b = P(ne + ".5.bias");
+  T.eW0 = P(ee + ".0.weight"); T.eb0 = P(ee + ".0.bias"); T.eW2 = P(ee + ".2.weight"); T.eb2 = P(ee + ".2.bias");
+  T.eW4 = P(ee + ".4.weight"); T.eb4 = P(ee + ".4.bias"); T.eln_g = P(ee + ".5.weight"); T.eln_b = P(ee + ".5.bias");
+  const std::string tp = "score_model.torsion_pred";
+  T.tW1 = P(tp + ".linear_1.weight"); T.tb1 = P(tp + ".linear_1.bias"); T.tW2 = P(tp + ".linear_2.weight"); T.tb2 = P(tp + ".linear_2.bias");
+  T.tWf = P(tp + ".linear_final.weight"); T.tbf = P(tp + ".linear_final.bias");
+  for (int b = 0; b < NBLK; ++b) {
+    BlockParams& p = ctx->blk[b];
+    const std::string bs = std::to_string(b), ip = t + "ipa_" + bs;
+    p.head_w = P(ip + ".head_weights");
+    p.Wq = P(ip + ".linear_q.weight"); p.bq = P(ip + ".linear_q.bias"); p.Wkv = P(ip + ".linear_kv.weight"); p.bkv = P(ip + ".linear_kv.bias");
+    p.Wqp = P(ip + ".linear_q_points.weight"); p.bqp = P(ip + ".linear_q_points.bias");
+    p.Wkvp = P(ip + ".linear_kv_points.weight"); p.bkvp = P(ip + ".linear_kv_points.bias");
+    p.Wb = P(ip + ".linear_b.weight"); p.bb = P(ip + ".linear_b.bias"); p.Wd = P(ip + ".down_z.weight"); p.bd = P(ip + ".down_z.bias");
+    p.Wout = P(ip + ".linear_out.weight"); p.bout = P(ip + ".linear_out.bias");
+    p.ln_g = P(t + "ipa_ln_" + bs + ".weight"); p.ln_b = P(t + "ipa_ln_" + bs + ".bias");
+    p.Wskip = P(t + "skip_embed_" + bs + ".weight"); p.bskip = P(t + "skip_embed_" + bs + ".bias");
+    for (int l = 0; l < TF_LAYERS; ++l) {
+      const std::string q = t + "seq_tfmr_" + bs + ".layers." + std::to_string(l);
+      auto& L = p.tf[l];
+      L.Win = P(q + ".self_attn.in_proj_weight"); L.bin = P(q + ".self_attn.in_proj_bias");
+      L.Wo = P(q + ".self_attn.out_proj.weight"); L.bo = P(q + ".self_attn.out_proj.bias");
+      L.W1 = P(q + ".linear1.weight"); L.b1 = P(q + ".linear1.bias"); L.W2 = P(q + ".linear2.weight"); L.b2 = P(q + ".linear2.bias");
+      L.n1g = P(q + ".norm1.weight"); L.n1b = P(q + ".norm1.bias"); L.n2g = P(q + ".norm2.weight"); L.n2b = P(q + ".norm2.bias");
+    }
+    p.Wpost = P(t + "post_tfmr_" + bs + ".weight"); p.bpost = P(t + "post_tfmr_" + bs + ".bias");
+    const std::string nt = t + "node_transition_" + bs;
+    p.Wt1 = P(nt + ".linear_1.weight"); p.bt1 = P(nt + ".linear_1.bias"); p.Wt2 = P(nt + ".linear_2.weight"); p.bt2 = P(nt + ".linear_2.bias");
+    p.Wt3 = P(nt + ".linear_3.weight"); p.bt3 = P(nt + ".linear_3.bias"); p.tln_g = P(nt + ".ln.weight"); p.tln_b = P(nt + ".ln.bias");
+    p.Wbb = P(t + "bb_update_" + bs + ".linear.weight"); p.bbb = P(t + "bb_update_" + bs + ".linear.bias");
+    if (b < NBLK - 1) {
+      const std::string et = t + "edge_transition_" + bs;
+      p.Wie = P(et + ".initial_embed.weight"); p.bie = P(et + ".initial_embed.bias");
+      p.We1 = P(et + ".trunk.0.weight"); p.be1 = P(et + ".trunk.0.bias"); p.We2 = P(et + ".trunk.2.weight"); p.be2 = P(et + ".trunk.2.bias");
+      p.Wef = P(et + ".final_layer.weight"); p.bef = P(et + ".final_layer.bias");
+      p.eln_g = P(et + ".layer_norm.weight"); p.eln_b = P(et + ".layer_norm.bias");
+    }
+  }
+  ctx->finalized = true;
+  return FDPT_OK;
+}
+
+int fdpt_reserve(fdpt_ctx* ctx, int B, int N) {
+  if (!ctx || B <= 0 || N <= 0) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return reserve_ws(ctx, B, N);
+}
+
+int64_t fdpt_workspace_bytes(const fdpt_ctx* ctx) { return ctx ? (int64_t)ctx->ws.bytes : 0; }
+int64_t fdpt_launch_count(const fdpt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int fdpt_forward(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_out* out, void* stream) {
+  if (!ctx || !in) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return forward_impl(ctx, B, N, in, out, (cudaStream_t)stream);
+}
+
+int fdpt_reverse(fdpt_ctx* ctx, int B, int N, const float* rigids_t, const double* rot_score, const float* trans_score,
+                 const float* diffuse_mask, const double* z_rot, const double* z_trans, const double* sched_row, int center,
+                 int diffuse_rot, int diffuse_trans, float* rigids_out, void* stream) {
+  if (!ctx || !rigids_t || !rot_score || !trans_score || !diffuse_mask || !z_rot || !z_trans || !sched_row || !rigids_out) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  RET(reserve_ws(ctx, std::max(B, ctx->ws.capB), std::max(N, ctx->ws.capN)));
+  CK(cudaMemcpyAsync(ctx->ws.sched_dev, sched_row, sizeof(double) * FDPT_SCHED_COLS, cudaMemcpyHostToDevice, st));
+  ReverseArgs a;
+  a.N = N; a.rigids_t = rigids_t; a.rot_score = rot_score; a.trans_score = trans_score; a.dmask = diffuse_mask; a.z_rot = z_rot;
+  a.z_trans = z_trans; a.sched = ctx->ws.sched_dev; a.center = center; a.diffuse_rot = diffuse_rot; a.diffuse_trans = diffuse_trans;
+  a.cs = ctx->cfg.coordinate_scaling; a.rigids_out = rigids_out;
+  reverse_kernel<<<B, 256, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+
+int fdpt_backbone(fdpt_ctx* ctx, int B, int N, const float* rigids, const float* psi, const int32_t* aatype, float* atom37_bb,
+                  void* stream) {
+  if (!ctx || !rigids || !psi || !atom37_bb) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int M = B * N;
+  backbone_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(M, rigids, psi, aatype, ctx->ideal, ctx->psi_frame, ctx->atom_mask, atom37_bb);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+
+int fdpt_rot_score(fdpt_ctx* ctx, int B, int N, const float* quats_t, const float* quats_0, const double* sigma, const float* mask,
+                   double* out, void* stream) {
+  if (!ctx || !quats_t || !quats_0 || !sigma || !out) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int M = B * N;
+  rot_score_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(M, N, quats_t, 4, quats_0, 4, sigma, mask, out);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+
+int fdpt_trans_score(fdpt_ctx* ctx, int B, int N, const float* trans_t, const float* trans_0, const float* t32, const float* mask,
+                     int scale, float* out, void* stream) {
+  if (!ctx || !trans_t || !trans_0 || !t32 || !out) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int M = B * N;
+  trans_score_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(M, N, trans_t, 3, trans_0, 3, 1.0f, t32, (float)ctx->cfg.r3_min_b,
+                                                                        (float)ctx->cfg.r3_max_b, ctx->cfg.coordinate_scaling, scale, mask, out);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+
+int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t, const double* sched, const float* t_emb_tab,
+                const double* noise, int self_condition, int center, int diffuse_rot, int diffuse_trans, const fdpt_traj* out,
+                void* stream) {
+  if (!ctx || !feats || !sched || !t_emb_tab || !out || num_t <= 0 || num_t > 4096) return FDPT_ERR_INVALID;
+  if (num_t > 1 && !noise) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  RET(reserve_ws(ctx, B, N));
+  Workspace& w = ctx->ws;
+  const long long M = (long long)B * N;
+  const int T = num_t;
+  CK(cudaMemcpyAsync(w.sched_dev, sched, sizeof(double) * FDPT_SCHED_COLS * T, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(w.rig_cur, feats->rigids_t, sizeof(float) * M * 7, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(w.sc_ca, feats->sc_ca_t, sizeof(float) * M * 3, cudaMemcpyDeviceToDevice, st));
+  const int fo = out->final_only;
+  if (out->rigid_traj && !fo) CK(cudaMemcpyAsync(out->rigid_traj + (long long)T * M * 7, w.rig_cur, sizeof(float) * M * 7, cudaMemcpyDeviceToDevice, st));
+  fdpt_feats f = *feats;
+  f.rigids_t = w.rig_cur; f.sc_ca_t = w.sc_ca; f.t_emb = w.t_emb_b; f.t32 = w.t32_b; f.sigma = w.sigma_b;
+  fdpt_out o;
+  memset(&o, 0, sizeof(o));
+  o.rigids = w.pred_rigids; o.rot_score = w.rot_score; o.trans_score = w.trans_score; o.psi = w.psi;
+  const unsigned gM3 = (unsigned)((M * 3 + 255) / 256), gM = (unsigned)((M + 127) / 128);
+  auto set_step = [&](int s) -> int {
+    set_step_kernel<<<(B * EMB + 255) / 256, 256, 0, st>>>(B, s, t_emb_tab, w.sched_dev, w.t_emb_b, w.t32_b, w.sigma_b);
+    LAUNCH_CHECK();
+    return FDPT_OK;
+  };
+  if (self_condition) {  // experiments/utils.py:571-578
+    RET(set_step(0));
+    RET(forward_impl(ctx, B, N, &f, &o, st));
+    copy_trans_kernel<<<gM3, 256, 0, st>>>((int)M, w.pred_rigids, w.sc_ca);
+    LAUNCH_CHECK();
+  }
+  const int32_t* aat = ctx->cfg.with_aatype ? feats->aatype : nullptr;
+  for (int s = 0; s < T; ++s) {
+    const bool last = sched[s * FDPT_SCHED_COLS + FDPT_SCHED_SPARE] != 0.0;  // !(t > min_t)
+    RET(set_step(s));
+    RET(forward_impl(ctx, B, N, &f, &o, st));
+    if (!last) {
+      copy_trans_kernel<<<gM3, 256, 0, st>>>((int)M, w.pred_rigids, w.sc_ca);
+      LAUNCH_CHECK();
+      ReverseArgs a;
+      a.N = N; a.rigids_t = w.rig_cur; a.rot_score = w.rot_score; a.trans_score = w.trans_score; a.dmask = w.dmask;
+      a.z_rot = noise + ((long long)s * 2 + 0) * M * 3; a.z_trans = noise + ((long long)s * 2 + 1) * M * 3;
+      a.sched = w.sched_dev + s * FDPT_SCHED_COLS; a.center = center; a.diffuse_rot = diffuse_rot; a.diffuse_trans = diffuse_trans;
+      a.cs = ctx->cfg.coordinate_scaling; a.rigids_out = w.rig_next;
+      reverse_kernel<<<B, 256, 0, st>>>(a);
+      LAUNCH_CHECK();
+    } else {
+      CK(cudaMemcpyAsync(w.rig_next, w.pred_rigids, sizeof(float) * M * 7, cudaMemcpyDeviceToDevice, st));
+    }
+    const long long slot = fo ? 0 : (T - 1 - s);
+    const bool write = !fo || s == T - 1;
+    // backbone of x_{t-1} and of the x0 prediction (experiments/utils.py:396-410); always computed, like the reference
+    float* bb = (write && out->prot_traj) ? out->prot_traj + slot * M * 15 : w.bb_tmp;
+    backbone_kernel<<<gM, 128, 0, st>>>((int)M, w.rig_next, w.psi, aat, ctx->ideal, ctx->psi_frame, ctx->atom_mask, bb);
+    LAUNCH_CHECK();
+    float* bb0 = (write && out->rigid_0_traj) ? out->rigid_0_traj + slot * M * 15 : w.bb_tmp;
+    backbone_kernel<<<gM, 128, 0, st>>>((int)M, w.pred_rigids, w.psi, aat, ctx->ideal, ctx->psi_frame, ctx->atom_mask, bb0);
+    LAUNCH_CHECK();
+    if (write && out->trans_traj) {
+      trans0_kernel<<<gM, 128, 0, st>>>((int)M, w.pred_rigids, w.rig_next, feats->res_mask, feats->fixed_mask, out->trans_traj + slot * M * 3);
+      LAUNCH_CHECK();
+    }
+    if (write && out->rigid_traj) CK(cudaMemcpyAsync(out->rigid_traj + slot * M * 7, w.rig_next, sizeof(float) * M * 7, cudaMemcpyDeviceToDevice, st));
+    std::swap(w.rig_cur, w.rig_next);
+    f.rigids_t = w.rig_cur;
+  }
+  if (out->psi_pred) CK(cudaMemcpyAsync(out->psi_pred, w.psi, sizeof(float) * M * 2, cudaMemcpyDeviceToDevice, st));
+  return FDPT_OK;
+}
+
+// ---- unit entry points ------------------------------------------------------------------------------------
+int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act, float* y, void* stream) {
+  if (!ctx || !x || !w || !y) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  Lin lin{ctx, (cudaStream_t)stream};
+  return lin(x, K, w, K, bias, y, N, M, N, K, act);
+}
+
+int fdpt_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z, const float* quats, const float* trans,
+             const float* mask, float* out, void* stream) {
+  if (!ctx || blk < 0 || blk >= NBLK || !s || !z || !quats || !trans || !mask || !out) return FDPT_ERR_INVALID;
+  if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
+  cudaSetDevice(ctx->device);
+  RET(reserve_ws(ctx, B, N));
+  return run_ipa(ctx, blk, B, N, s, z, quats, trans, mask, out, C_S, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int fdpt_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* z_in, const float* mask, float* z_out,
+                         void* stream) {
+  if (!ctx || blk < 0 || blk >= NBLK - 1 || !node || !z_in || !mask || !z_out) return FDPT_ERR_INVALID;
+  if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
+  cudaSetDevice(ctx->device);
+  RET(reserve_ws(ctx, B, N));
+  return run_edge_transition(ctx, blk, B, N, node, z_in, mask, z_out, (cudaStream_t)stream);
+}
+
+int fdpt_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, float* edge_out, void* stream) {
+  if (!ctx || !in || !node_out || !edge_out) return FDPT_ERR_INVALID;
+  if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
+  cudaSetDevice(ctx->device);
+  RET(reserve_ws(ctx, B, N));
+  return run_embed(ctx, B, N, in, node_out, edge_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+// kernels_misc.cuh — LayerNorm, feature building, frame algebra, small elementwise kernels.
+#pragma once
+#include "common.cuh"
+
+namespace fdpt {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim C (eps 1e-5, torch default), one warp per row.
+//   y = LN(x) * gamma + beta ; optionally y *= rowmask[row] (node mask) or pair mask m[b,i]*m[b,j].
+// x and y may alias.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, float* y, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, long long rows,
+                                                        const float* __restrict__ rowmask,
+                                                        const float* __restrict__ pairmask, int nres, long long row0) {
+  constexpr int PER = C / 32;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * C;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i];
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + 1e-5f);
+  float m = 1.f;
+  if (rowmask) m = rowmask[row];
+  if (pairmask) {
+    const long long p = row0 + row;
+    const long long nn = (long long)nres * nres;
+    const long long b = p / nn;
+    const int rem = (int)(p - b * nn);
+    const int i = rem / nres, j = rem - i * nres;
+    m = pairmask[b * nres + i] * pairmask[b * nres + j];
+  }
+  float* yr = y + row * C;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    yr[c] = ((v[i] - mean) * rstd * gamma[c] + beta[c]) * m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Node features (Embedder.forward, score_network.py:153-182):
+//   feat1d[m, :F1] = [onehot21(aatype) | t_emb (eps row on fixed residues) | fixed_mask]      (F1 = 54, or 33 without aatype)
+//   node_feat[m, :F1+32] = [feat1d | idx_emb]
+// ------------------------------------------------------------------------------------------------
+__global__ void node_feats_kernel(int M, int N, int with_aatype, const int32_t* __restrict__ aatype,
+                                  const float* __restrict__ fixed_mask, const float* __restrict__ t_emb,
+                                  const float* __restrict__ t_emb_eps, const float* __restrict__ idx_emb,
+                                  float* __restrict__ feat1d, float* __restrict__ node_feat) {
+  const int m = blockIdx.x * blockDim.y + threadIdx.y;
+  if (m >= M) return;
+  const int b = m / N;
+  const int F1 = with_aatype ? 54 : 33;
+  const int FN = F1 + EMB;
+  const float fm = fixed_mask[m];
+  const int aa = with_aatype ? aatype[m] : 0;
+  for (int c = threadIdx.x; c < FN; c += blockDim.x) {
+    float v;
+    int cc = c;
+    if (with_aatype) {
+      if (c < 21) {
+        v = (c == aa) ? 1.f : 0.f;
+        cc = -1;
+      } else {
+        cc = c - 21;
+      }
+    }
+    if (cc >= 0) {
+      if (cc < EMB) {
+        v = (with_aatype && fm != 0.f) ? t_emb_eps[cc] : t_emb[b * EMB + cc];
+      } else if (cc == EMB) {
+        v = fm;
+      } else {
+        v = idx_emb[(long long)m * EMB + (cc - EMB - 1)];
+      }
+    }
+    node_feat[(long long)m * FN + c] = v;
+    if (c < F1) feat1d[(long long)m * F1 + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Edge-embedder layer 1, factorised:
+//   h1[p, c] = relu( PA[b,i,c] + PB[b,j,c] + RelProj[seq_i - seq_j - rel_min, c] + W0[c, dcol0 + bin(d_ij)] )
+// PA already holds the layer bias.  bin: (d > lower[k]) & (d < upper[k]), upper[21] = 1e8
+// (framedipt/data/utils.py:541-550); d = ||sc_ca_i - sc_ca_j|| in fp32.
+// One warp per pair, lane covers 4 channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) edge_l1_kernel(long long row0, long long rows, int N, const float* __restrict__ PA,
+                                                      const float* __restrict__ PB, const float* __restrict__ RelProj,
+                                                      const int32_t* __restrict__ seq_idx, int rel_min, int rel_count,
+                                                      const float* __restrict__ sc_ca, const float* __restrict__ bin_lower,
+                                                      const float* __restrict__ W0, int ldw, int dcol0,
+                                                      float* __restrict__ h1) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const long long p = row0 + r;
+  const long long nn = (long long)N * N;
+  const long long b = p / nn;
+  const int rem = (int)(p - b * nn);
+  const int i = rem / N, j = rem - i * N;
+  const long long mi = b * N + i, mj = b * N + j;
+  const float dx = sc_ca[mi * 3 + 0] - sc_ca[mj * 3 + 0];
+  const float dy = sc_ca[mi * 3 + 1] - sc_ca[mj * 3 + 1];
+  const float dz = sc_ca[mi * 3 + 2] - sc_ca[mj * 3 + 2];
+  const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  int bin = -1;
+#pragma unroll 1
+  for (int k = 0; k < NBINS; ++k) {
+    const float lo = bin_lower[k];
+    const float hi = (k + 1 < NBINS) ? bin_lower[k + 1] : 1e8f;
+    if (d > lo && d < hi) bin = k;
+  }
+  int rel = seq_idx[mi] - seq_idx[mj] - rel_min;
+  rel = min(max(rel, 0), rel_count - 1);
+  const int c = lane * 4;
+  const float4 a = *reinterpret_cast<const float4*>(PA + mi * C_Z + c);
+  const float4 bb = *reinterpret_cast<const float4*>(PB + mj * C_Z + c);
+  const float4 rr = *reinterpret_cast<const float4*>(RelProj + (long long)rel * C_Z + c);
+  float v[4] = {a.x + bb.x + rr.x, a.y + bb.y + rr.y, a.z + bb.z + rr.z, a.w + bb.w + rr.w};
+  if (bin >= 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += W0[(long long)(c + k) * ldw + dcol0 + bin];
+  }
+  float4 o = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+  *reinterpret_cast<float4*>(h1 + r * C_Z + c) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small strided copy:  dst[m, dcol0 + c] = src[m, c] * (rowmask ? rowmask[m] : 1)   for c < cols
+// ------------------------------------------------------------------------------------------------
+__global__ void copy_cols_kernel(long long M, int cols, const float* __restrict__ src, int lds, float* __restrict__ dst,
+                                 int ldd, int dcol0, const float* __restrict__ rowmask) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * cols) return;
+  const long long m = idx / cols;
+  const int c = (int)(idx - m * cols);
+  float v = src[m * lds + c];
+  if (rowmask) v *= rowmask[m];
+  dst[m * ldd + dcol0 + c] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frames init (IpaScore.forward, ipa_pytorch.py:517-524): quats = rigids_t[..., :4], trans = rigids_t[..., 4:] * 0.1
+// plus diffuse_mask = (1 - fixed) * res_mask
+// ------------------------------------------------------------------------------------------------
+__global__ void init_frames_kernel(int M, const float* __restrict__ rigids, float scale, const float* __restrict__ res_mask,
+                                   const float* __restrict__ fixed_mask, float* __restrict__ quats,
+                                   float* __restrict__ trans, float* __restrict__ diffuse_mask) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) quats[m * 4 + k] = rigids[m * 7 + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) trans[m * 3 + k] = rigids[m * 7 + 4 + k] * scale;
+  diffuse_mask[m] = (1.f - fixed_mask[m]) * res_mask[m];
+}
+
+// final frames: rigids[m] = [quats | trans / cs]   (unscale_rigids, ipa_pytorch.py:495-507: fp32 divide)
+__global__ void finish_frames_kernel(int M, const float* __restrict__ quats, const float* __restrict__ trans, float cs,
+                                     float* __restrict__ rigids) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rigids[m * 7 + k] = quats[m * 4 + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) rigids[m * 7 + 4 + k] = __fdiv_rn(trans[m * 3 + k], cs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rigid.compose_q_update_vec (rigid_utils.py:1039-1063, 587-616, 266-275):
+//   q' = normalise(q + m * (q (x) (0, u0..2)))  ;  t' = t + m * R(q) u3..5      (t in 0.1 A units)
+// ------------------------------------------------------------------------------------------------
+__global__ void compose_update_kernel(int M, const float* __restrict__ upd, const float* __restrict__ dmask,
+                                      float* __restrict__ quats, float* __restrict__ trans) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float q[4], R[9];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = quats[m * 4 + k];
+  const float u[6] = {upd[m * 6 + 0], upd[m * 6 + 1], upd[m * 6 + 2], upd[m * 6 + 3], upd[m * 6 + 4], upd[m * 6 + 5]};
+  const float mk = dmask[m];
+  const float v[4] = {0.f, u[0], u[1], u[2]};
+  float dq[4];
+  quat_mul(q, v, dq);
+  float nq[4];
+  float n2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    nq[k] = q[k] + dq[k] * mk;
+    n2 += nq[k] * nq[k];
+  }
+  const float inv = 1.f / sqrtf(n2);
+  quat_to_rot(q, R);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) quats[m * 4 + k] = nq[k] * inv;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    trans[m * 3 + r] += (R[r * 3 + 0] * u[3] + R[r * 3 + 1] * u[4] + R[r * 3 + 2] * u[5]) * mk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax with scale and key mask (sequence transformer; boolean key-padding semantics).
+// S[rows, N]: row = ((b*H + h)*N + i).  One warp per row, in place.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long rows, int N, int rows_per_batch,
+                                                           float scale, const float* __restrict__ keymask) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long b = row / rows_per_batch;
+  float* s = S + row * N;
+  const float* km = keymask + b * N;
+  float mx = -INFINITY;
+  for (int j = lane; j < N; j += 32)
+    if (km[j] != 0.f) mx = fmaxf(mx, s[j] * scale);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    const float e = (km[j] != 0.f) ? expf(s[j] * scale - mx) : 0.f;
+    s[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  for (int j = lane; j < N; j += 32) s[j] *= inv;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Torsion head epilogue + psi blend (ipa_pytorch.py:355-361, score_network.py:258-260):
+//   psi = u / sqrt(max(|u|^2, 1e-8)) ; psi = dm * psi + (1 - dm) * gt_psi,  dm = 1 - fixed_mask
+// ------------------------------------------------------------------------------------------------
+__global__ void psi_kernel(int M, const float* __restrict__ u, const float* __restrict__ fixed_mask,
+                           const float* __restrict__ gt_psi, float* __restrict__ psi) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float a = u[m * 2], b = u[m * 2 + 1];
+  const float den = sqrtf(fmaxf(a * a + b * b, 1e-8f));
+  const float dm = 1.f - fixed_mask[m];
+  psi[m * 2 + 0] = dm * (a / den) + (1.f - dm) * gt_psi[m * 2 + 0];
+  psi[m * 2 + 1] = dm * (b / den) + (1.f - dm) * gt_psi[m * 2 + 1];
+}
+
+}  // namespace fdpt

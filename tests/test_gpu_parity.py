@@ -1,0 +1,160 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libfdpt.so) against the reference-generated golden
+fixtures and the CPU oracle.  Tolerances are fp32-class (SURVEY §8c parity protocol)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import bb_rmsd, rot_angle_between
+
+pytestmark = pytest.mark.gpu
+
+from framedipt_b200.config import default_conf  # noqa: E402
+
+
+def _load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+def _feats(g, device=None):
+    f = {k[3:]: torch.tensor(v) for k, v in g.items() if k.startswith("in_")}
+    if device is not None:
+        f = {k: v.to(device) for k, v in f.items()}
+    return f
+
+
+@pytest.fixture(scope="module")
+def model(state_dict):
+    from framedipt_b200 import SE3Diffuser
+    from framedipt_b200.score_network import ScoreNetwork
+
+    conf = default_conf()
+    diffuser = SE3Diffuser(conf.diffuser)
+    m = ScoreNetwork(conf.model, diffuser, inpainting=True)
+    m.load_state_dict(state_dict)
+    m = m.to("cuda").eval()
+    return m, diffuser
+
+
+@pytest.fixture(scope="module")
+def ctx(model):
+    return model[0].context(torch.device("cuda", 0))
+
+
+def test_linear(ctx):
+    g = torch.Generator().manual_seed(1)
+    for (M, N, K, act) in [(100, 70, 86, 1), (257, 256, 2688, 0), (64, 6, 256, 0)]:
+        x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+        y = ctx.linear(x.cuda(), w.cuda(), b.cuda(), act).cpu()
+        ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        if act:
+            ref = ref.relu()
+        assert (y - ref.float()).abs().max() < 1e-5 * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize("name", ["forward_small.npz", "forward_small_padded.npz"])
+def test_embed_ipa_edge_kernels(golden_dir, model, ctx, name):
+    g = _load(golden_dir, name)
+    m, _ = model
+    feats = _feats(g, "cuda")
+    pf = m.prepare(feats, torch.device("cuda", 0))
+    node, edge = ctx.embed(pf, feats["t"])
+    valid = g["in_res_mask"].astype(bool)
+    em = valid[:, :, None] & valid[:, None, :]
+    assert np.abs(node.cpu().numpy() - g["tap_node_embed_raw"])[valid].max() < 2e-4
+    assert np.abs(edge.cpu().numpy() - g["tap_edge_embed_raw"])[em].max() < 5e-4
+    assert np.all(edge.cpu().numpy()[~em] == 0)
+    # IPA block 0 on the reference's own inputs
+    mask = torch.tensor(g["in_res_mask"], dtype=torch.float32).cuda()
+    s = torch.tensor(g["tap_node_embed_raw"]).cuda() * mask[..., None]
+    z = torch.tensor(g["tap_edge_embed_raw"]).cuda() * (mask[:, :, None] * mask[:, None, :])[..., None]
+    rig = torch.tensor(g["in_rigids_t"]).cuda().float()
+    out = ctx.ipa(0, s.contiguous(), z.contiguous(), rig[..., :4].contiguous(), (rig[..., 4:] * 0.1).contiguous(), mask.contiguous())
+    ref = g["tap_ipa_0"]
+    assert np.abs(out.cpu().numpy() - ref)[valid].max() < 1e-4 * max(1.0, np.abs(ref).max())
+    # edge transition block 0
+    node_in = torch.tensor(g["tap_node_transition_0"]).cuda() * mask[..., None]
+    zo = ctx.edge_transition(0, node_in.contiguous(), z.contiguous(), mask.contiguous())
+    assert np.abs(zo.cpu().numpy() - g["tap_edge_transition_0"])[em].max() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["forward_small.npz", "forward_small_padded.npz"])
+def test_forward_vs_reference(golden_dir, model, name):
+    g = _load(golden_dir, name)
+    m, _ = model
+    out = m(_feats(g, "cuda"))
+    valid = g["in_res_mask"].astype(bool)
+    r, r_ref = out["rigids"].cpu().numpy(), g["out_rigids"]
+    assert np.abs(r[..., 4:] - r_ref[..., 4:])[valid].max() < 1e-4  # Angstrom
+    assert rot_angle_between(r[..., :4], r_ref[..., :4])[valid].max() < 1e-4  # rad
+    ts = np.abs(g["out_trans_score"]).max()
+    assert np.abs(out["trans_score"].cpu().numpy() - g["out_trans_score"]).max() < 1e-4 * ts
+    rs = np.abs(g["out_rot_score"]).max()
+    assert out["rot_score"].dtype == torch.float64
+    assert np.abs(out["rot_score"].cpu().numpy() - g["out_rot_score"]).max() < 2e-3 * rs
+    assert np.abs(out["psi"].cpu().numpy() - g["out_psi"])[valid].max() < 1e-4
+    assert np.abs(out["atom37"].cpu().numpy()[:, :, :5] - g["out_atom37"])[valid].max() < 2e-4
+    assert out["atom37"].shape == (2, 24, 37, 3) and out["atom14"].shape == (2, 24, 14, 3)
+
+
+def test_scores_grid(golden_dir, model, ctx):
+    g = _load(golden_dir, "scores_grid.npz")
+    _, diffuser = model
+    sigma = torch.tensor(diffuser._so3_diffuser.grid_sigma(g["t"])).cuda()
+    q_t = torch.tensor(g["q_t"]).cuda()
+    q_id = torch.zeros_like(q_t)
+    q_id[..., 0] = 1
+    for q0, key in ((q_id, "rot_score_identity0"), (torch.tensor(g["q_0"]).cuda(), "rot_score_random0")):
+        s = ctx.rot_score(q_t, q0.contiguous(), sigma).cpu().numpy()
+        assert np.abs(s - g[key]).max() <= 2e-5 * np.abs(g[key]).max()
+    ts = ctx.trans_score(torch.tensor(g["trans_t"]).cuda(), torch.tensor(g["trans_0"]).cuda(), torch.tensor(g["t"]).cuda()).cpu().numpy()
+    assert np.abs(ts - g["trans_score"]).max() <= 2e-6 * np.abs(g["trans_score"]).max()
+
+
+def test_reverse_and_backbone(golden_dir, model, ctx):
+    g = _load(golden_dir, "reverse_small.npz")
+    _, diffuser = model
+    rig = torch.tensor(g["rigids_t"]).cuda()
+    for ci in range(3):
+        t, dt, ns, center = g[f"c{ci}_params"]
+        row = diffuser.step_scalars(float(t), float(dt), float(ns))
+        out = ctx.reverse(rig, torch.tensor(g["rot_score"]).cuda(), torch.tensor(g["trans_score"]).cuda(),
+                          torch.tensor(g["diffuse_mask"], dtype=torch.float32).cuda(), torch.tensor(g[f"c{ci}_z_rot"]).cuda(),
+                          torch.tensor(g[f"c{ci}_z_trans"]).cuda(), row, center=bool(center)).cpu().numpy()
+        assert np.abs(out[..., 4:] - g[f"c{ci}_trans"]).max() < 1e-5
+        assert rot_angle_between(out[..., :4], g[f"c{ci}_tensor7"][..., :4]).max() < 2e-3  # fp32 quaternion of an fp32 matrix
+        from oracle.framedipt_oracle import quat_to_rot
+        R = quat_to_rot(torch.tensor(out[..., :4])).numpy()
+        assert np.abs(R - g[f"c{ci}_rotmats"]).max() < 2e-6
+    bb = ctx.backbone(rig, torch.tensor(g["psi"]).cuda(), torch.tensor(g["aatype"], dtype=torch.int32).cuda()).cpu().numpy()
+    assert np.abs(bb - g["atom37"][:, :, :5]).max() < 1e-5
+
+
+@pytest.mark.parametrize("name,num_t", [("traj_small.npz", 10), ("traj_cfg1.npz", 50)])
+def test_trajectory_vs_reference(golden_dir, model, name, num_t):
+    """Free-running sampling with the reference's noise: per-residue backbone RMSD <= 1e-3 Å (north star)."""
+    from framedipt_b200.inference import inference_fn
+
+    g = _load(golden_dir, name)
+    m, diffuser = model
+    out = inference_fn(m, diffuser, _feats(g, "cuda"), num_t=num_t, min_t=0.01, aux_traj=True, noise_scale=0.1, inpainting=True,
+                       input_aatype=True, noise=g["noise"])
+    T, B, N = g["prot_traj"].shape[:3]
+    assert out["prot_traj"].shape == (T, B, N, 37, 3) and out["rigid_traj"].shape == (T + 1, B, N, 7)
+    assert out["trans_traj"].shape == (T, B, N, 3) and out["psi_pred"].shape == (1, B, N, 2) and out["rigid_0_traj"].shape == (T, B, N, 37, 3)
+    r = bb_rmsd(out["prot_traj"][0][:, :, :5], g["prot_traj"][0])
+    print(f"{name}: per-residue RMSD max {r.max():.3e} mean {r.mean():.3e}; reference 8-vs-1-thread floor {g['floor_8v1_final'].max():.3e}")
+    assert r.max() < 1e-3
+    assert np.all(out["prot_traj"][..., 5:, :] == 0)
+    # first reverse step (one forward) must agree tightly
+    r_first = bb_rmsd(out["prot_traj"][-1][:, :, :5], g["prot_traj"][-1])
+    assert r_first.max() < 2e-4
+    assert np.abs(out["trans_traj"][0] - g["trans_traj"][0]).max() < 1e-3
+    assert np.abs(out["rigid_traj"][-1] - g["rigid_traj"][-1]).max() == 0  # x_T passthrough
+
+
+def test_no_cpu_fallback(model):
+    m, _ = model
+    with pytest.raises(Exception):
+        m({"rigids_t": torch.zeros(1, 4, 7)})

@@ -1,0 +1,103 @@
+"""CPU tests: host logic, C-ABI exports, synthetic inputs, schedule."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from util import rot_angle_between
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fdpt.h")).read()
+    names = set(re.findall(r"\b(fdpt_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 15
+    lib_path = os.path.join(ROOT, "framedipt_b200", "libfdpt.so")
+    if not os.path.exists(lib_path):
+        import __graft_entry__ as ge
+        ge.build()
+    lib = ctypes.CDLL(lib_path)
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.fdpt_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.fdpt_version()
+
+
+def test_param_specs_match_reference_inventory():
+    from framedipt_b200.params import param_specs, synthetic_state_dict
+
+    sd = synthetic_state_dict(0)
+    assert sum(v.numel() for v in sd.values()) == 17_456_942
+    assert len(sd) == len(param_specs())
+    sd2 = synthetic_state_dict(0)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+
+
+def test_sample_ref_matches_reference(golden_dir):
+    from framedipt_b200 import SE3Diffuser, synthetic
+    from framedipt_b200.config import default_conf
+
+    g = np.load(os.path.join(golden_dir, "sample_ref.npz"))
+    diffuser = SE3Diffuser(default_conf().diffuser)
+    np.random.seed(123)
+    f = synthetic.make_features(synthetic.WORKLOADS["cfg1_monomer64"], diffuser, seed=0)
+    r, ref = f["rigids_t"].numpy(), g["inpaint_rigids_t"]
+    assert np.abs(r[..., 4:] - ref[..., 4:]).max() < 1e-5
+    assert rot_angle_between(r[..., :4], ref[..., :4]).max() < 1e-5
+    f2 = synthetic.make_features(synthetic.Workload("denovo32", 2, (32,), (), 10, de_novo=True), diffuser, seed=0)
+    r, ref = f2["rigids_t"].numpy(), g["denovo_rigids_t"]
+    assert np.abs(r[..., 4:] - ref[..., 4:]).max() < 1e-5
+    assert rot_angle_between(r[..., :4], ref[..., :4]).max() < 1e-5
+
+
+def test_schedule_matches_oracle():
+    from framedipt_b200 import SE3Diffuser
+    from framedipt_b200.config import default_conf
+    from oracle import framedipt_oracle as orc
+
+    d = SE3Diffuser(default_conf().diffuser)
+    for num_t in (50, 100, 500):
+        for t in np.linspace(0.01, 1.0, num_t):
+            row = d.step_scalars(float(t), 1 / num_t, 0.1)
+            assert row[1] == orc.sigma_grid_value(np.array(np.float32(t)))
+            g = orc.so3_diffusion_coef(t)
+            assert abs(row[2] - g * g / num_t) < 1e-15 and abs(row[4] - (0.1 + t * 19.9)) < 1e-15
+    with pytest.raises(ValueError):
+        d._so3_diffuser.sigma(1.5)
+
+
+def test_sample_ref_errors():
+    from framedipt_b200 import SE3Diffuser
+    from framedipt_b200.config import default_conf
+    from framedipt_b200.rigid import Rigid
+
+    d = SE3Diffuser(default_conf().diffuser)
+    with pytest.raises(ValueError):
+        d.sample_ref(n_samples=4, diffuse_mask=np.ones(4))
+    with pytest.raises(ValueError):
+        d.sample_ref(n_samples=4, impute=Rigid.identity((5,)), diffuse_mask=np.ones(4))
+
+
+def test_host_embeddings_match_oracle():
+    from framedipt_b200 import runtime
+    from oracle import framedipt_oracle as orc
+
+    idx = torch.tensor([[0, 1, 5, 230, 1023], [3, 7, 300, 500, 900]])
+    assert torch.equal(runtime.index_embedding(idx), orc.index_embedding(idx).float())
+    t = torch.tensor([0.01, 0.37, 1.0])
+    assert torch.equal(runtime.timestep_embedding(t), orc.timestep_embedding(t))
+
+
+def test_workloads_cover_baseline_configs():
+    from framedipt_b200 import synthetic
+
+    w = synthetic.WORKLOADS
+    assert w["cfg1_monomer64"].n_res == 64 and w["cfg2_tcr350"].n_res == 350 and w["cfg3_denovo256"].batch == 64
+    assert w["cfg4_tcrpmhc800"].n_res == 800 and w["cfg5_sweep1024"].n_res == 1024
+    st = synthetic.static_features(w["cfg2_tcr350"], 0)
+    assert st["seq_idx"][170] == 170 + 200  # RESIDUE_GAP between chains
+    assert st["fixed_mask"].sum() == 350 - 24

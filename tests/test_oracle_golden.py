@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from util import bb_rmsd, rot_angle_between
+
 from oracle import framedipt_oracle as orc
 
 
@@ -15,12 +17,6 @@ def _load(golden_dir, name):
 
 def _feats(g):
     return {k[3:]: torch.tensor(v) for k, v in g.items() if k.startswith("in_")}
-
-
-def rot_angle_between(q1, q2):
-    """Angle (rad) between rotations given as quaternions; sign-invariant."""
-    d = np.abs((q1 * q2).sum(-1)) / (np.linalg.norm(q1, axis=-1) * np.linalg.norm(q2, axis=-1))
-    return 2 * np.arccos(np.clip(d, 0, 1))
 
 
 @pytest.mark.parametrize("name", ["forward_small.npz", "forward_small_padded.npz"])
@@ -88,11 +84,6 @@ def test_sample_ref(golden_dir):
     ref = g["inpaint_rigids_t"][0]
     assert np.abs(r[:, 4:] - ref[:, 4:]).max() < 1e-5
     assert rot_angle_between(r[:, :4], ref[:, :4]).max() < 1e-3
-
-
-def bb_rmsd(a, b):
-    d = a[..., [0, 1, 2, 4], :] - b[..., [0, 1, 2, 4], :]
-    return np.sqrt((d ** 2).sum(-1).mean(-1))
 
 
 def test_trajectory_small(golden_dir, state_dict):
