@@ -16,6 +16,7 @@
 #include "kernels_diffusion.cuh"
 #include "kernels_ipa.cuh"
 #include "kernels_misc.cuh"
+#include "tc_linear.cuh"
 #include "backbone_tables.inc"
 
 using namespace fdpt;
@@ -78,6 +79,11 @@ struct fdpt_ctx {
   Workspace ws;
   int64_t launches = 0;
   int max_smem_optin = 0;
+  // live profiling (event pairs per slot)
+  bool prof_on = false;
+  struct ProfRec { cudaEvent_t a, b; int slot; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace {
@@ -103,6 +109,31 @@ int fail(fdpt_ctx* c, int code, const char* fmt, ...) {
     ctx->launches++;     \
     CK(cudaGetLastError()); \
   } while (0)
+
+cudaEvent_t prof_event(fdpt_ctx* c) {
+  if (!c->ev_pool.empty()) {
+    cudaEvent_t e = c->ev_pool.back();
+    c->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+// RAII scope: records an event pair around everything enqueued on `st` during its lifetime
+struct ProfScope {
+  fdpt_ctx* c; cudaStream_t st; int idx = -1;
+  ProfScope(fdpt_ctx* c_, int slot, cudaStream_t st_) : c(c_), st(st_) {
+    if (!c->prof_on) return;
+    fdpt_ctx::ProfRec r{prof_event(c), prof_event(c), slot};
+    cudaEventRecord(r.a, st);
+    c->prof.push_back(r);
+    idx = (int)c->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(c->prof[idx].b, st);
+  }
+};
 
 int f1_dim(const fdpt_ctx* c) { return c->cfg.with_aatype ? 54 : 33; }
 
@@ -236,6 +267,7 @@ int layernorm(fdpt_ctx* ctx, cudaStream_t st, const float* x, float* y, const fl
 
 // ---- embedder -------------------------------------------------------------------------------------------
 int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, float* z_out, cudaStream_t st) {
+  ProfScope ps(ctx, FDPT_PROF_EDGE_EMBED, st);
   Workspace& w = ctx->ws;
   const long long M = (long long)B * N, P = M * N;
   const int F1 = f1_dim(ctx), FN = F1 + EMB, EIN = 2 * F1 + EMB + NBINS;
@@ -272,6 +304,7 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
 // ---- IPA ---------------------------------------------------------------------------------------------------
 int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z, const float* quats, const float* trans,
             const float* mask, float* out, int ldo, const float* residual, const float* outmask, cudaStream_t st) {
+  ProfScope ps(ctx, FDPT_PROF_IPA_TOTAL, st);
   Workspace& w = ctx->ws;
   const BlockParams& p = ctx->blk[blk];
   const long long M = (long long)B * N;
@@ -297,6 +330,7 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z
     a.mask = mask; a.Wb = p.Wb; a.bb = p.bb; a.head_w = p.head_w; a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat;
     const size_t smem = ipa_core_smem_bytes(N);
     if ((int)smem > ctx->max_smem_optin) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs %zu B of shared memory in ipa_core", N, smem);
+    ProfScope pc(ctx, FDPT_PROF_IPA_CORE, st);
     ipa_core_kernel<<<dim3(N, B), 256, smem, st>>>(a);
     LAUNCH_CHECK();
   }
@@ -317,6 +351,7 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z
 // ---- edge transition -----------------------------------------------------------------------------------------
 int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* z_in, const float* mask, float* z_out,
                         cudaStream_t st) {
+  ProfScope ps(ctx, FDPT_PROF_EDGE_TRANSITION, st);
   Workspace& w = ctx->ws;
   const BlockParams& p = ctx->blk[blk];
   const long long M = (long long)B * N, P = M * N;
@@ -353,6 +388,7 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
 
 // ---- sequence transformer (post-norm encoder, ipa_pytorch.py:433-443, 533-539) ------------------------------------
 int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaStream_t st) {
+  ProfScope ps(ctx, FDPT_PROF_SEQ_TFMR, st);
   Workspace& w = ctx->ws;
   const BlockParams& p = ctx->blk[blk];
   const long long M = (long long)B * N;
@@ -403,6 +439,7 @@ int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_o
   if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
   if (B <= 0 || N <= 0) return fail(ctx, FDPT_ERR_INVALID, "bad B=%d N=%d", B, N);
   RET(reserve_ws(ctx, B, N));
+  ProfScope pfwd(ctx, FDPT_PROF_FORWARD, st);
   Workspace& w = ctx->ws;
   const long long M = (long long)B * N;
   Lin lin{ctx, st};
@@ -616,6 +653,36 @@ int fdpt_reserve(fdpt_ctx* ctx, int B, int N) {
   return reserve_ws(ctx, B, N);
 }
 
+int fdpt_profile_enable(fdpt_ctx* ctx, int on) {
+  if (!ctx) return FDPT_ERR_INVALID;
+  ctx->prof_on = on != 0;
+  return FDPT_OK;
+}
+
+int fdpt_profile_read(fdpt_ctx* ctx, int slot, int* count, double* total_ms) {
+  if (!ctx || !count || !total_ms || slot < 0 || slot >= FDPT_PROF_SLOTS) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CK(cudaDeviceSynchronize());
+  *count = 0;
+  *total_ms = 0.0;
+  std::vector<fdpt_ctx::ProfRec> keep;
+  for (auto& r : ctx->prof) {
+    if (r.slot != slot) {
+      keep.push_back(r);
+      continue;
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      *total_ms += ms;
+      (*count)++;
+    }
+    ctx->ev_pool.push_back(r.a);
+    ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.swap(keep);
+  return FDPT_OK;
+}
+
 int64_t fdpt_workspace_bytes(const fdpt_ctx* ctx) { return ctx ? (int64_t)ctx->ws.bytes : 0; }
 int64_t fdpt_launch_count(const fdpt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -677,7 +744,7 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
                 const double* noise, int self_condition, int center, int diffuse_rot, int diffuse_trans, const fdpt_traj* out,
                 void* stream) {
   if (!ctx || !feats || !sched || !t_emb_tab || !out || num_t <= 0 || num_t > 4096) return FDPT_ERR_INVALID;
-  if (num_t > 1 && !noise) return FDPT_ERR_INVALID;
+  if (num_t > 1 && !noise) return FDPT_ERR_INVALID;  /* noise rows are indexed by step: every step whose IS_LAST flag is 0 reads row s */
   cudaSetDevice(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   RET(reserve_ws(ctx, B, N));
@@ -708,7 +775,7 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
   }
   const int32_t* aat = ctx->cfg.with_aatype ? feats->aatype : nullptr;
   for (int s = 0; s < T; ++s) {
-    const bool last = sched[s * FDPT_SCHED_COLS + FDPT_SCHED_SPARE] != 0.0;  // !(t > min_t)
+    const bool last = sched[s * FDPT_SCHED_COLS + FDPT_SCHED_IS_LAST] != 0.0;  // !(t > min_t)
     RET(set_step(s));
     RET(forward_impl(ctx, B, N, &f, &o, st));
     if (!last) {
@@ -751,6 +818,26 @@ int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float*
   cudaSetDevice(ctx->device);
   Lin lin{ctx, (cudaStream_t)stream};
   return lin(x, K, w, K, bias, y, N, M, N, K, act);
+}
+
+int fdpt_tc_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act, float* y,
+                   void* stream) {
+  if (!ctx || !x || !w || !y || M <= 0 || N % 128 || K % 64 || K > 512 || K <= 0 || N <= 0) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  __half* img = nullptr;
+  CK(cudaMalloc(&img, (size_t)N * K * sizeof(__half)));
+  const long long chunks = (long long)N * (K / 8);
+  tc::pack_weight_image_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(w, K, N, K, K, img);
+  LAUNCH_CHECK();
+  tc::TcLinearArgs a{x, K, M, K, img, N, bias, act, y, N};
+  const size_t smem = tc::tc_linear_smem_bytes(K);
+  CK(cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::tc_linear_kernel<<<(M + 127) / 128, 192, smem, st>>>(a);
+  LAUNCH_CHECK();
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(img));
+  return FDPT_OK;
 }
 
 int fdpt_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z, const float* quats, const float* trans,

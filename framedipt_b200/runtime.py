@@ -88,8 +88,11 @@ def lib() -> C.CDLL:
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_Traj), C.c_void_p]
         L.fdpt_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_void_p]
+        L.fdpt_tc_linear.argtypes = L.fdpt_linear.argtypes
         L.fdpt_ipa.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.fdpt_edge_transition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.fdpt_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.fdpt_profile_read.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.fdpt_embed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_Feats), C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -197,6 +200,20 @@ class Context:
     def workspace_bytes(self) -> int:
         return int(lib().fdpt_workspace_bytes(self._h))
 
+    PROF_SLOTS = {"ipa_core": 0, "edge_transition": 1, "edge_embed": 2, "ipa_total": 3, "seq_tfmr": 4, "forward": 5}
+
+    def profile_enable(self, on: bool = True):
+        self._ck(lib().fdpt_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict[str, tuple[int, float]]:
+        """{slot: (launch count, total ms)} measured with CUDA events on the launching stream; clears the records."""
+        out = {}
+        for name, slot in self.PROF_SLOTS.items():
+            n, ms = C.c_int(0), C.c_double(0.0)
+            self._ck(lib().fdpt_profile_read(self._h, slot, C.byref(n), C.byref(ms)))
+            out[name] = (n.value, ms.value)
+        return out
+
     # ---- parameters
     def load_state_dict(self, sd: dict, strict: bool = True):
         expected = {k for k, _, _ in param_specs(self.dims, self.with_aatype)}
@@ -253,7 +270,9 @@ class Context:
                    _ptr(out["psi_pred"]), int(final_only))
         t_emb_tab = t_emb_tab.to(dev, torch.float32).contiguous()
         if noise is not None:
-            assert noise.dtype == torch.float64 and noise.is_cuda and tuple(noise.shape) == (T - 1, 2, B, N, 3), (noise.shape, noise.dtype)
+            n_rev = int((sched[:, 7] == 0).sum())
+            assert noise.dtype == torch.float64 and noise.is_cuda and noise.shape[0] >= max(n_rev, T - 1) and \
+                tuple(noise.shape[1:]) == (2, B, N, 3), (noise.shape, noise.dtype)
         fs = pf.struct()
         self._ck(lib().fdpt_sample(self._h, B, N, C.byref(fs), T, sched.ctypes.data_as(C.POINTER(C.c_double)), _ptr(t_emb_tab),
                                    _ptr(noise), int(self_condition), int(center), int(diffuse_rot), int(diffuse_trans), C.byref(tr),
@@ -267,6 +286,13 @@ class Context:
         Nn = w.shape[0]
         y = torch.empty(M, Nn, device=self.device)
         self._ck(lib().fdpt_linear(self._h, M, Nn, K, _ptr(x), _ptr(w), _ptr(b), act, _ptr(y), self.stream))
+        return y
+
+    def tc_linear(self, x, w, b, act=0):
+        M, K = x.shape
+        Nn = w.shape[0]
+        y = torch.empty(M, Nn, device=self.device)
+        self._ck(lib().fdpt_tc_linear(self._h, M, Nn, K, _ptr(x), _ptr(w), _ptr(b), act, _ptr(y), self.stream))
         return y
 
     def ipa(self, blk, s, z, quats, trans, mask):

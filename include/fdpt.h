@@ -56,7 +56,7 @@ enum {
   FDPT_SCHED_R3_BT = 4,      /* b_t */
   FDPT_SCHED_DT = 5,         /* dt */
   FDPT_SCHED_R3_NOISE = 6,   /* sqrt(b_t) * sqrt(dt) * noise_scale */
-  FDPT_SCHED_SPARE = 7,
+  FDPT_SCHED_IS_LAST = 7,    /* 1.0 when !(t > min_t): take the x0 prediction instead of a reverse step */
   FDPT_SCHED_COLS = 8
 };
 
@@ -151,10 +151,29 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
 /* number of kernel launches enqueued by this context since creation (bench.py's gpu_launches) */
 int64_t fdpt_launch_count(const fdpt_ctx* ctx);
 
+/* Live per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+ * When enabled, every launch of the listed kernels / kernel groups inside fdpt_forward / fdpt_sample is bracketed
+ * by an event pair; fdpt_profile_read synchronises the device, sums the elapsed times per slot and clears them. */
+enum {
+  FDPT_PROF_IPA_CORE = 0,         /* ipa_core kernel alone (the HBM-bound point-attention kernel) */
+  FDPT_PROF_EDGE_TRANSITION = 1,  /* whole EdgeTransition (all its kernels) */
+  FDPT_PROF_EDGE_EMBED = 2,       /* whole Embedder */
+  FDPT_PROF_IPA_TOTAL = 3,        /* whole IPA incl. projections and linear_out */
+  FDPT_PROF_SEQ_TFMR = 4,
+  FDPT_PROF_FORWARD = 5,          /* whole forward */
+  FDPT_PROF_SLOTS = 8
+};
+int fdpt_profile_enable(fdpt_ctx* ctx, int on);
+int fdpt_profile_read(fdpt_ctx* ctx, int slot, int* count, double* total_ms);
+
 /* ---- unit entry points (parity tests per kernel; same kernels the hot path launches) ---------- */
 /* y[M,N] = act(x[M,K] @ w[N,K]^T + bias) ; act: 0 none, 1 relu */
 int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act,
                 float* y, void* stream);
+/* same contract on the tcgen05 tensor cores (fp16 operands, fp32 accumulate): K multiple of 64 (<= 512), N multiple of 128.
+ * Bring-up / unit entry of the building blocks the fused pair-side kernels use. */
+int fdpt_tc_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act,
+                   float* y, void* stream);
 /* InvariantPointAttention.forward (ipa_pytorch.py:170-329) of block `blk` on given s [B,N,c_s], z [B,N,N,c_z],
  * frames (quats [B,N,4], trans in 0.1 A units [B,N,3]), mask [B,N] -> out [B,N,c_s] (linear_out applied, not masked) */
 int fdpt_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z, const float* quats,

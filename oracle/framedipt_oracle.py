@@ -303,6 +303,34 @@ def rot_score(quats_t, quats_0, t):
     return sc[..., None] * v / omega[..., None]
 
 
+def rot_score_conditioning(quats_t, quats_0, t):
+    """Conditioning probe for tests.  The reference evaluates sin/cos((l+1/2) omega) of its 1000-term IGSO(3) series
+    in float32 (arguments up to ~3000 rad), so each term carries ~1e-7 relative noise that depends on the libm used.
+    Where the series cancels massively (omega >> sigma: the density is negligible; omega -> 0 or pi) the reference's
+    own value is dominated by that noise and two equally valid libm implementations disagree.  Returns, per element,
+    the expected libm-noise level of the score MAGNITUDE: 1.2e-7 * (sum|terms_df| / |f + 1e-4| + |df| sum|terms_f| / (f+1e-4)^2)
+    and the magnitude itself."""
+    q0 = quats_0.clone()
+    q0[..., 1:] *= -1
+    q0 = q0 / (quats_0 ** 2).sum(-1, keepdim=True)
+    v = quat_to_rotvec(quat_multiply(q0, quats_t))
+    omega = (torch.linalg.norm(v, dim=-1) + 1e-6).numpy().astype(np.float64)
+    sig = sigma_grid_value(t.cpu().numpy())[:, None]
+    l = np.arange(1000)
+    lh = l + 0.5
+    arg = omega[..., None] * lh
+    coef = (2 * l + 1) * np.exp(-l * (l + 1) * sig[..., None] ** 2 / 2)
+    hi, c = np.sin(arg), np.cos(arg)
+    lo, dlo = np.sin(omega / 2)[..., None], 0.5 * np.cos(omega / 2)[..., None]
+    tf = coef * hi / lo
+    tdf_abs = coef * (np.abs(lo * lh * c) + np.abs(hi * dlo)) / lo ** 2  # magnitudes of the two cancelling products
+    tdf = coef * (lo * lh * c - hi * dlo) / lo ** 2
+    f, df = tf.sum(-1), tdf.sum(-1)
+    den = np.abs(f + 1e-4)
+    noise = 1.2e-7 * (tdf_abs.sum(-1) / den + np.abs(df) * np.abs(tf).sum(-1) / den ** 2)
+    return noise, np.abs(df / (f + 1e-4))
+
+
 def marginal_b_t(t):
     """r3_diffuser.py:87-96."""
     return t * MIN_B + 0.5 * (t ** 2) * (MAX_B - MIN_B)
