@@ -146,7 +146,7 @@ def main():
     cores = os.cpu_count() or 1
     config = {"workload": f"{wl.name}: B={wl.batch}/GPU, N_res={wl.n_res}, schedule num_t={wl.num_t}, inpainting={not wl.de_novo}",
               "batch_per_gpu": wl.batch, "n_res": wl.n_res, "parallelism": f"sample-parallel x{args.gpus}",
-              "l2_policy": f"inputs larger than L2: pair representation z = {wl.batch * wl.n_res ** 2 * 512 / 1e6:.0f} MB per forward pass"}
+              "l2_policy": f"inputs larger than L2: pair representation z (fp16) = {wl.batch * wl.n_res ** 2 * 256 / 1e6:.0f} MB, streamed 11x per forward"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -276,7 +276,8 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         n_ipa, ms_ipa = prof["ipa_core"]
-        ipa_bytes = B * (512 * N * N + 38064 * N)  # z read once + per-residue q/k/v/points + concat, fp32
+        # SURVEY §8d with z stored as fp16 (256 B/pair): z read once + per-residue q/k/v/points + concat (fp32)
+        ipa_bytes = B * (256 * N * N + 38064 * N)
         ipa_s = ms_ipa * 1e-3 / max(n_ipa, 1)
         n_et, ms_et = prof["edge_transition"]
         et_flops = 688128.0 * B * N * N  # 2*MACs as the reference computes them
@@ -288,7 +289,7 @@ def main():
                     "frac": ipa_bytes / ipa_s / 1e9 / peaks["hbm_gbs"], "traffic": None, "launches": n_ipa, "avg_ms": ipa_s * 1e3,
                     "share_of_forward": shares["ipa_core"], "peak_source": peaks["source"]}
         tpeak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        roof_et = {"kernel": "edge_transition (gemm_simt chain)", "bound": "tensor", "achieved": et_flops / et_s / 1e12, "peak": tpeak,
+        roof_et = {"kernel": "et_fused_kernel (+ per-residue prologue GEMMs)", "bound": "tensor", "achieved": et_flops / et_s / 1e12, "peak": tpeak,
                    "unit": "TFLOP/s", "frac": et_flops / et_s / 1e12 / tpeak, "traffic": None, "launches": n_et, "avg_ms": et_s * 1e3,
                    "share_of_forward": shares["edge_transition"], "peak_source": peaks["source"] + " (sustained bf16)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,

@@ -1,0 +1,429 @@
+// et_fused.cuh — EdgeTransition (ipa_pytorch.py:61-102) as ONE persistent tcgen05 kernel.
+//
+//   x = [z_ij | n_i | n_j] (384);  y = relu(W2 relu(W1 x + b1) + b2) + x;  z' = LN(Wf y + bf) * m_i m_j
+//
+// Per 128-pair tile (fixed b, i; 128 consecutive j) the three GEMMs are chained through TMEM/shared memory; only z is
+// read (fp16 tile image, 32 KB) and written (32 KB) in HBM.  The n_i terms are per-residue and enter as epilogue
+// vectors (U_i = W1[:,128:256] n_i + b1, Pf_i = Wf[:,128:256] n_i + bf); the n_j terms enter as two extra k-blocks of
+// the A operand (a per-(b, j-block) fp16 image shared by all i).  The residual Wf x is folded into GEMM 3.
+//
+//   GEMM1  D1[128 x 384] = [z | n_j] (K=256) . W1cat^T          W1cat = [W1[:, 0:128] | W1[:, 256:384]]
+//   E1     h1 = relu(D1 + U_i)                      -> fp16, 128-column chunks in shared memory
+//   GEMM2  D2[128 x 384] += h1_chunk(c) . W2[:, chunk c]^T       (accumulated over the three K chunks as they appear)
+//   E2     r2 = relu(D2 + b2)                       -> fp16 chunks
+//   GEMM3  D3[128 x 128] = [z | n_j] . W3cat[:, 384:640]^T + sum_c r2_chunk(c) . W3cat[:, chunk c]^T
+//                                                     W3cat = [Wf | Wf[:, 0:128] | Wf[:, 256:384]]
+//   E3     z' = LN(D3 + Pf_i) * mask                -> fp16 tile image, bulk store
+//
+// TMEM: columns [0,384) = D2, [384,512) = D1 chunk stage / D3.   Shared memory (224 KB): A0z x2 (64 KB, bulk-copied,
+// double buffered across tiles), A0n (32 KB), two 32 KB chunk buffers (h1 / r2 / output staging), 4-stage weight ring.
+// Warps 0-3: epilogue workers (thread <-> tile row <-> TMEM lane); warp 4: MMA issuer + TMEM owner; warp 5: loader.
+// All operands fp16 (10-bit mantissa = TF32 precision, which the pair side tolerates: SURVEY §7 hard part 1), fp32 accumulate.
+#pragma once
+#include "tc_common.cuh"
+
+namespace fdpt {
+namespace tc {
+
+constexpr int ET_TILE_BYTES = 32768;    // 128 rows x 128 halfs (two k-blocks)
+constexpr int ET_WSTAGES = 3;
+constexpr int ET_STAGE_BYTES = 16384;   // 128 weight rows x one k-block
+
+struct EtArgs {
+  int B, N, JB;                 // JB = ceil(N/128) j-blocks
+  const __half* z_in;           // tile images [B][N][JB][32 KB]
+  __half* z_out;                // may alias z_in
+  const __half* n_img;          // [B][JB][32 KB] images of n_emb rows (zero padded)
+  const float* Ui;              // [B*N, 384]
+  const float* Pf;              // [B*N, 128]
+  const float* b2;              // [384]
+  const float* ln_g; const float* ln_b;  // [128]
+  const float* mask;            // [B*N]
+  const __half* W1cat;          // image [4 kb][384][128 B]
+  const __half* W2;             // image [6 kb][384][128 B]
+  const __half* W3cat;          // image [10 kb][128][128 B]
+  long long tiles;              // B*N*JB
+};
+
+struct EtPhase {  // phase counters of one role
+  uint32_t w = 0, az[2] = {0, 0}, an = 0, ds_full = 0, ds_empty = 0, buf_full[2] = {0, 0}, buf_free[2] = {0, 0}, d2_full = 0, d2_empty = 0;
+};
+
+__global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* A0z = smem;                                 // 2 x 32 KB
+  uint8_t* A0n = A0z + 2 * ET_TILE_BYTES;              // 32 KB
+  uint8_t* BUF = A0n + ET_TILE_BYTES;                  // 2 x 32 KB
+  uint8_t* WST = BUF + 2 * ET_TILE_BYTES;              // ET_WSTAGES x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(WST + ET_WSTAGES * ET_STAGE_BYTES);
+  uint64_t* w_full = bars;                   // [ET_WSTAGES]
+  uint64_t* w_empty = w_full + ET_WSTAGES;   // [4]
+  uint64_t* az_full = w_empty + ET_WSTAGES;  // [2]
+  uint64_t* az_empty = az_full + 2;          // [2]
+  uint64_t* an_full = az_empty + 2;          // [1]
+  uint64_t* ds_full = an_full + 1;           // [1]
+  uint64_t* ds_empty = ds_full + 1;          // [1]
+  uint64_t* buf_full = ds_empty + 1;         // [2]
+  uint64_t* buf_free = buf_full + 2;         // [2]
+  uint64_t* d2_full = buf_free + 2;          // [1]
+  uint64_t* d2_empty = d2_full + 1;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
+  float* Ui_s = reinterpret_cast<float*>(tmem_slot + 4);  // [384]
+  float* Pf_s = Ui_s + 384;                                // [128]
+  float* b2_s = Pf_s + 128;                                // [384]
+  float* g_s = b2_s + 384;                                 // [128]
+  float* be_s = g_s + 128;                                 // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long per = (a.tiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * per;
+  const long long t_end = min(a.tiles, t_begin + per);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ET_WSTAGES; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&az_full[s], 1);
+      mbar_init(&az_empty[s], 1);
+      mbar_init(&buf_full[s], 128);
+      mbar_init(&buf_free[s], 1);
+    }
+    mbar_init(an_full, 1);
+    mbar_init(ds_full, 1);
+    mbar_init(ds_empty, 128);
+    mbar_init(d2_full, 1);
+    mbar_init(d2_empty, 128);
+    fence_barrier_init();
+  }
+  for (int k = threadIdx.x; k < 384; k += blockDim.x) b2_s[k] = a.b2[k];
+  for (int k = threadIdx.x; k < 128; k += blockDim.x) {
+    g_s[k] = a.ln_g[k];
+    be_s[k] = a.ln_b[k];
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t D2 = tmem_base, DS = tmem_base + 384;
+
+  // tile -> (b*N+i, jb); the n_j image changes when (b, jb) changes. Tiles are ordered (b, jb, i) with i fastest.
+  auto tile_bjb = [&](long long t) -> long long { return t / a.N; };          // b*JB + jb
+  auto tile_m = [&](long long t, int& jb) -> long long {                      // returns b*N + i
+    const long long bjb = t / a.N;
+    const int i = (int)(t - bjb * a.N);
+    const long long b = bjb / a.JB;
+    jb = (int)(bjb - b * a.JB);
+    return b * a.N + i;
+  };
+
+  if (warp == 5) {
+    // ============================ loader ============================
+    if (lane == 0 && t_begin < t_end) {
+      uint32_t wit = 0;      // weight stage counter
+      auto load_z = [&](long long t) {
+        const int s = (int)((t - t_begin) & 1);
+        const uint32_t use = (uint32_t)((t - t_begin) >> 1);
+        mbar_wait(&az_empty[s], (use & 1) ^ 1);
+        mbar_arrive_expect_tx(&az_full[s], ET_TILE_BYTES);
+        int jb;
+        const long long m = tile_m(t, jb);
+        bulk_g2s(A0z + s * ET_TILE_BYTES, reinterpret_cast<const uint8_t*>(a.z_in) + ((m * a.JB + jb) * (long long)ET_TILE_BYTES), ET_TILE_BYTES,
+                 &az_full[s]);
+      };
+      auto load_n = [&](long long t) {
+        mbar_arrive_expect_tx(an_full, ET_TILE_BYTES);
+        bulk_g2s(A0n, reinterpret_cast<const uint8_t*>(a.n_img) + tile_bjb(t) * (long long)ET_TILE_BYTES, ET_TILE_BYTES, an_full);
+      };
+      auto stage = [&](const __half* img, int rows_total, int row0, int kb) {
+        const int s = wit % ET_WSTAGES;
+        mbar_wait(&w_empty[s], ((wit / ET_WSTAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&w_full[s], ET_STAGE_BYTES);
+        bulk_g2s(WST + s * ET_STAGE_BYTES, reinterpret_cast<const uint8_t*>(img) + ((size_t)kb * rows_total + row0) * 128, ET_STAGE_BYTES,
+                 &w_full[s]);
+        ++wit;
+      };
+      load_z(t_begin);
+      load_n(t_begin);
+      for (long long t = t_begin; t < t_end; ++t) {
+        // weight stream in the exact order the MMA warp consumes it
+        for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 0, kb);                                   // G1(0)
+        for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 128, kb);                                 // G1(1)
+        if (t + 1 < t_end) load_z(t + 1);                                                            // prefetch next z tile
+        for (int n = 0; n < 3; ++n) for (int kb = 0; kb < 2; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(0)
+        for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 256, kb);                                 // G1(2)
+        for (int n = 0; n < 3; ++n) for (int kb = 2; kb < 4; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(1)
+        for (int n = 0; n < 3; ++n) for (int kb = 4; kb < 6; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(2)
+        for (int kb = 6; kb < 10; ++kb) stage(a.W3cat, 128, 0, kb);                                  // G3 static ([z | n_j])
+        for (int kb = 0; kb < 6; ++kb) stage(a.W3cat, 128, 0, kb);                                   // G3 partials
+        if (t + 1 < t_end && tile_bjb(t + 1) != tile_bjb(t)) {
+          // the n_j image changes: wait until tile t's last reader (G3 static) has completed
+          const int s = (int)((t - t_begin) & 1);
+          const uint32_t use = (uint32_t)((t - t_begin) >> 1);
+          mbar_wait(&az_empty[s], use & 1);
+          load_n(t + 1);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 128);
+      uint32_t wit = 0, ds_e = 0, bf[2] = {0, 0}, d2_e = 0, an_f = 0;
+      auto gemm_kb = [&](uint32_t a_addr, uint32_t d_col, bool first_acc) {
+        // one k-block: wait the weight stage, 4 x (128x128x16) MMAs, release the stage
+        const int s = wit % ET_WSTAGES;
+        mbar_wait(&w_full[s], (wit / ET_WSTAGES) & 1);
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(WST + s * ET_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(d_col, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc, (first_acc && k == 0) ? 0u : 1u);
+        umma_commit(&w_empty[s]);
+        ++wit;
+      };
+      for (long long t = t_begin; t < t_end; ++t) {
+        const int zs = (int)((t - t_begin) & 1);
+        const uint32_t zuse = (uint32_t)((t - t_begin) >> 1);
+        mbar_wait(&az_full[zs], zuse & 1);
+        if (t == t_begin || tile_bjb(t) != tile_bjb(t - 1)) {
+          mbar_wait(an_full, an_f & 1);
+          ++an_f;
+        }
+        tc_fence_after();
+        const uint32_t az = smem_u32(A0z + zs * ET_TILE_BYTES), an = smem_u32(A0n);
+        const uint32_t bufa[2] = {smem_u32(BUF), smem_u32(BUF + ET_TILE_BYTES)};
+        auto a0_kb = [&](int kb) { return kb < 2 ? az + kb * 16384 : an + (kb - 2) * 16384; };
+        auto G1 = [&](int c) {
+          (void)c;
+          mbar_wait(ds_empty, (ds_e & 1) ^ 1);
+          ++ds_e;
+          tc_fence_after();
+          for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
+          umma_commit(ds_full);
+        };
+        auto G2 = [&](int c) {
+          const int b = c & 1;
+          mbar_wait(&buf_full[b], bf[b] & 1);
+          ++bf[b];
+          if (c == 0) {
+            mbar_wait(d2_empty, (d2_e & 1) ^ 1);
+            ++d2_e;
+          }
+          tc_fence_after();
+          for (int n = 0; n < 3; ++n)
+            for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, D2 + n * 128, c == 0 && kb == 0);
+          umma_commit(&buf_free[b]);
+          if (c == 2) umma_commit(d2_full);
+        };
+        G1(0);
+        G1(1);
+        G2(0);
+        G1(2);
+        G2(1);
+        G2(2);
+        // G3 static part: [z | n_j] . W3cat[:, 384:640]^T  -> DS (after E1(2) has drained it)
+        mbar_wait(ds_empty, (ds_e & 1) ^ 1);
+        ++ds_e;
+        tc_fence_after();
+        for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
+        umma_commit(&az_empty[zs]);
+        for (int c = 0; c < 3; ++c) {
+          const int b = c & 1;
+          mbar_wait(&buf_full[b], bf[b] & 1);
+          ++bf[b];
+          tc_fence_after();
+          for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, DS, false);
+          umma_commit(&buf_free[b]);
+        }
+        umma_commit(ds_full);
+      }
+    }
+  } else {
+    // ============================ epilogue workers (128 threads) ============================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t ds_f = 0, fr[2] = {0, 0}, d2_f = 0;
+    auto wait_free = [&](int b) {
+      mbar_wait(&buf_free[b], (fr[b] & 1) ^ 1);
+      ++fr[b];
+    };
+    // relu(v + add) -> fp16 -> swizzled chunk buffer row `row` (two k-blocks x 8 chunks)
+    auto store_chunk = [&](uint8_t* buf, const float* v /*[128]*/) {
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float* p = v + kb * 64 + c * 8;
+          const uint4 u = make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
+          *reinterpret_cast<uint4*>(buf + kb * 16384 + sw128_chunk_off(row, c)) = u;
+        }
+      }
+    };
+    for (long long t = t_begin; t < t_end; ++t) {
+      int jb;
+      const long long m = tile_m(t, jb);
+      const int j = jb * 128 + row;
+      // per-tile epilogue vectors (same i for the whole tile)
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of Ui_s/Pf_s are done
+      for (int k = threadIdx.x; k < 384; k += 128) Ui_s[k] = a.Ui[m * 384 + k];
+      Pf_s[threadIdx.x] = a.Pf[m * 128 + threadIdx.x];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float v[128];
+      // ---- E1: three chunks of h1
+      for (int c = 0; c < 3; ++c) {
+        mbar_wait(ds_full, ds_f & 1);
+        ++ds_f;
+        tc_fence_after();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld32(DS + lane_base + q * 32, v + q * 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(ds_empty);
+#pragma unroll
+        for (int n = 0; n < 128; ++n) v[n] = fmaxf(v[n] + Ui_s[c * 128 + n], 0.f);
+        wait_free(c & 1);
+        store_chunk(BUF + (c & 1) * ET_TILE_BYTES, v);
+        fence_proxy_async();
+        mbar_arrive(&buf_full[c & 1]);
+      }
+      // ---- E2: three chunks of r2
+      mbar_wait(d2_full, d2_f & 1);
+      ++d2_f;
+      tc_fence_after();
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld32(D2 + lane_base + c * 128 + q * 32, v + q * 32);
+        tmem_ld_wait();
+        if (c == 2) {
+          tc_fence_before();
+          mbar_arrive(d2_empty);
+        }
+#pragma unroll
+        for (int n = 0; n < 128; ++n) v[n] = fmaxf(v[n] + b2_s[c * 128 + n], 0.f);
+        wait_free(c & 1);
+        store_chunk(BUF + (c & 1) * ET_TILE_BYTES, v);
+        fence_proxy_async();
+        mbar_arrive(&buf_full[c & 1]);
+      }
+      // ---- E3: LayerNorm + mask -> fp16 tile image -> bulk store
+      mbar_wait(ds_full, ds_f & 1);
+      ++ds_f;
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tmem_ld32(DS + lane_base + q * 32, v + q * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(ds_empty);
+      float s = 0.f;
+#pragma unroll
+      for (int n = 0; n < 128; ++n) {
+        v[n] += Pf_s[n];
+        s += v[n];
+      }
+      const float mean = s * (1.f / 128.f);
+      float q2 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 128; ++n) {
+        const float d = v[n] - mean;
+        q2 += d * d;
+      }
+      const float rstd = rsqrtf(q2 * (1.f / 128.f) + 1e-5f);
+      float mk = 0.f;
+      if (j < a.N) mk = a.mask[m] * a.mask[(m / a.N) * a.N + j];
+#pragma unroll
+      for (int n = 0; n < 128; ++n) v[n] = ((v[n] - mean) * rstd * g_s[n] + be_s[n]) * mk;
+      wait_free(0);
+      store_chunk(BUF, v);
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * (long long)ET_TILE_BYTES);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(BUF)), "r"(ET_TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&buf_free[0]);
+      }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+inline size_t et_smem_bytes() {
+  return 1024 + 5 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 32 * 8 + 16 + (384 + 128 + 384 + 128 + 128) * 4 + 64;
+}
+
+// ---- layout helpers --------------------------------------------------------------------------------------------------
+// fp32 z[B,N,N,128] -> fp16 tile images [B][N][JB][2 kb][128 rows][128 B swizzled]; rows j >= N are zero.
+__global__ void z_to_image_kernel(int B, int N, int JB, const float* __restrict__ z, __half* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk
+  const long long total = (long long)B * N * JB * 128 * 16;
+  if (idx >= total) return;
+  const int kc = (int)(idx & 15);
+  const int r = (int)((idx >> 4) & 127);
+  const long long tile = idx >> 11;
+  const int jb = (int)(tile % JB);
+  const long long m = tile / JB;
+  const int j = jb * 128 + r;
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (j < N) {
+    const float4* src = reinterpret_cast<const float4*>(z + (m * N + j) * 128 + kc * 8);
+    const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
+    u = make_uint4(pack_half2(x0.x, x0.y), pack_half2(x0.z, x0.w), pack_half2(x1.x, x1.y), pack_half2(x1.z, x1.w));
+  }
+  uint8_t* dst = reinterpret_cast<uint8_t*>(img) + tile * ET_TILE_BYTES + (kc >> 3) * 16384 + sw128_chunk_off(r, kc & 7);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+
+__global__ void image_to_z_kernel(int B, int N, int JB, const __half* __restrict__ img, float* __restrict__ z) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * N * JB * 128 * 16;
+  if (idx >= total) return;
+  const int kc = (int)(idx & 15);
+  const int r = (int)((idx >> 4) & 127);
+  const long long tile = idx >> 11;
+  const int jb = (int)(tile % JB);
+  const long long m = tile / JB;
+  const int j = jb * 128 + r;
+  if (j >= N) return;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(img) + tile * ET_TILE_BYTES + (kc >> 3) * 16384 + sw128_chunk_off(r, kc & 7);
+  const uint4 u = *reinterpret_cast<const uint4*>(src);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  float* dst = z + (m * N + j) * 128 + kc * 8;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h[e]);
+    dst[2 * e] = f.x;
+    dst[2 * e + 1] = f.y;
+  }
+}
+
+// n_emb [B*N,128] fp32 -> per-(b, j-block) fp16 images [B][JB][2 kb][128 rows][128 B]
+__global__ void n_to_image_kernel(int B, int N, int JB, const float* __restrict__ n_emb, __half* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * JB * 128 * 16;
+  if (idx >= total) return;
+  const int kc = (int)(idx & 15);
+  const int r = (int)((idx >> 4) & 127);
+  const long long tile = idx >> 11;  // b*JB + jb
+  const int jb = (int)(tile % JB);
+  const long long b = tile / JB;
+  const int j = jb * 128 + r;
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (j < N) {
+    const float4* src = reinterpret_cast<const float4*>(n_emb + (b * N + j) * 128 + kc * 8);
+    const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
+    u = make_uint4(pack_half2(x0.x, x0.y), pack_half2(x0.z, x0.w), pack_half2(x1.x, x1.y), pack_half2(x1.z, x1.w));
+  }
+  uint8_t* dst = reinterpret_cast<uint8_t*>(img) + tile * ET_TILE_BYTES + (kc >> 3) * 16384 + sw128_chunk_off(r, kc & 7);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+
+}  // namespace tc
+}  // namespace fdpt

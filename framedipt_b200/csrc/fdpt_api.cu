@@ -16,6 +16,7 @@
 #include "kernels_diffusion.cuh"
 #include "kernels_ipa.cuh"
 #include "kernels_misc.cuh"
+#include "et_fused.cuh"
 #include "tc_linear.cuh"
 #include "backbone_tables.inc"
 
@@ -39,6 +40,8 @@ struct BlockParams {
   const float *Wbb, *bbb;
   // edge transition (blocks 0..2)
   const float *Wie, *bie, *We1, *be1, *We2, *be2, *Wef, *bef, *eln_g, *eln_b;
+  // fp16 128B-swizzled weight images for the fused tcgen05 EdgeTransition kernel (et_fused.cuh)
+  __half *imgW1cat = nullptr, *imgW2 = nullptr, *imgW3cat = nullptr;
 };
 
 struct Workspace {
@@ -55,7 +58,9 @@ struct Workspace {
   float *n_emb, *U, *V, *Pf, *Qf;
   float *tors_u;
   // pair side
-  float *z, *S, *h1, *h2, *ho;
+  float *zf32, *S, *h1, *h2, *ho;  // zf32: fp32 [P,128] scratch used only by the unit entry points
+  __half *z, *n_img;               // z: fp16 tile images [B][N][JB][32 KB]; n_img: [B][JB][32 KB]
+  int JB;
   // outputs / sampling state
   float *pred_rigids, *trans_score, *psi, *rig_cur, *rig_next, *sc_ca, *t_emb_b, *t32_b, *bb_tmp;
   double *rot_score, *sigma_b, *sched_dev;
@@ -78,7 +83,7 @@ struct fdpt_ctx {
   float *bin_lower = nullptr, *ideal = nullptr, *psi_frame = nullptr, *atom_mask = nullptr;
   Workspace ws;
   int64_t launches = 0;
-  int max_smem_optin = 0;
+  int max_smem_optin = 0, num_sms = 148;
   // live profiling (event pairs per slot)
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int slot; };
@@ -197,7 +202,7 @@ T* carve(char*& p, size_t n) {
 
 int reserve_ws(fdpt_ctx* ctx, int B, int N) {
   Workspace& w = ctx->ws;
-  if (w.base && B <= w.capB && N <= w.capN && (long long)B * N <= (long long)w.capB * w.capN) return FDPT_OK;
+  if (w.base && B <= w.capB && N == w.capN) return FDPT_OK;  // tile-image layout (and its zero padding) is per N
   CK(cudaDeviceSynchronize());
   if (w.base) CK(cudaFree(w.base));
   w = Workspace();
@@ -218,7 +223,9 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.upd = carve<float>(p, M * 8); w.quats = carve<float>(p, M * 4); w.trans = carve<float>(p, M * 4); w.dmask = carve<float>(p, M);
     w.n_emb = carve<float>(p, M * C_Z); w.U = carve<float>(p, M * ET_HID); w.V = carve<float>(p, M * ET_HID);
     w.Pf = carve<float>(p, M * C_Z); w.Qf = carve<float>(p, M * C_Z); w.tors_u = carve<float>(p, M * 2);
-    w.z = carve<float>(p, P * C_Z); w.S = carve<float>(p, P * NH);
+    const size_t JB = (size_t)(N + 127) / 128;
+    w.z = carve<__half>(p, M * JB * 16384); w.n_img = carve<__half>(p, (size_t)B * JB * 16384);
+    w.zf32 = nullptr; w.S = carve<float>(p, P * NH);
     w.h1 = carve<float>(p, (size_t)chunk * ET_HID); w.h2 = carve<float>(p, (size_t)chunk * ET_HID); w.ho = carve<float>(p, (size_t)chunk * C_Z);
     w.pred_rigids = carve<float>(p, M * 7); w.trans_score = carve<float>(p, M * 3); w.psi = carve<float>(p, M * 2);
     w.rig_cur = carve<float>(p, M * 7); w.rig_next = carve<float>(p, M * 7); w.sc_ca = carve<float>(p, M * 3);
@@ -229,7 +236,8 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
       CK(cudaMalloc(&w.base, w.bytes));
     }
   }
-  w.capB = B; w.capN = N; w.pair_chunk = chunk;
+  w.capB = B; w.capN = N; w.pair_chunk = chunk; w.JB = (N + 127) / 128;
+  CK(cudaMemset(w.z, 0, sizeof(__half) * M * w.JB * 16384));  // padded rows (j >= N) of the tile images stay zero
   return FDPT_OK;
 }
 
@@ -266,7 +274,7 @@ int layernorm(fdpt_ctx* ctx, cudaStream_t st, const float* x, float* y, const fl
 }
 
 // ---- embedder -------------------------------------------------------------------------------------------
-int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, float* z_out, cudaStream_t st) {
+int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, __half* z_out, cudaStream_t st) {
   ProfScope ps(ctx, FDPT_PROF_EDGE_EMBED, st);
   Workspace& w = ctx->ws;
   const long long M = (long long)B * N, P = M * N;
@@ -296,13 +304,14 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
     LAUNCH_CHECK();
     RET(lin(w.h1, C_Z, T.eW2, C_Z, T.eb2, w.h2, C_Z, rows, C_Z, C_Z, 1));
     RET(lin(w.h2, C_Z, T.eW4, C_Z, T.eb4, w.ho, C_Z, rows, C_Z, C_Z, 0));
-    RET(layernorm<C_Z>(ctx, st, w.ho, z_out + r0 * C_Z, T.eln_g, T.eln_b, rows, nullptr, in->res_mask, N, r0));
+    pair_ln_image_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.ho, z_out, T.eln_g, T.eln_b, rows, in->res_mask, N, w.JB, r0);
+    LAUNCH_CHECK();
   }
   return FDPT_OK;
 }
 
 // ---- IPA ---------------------------------------------------------------------------------------------------
-int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z, const float* quats, const float* trans,
+int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* z, const float* quats, const float* trans,
             const float* mask, float* out, int ldo, const float* residual, const float* outmask, cudaStream_t st) {
   ProfScope ps(ctx, FDPT_PROF_IPA_TOTAL, st);
   Workspace& w = ctx->ws;
@@ -326,7 +335,7 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z
   }
   {
     IpaCoreArgs a;
-    a.B = B; a.N = N; a.S = w.S; a.z = z; a.q_pts = w.q_pts; a.k_pts = w.k_pts; a.v_pts = w.v_pts; a.quats = quats; a.trans = trans;
+    a.B = B; a.N = N; a.S = w.S; a.z = z; a.JB = w.JB; a.q_pts = w.q_pts; a.k_pts = w.k_pts; a.v_pts = w.v_pts; a.quats = quats; a.trans = trans;
     a.mask = mask; a.Wb = p.Wb; a.bb = p.bb; a.head_w = p.head_w; a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat;
     const size_t smem = ipa_core_smem_bytes(N);
     if ((int)smem > ctx->max_smem_optin) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs %zu B of shared memory in ipa_core", N, smem);
@@ -348,41 +357,30 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z
   return FDPT_OK;
 }
 
-// ---- edge transition -----------------------------------------------------------------------------------------
-int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* z_in, const float* mask, float* z_out,
+// ---- edge transition (fused tcgen05 kernel, et_fused.cuh) ------------------------------------------------------
+int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const __half* z_in, const float* mask, __half* z_out,
                         cudaStream_t st) {
   ProfScope ps(ctx, FDPT_PROF_EDGE_TRANSITION, st);
   Workspace& w = ctx->ws;
   const BlockParams& p = ctx->blk[blk];
-  const long long M = (long long)B * N, P = M * N;
+  const long long M = (long long)B * N;
   Lin lin{ctx, st};
+  // per-residue parts: n = initial_embed(node); U_i = W1[:,128:256] n_i + b1; Pf_i = Wf[:,128:256] n_i + bf
   RET(lin(node, C_S, p.Wie, C_S, p.bie, w.n_emb, C_Z, M, C_Z, C_S));
-  // x = [z | n_i | n_j]; trunk.0 and final_layer are split column-wise so the node parts are per-residue
   RET(lin(w.n_emb, C_Z, p.We1 + C_Z, ET_HID, p.be1, w.U, ET_HID, M, ET_HID, C_Z));
-  RET(lin(w.n_emb, C_Z, p.We1 + 2 * C_Z, ET_HID, nullptr, w.V, ET_HID, M, ET_HID, C_Z));
   RET(lin(w.n_emb, C_Z, p.Wef + C_Z, ET_HID, p.bef, w.Pf, C_Z, M, C_Z, C_Z));
-  RET(lin(w.n_emb, C_Z, p.Wef + 2 * C_Z, ET_HID, nullptr, w.Qf, C_Z, M, C_Z, C_Z));
-  for (long long r0 = 0; r0 < P; r0 += w.pair_chunk) {
-    const long long rows = std::min<long long>(w.pair_chunk, P - r0);
-    const float* zc = z_in + r0 * C_Z;
-    {  // h1 = relu(W1z z + U_i + V_j)
-      GemmArgs g;
-      g.A = zc; g.lda = C_Z; g.B = p.We1; g.ldb = ET_HID; g.C = w.h1; g.ldc = ET_HID; g.M = (int)rows; g.N = ET_HID; g.K = C_Z;
-      g.U = w.U; g.V = w.V; g.lduv = ET_HID; g.nres = N; g.row0 = r0; g.relu = 1;
-      CK(launch_gemm(g, true, 1, st));
-      ctx->launches++;
-    }
-    RET(lin(w.h1, ET_HID, p.We2, ET_HID, p.be2, w.h2, ET_HID, rows, ET_HID, ET_HID, 1));
-    {  // o = Wf r2 + P_i + Q_j  (+ Wf[:, :128] z below)
-      GemmArgs g;
-      g.A = w.h2; g.lda = ET_HID; g.B = p.Wef; g.ldb = ET_HID; g.C = w.ho; g.ldc = C_Z; g.M = (int)rows; g.N = C_Z; g.K = ET_HID;
-      g.U = w.Pf; g.V = w.Qf; g.lduv = C_Z; g.nres = N; g.row0 = r0;
-      CK(launch_gemm(g, true, 1, st));
-      ctx->launches++;
-    }
-    RET(lin(zc, C_Z, p.Wef, ET_HID, nullptr, w.ho, C_Z, rows, C_Z, C_Z, 0, nullptr, 0, nullptr, 1));
-    RET(layernorm<C_Z>(ctx, st, w.ho, z_out + r0 * C_Z, p.eln_g, p.eln_b, rows, nullptr, mask, N, r0));
+  {
+    const long long chunks = (long long)B * w.JB * 128 * 16;
+    tc::n_to_image_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(B, N, w.JB, w.n_emb, w.n_img);
+    LAUNCH_CHECK();
   }
+  tc::EtArgs a;
+  a.B = B; a.N = N; a.JB = w.JB; a.z_in = z_in; a.z_out = z_out; a.n_img = w.n_img; a.Ui = w.U; a.Pf = w.Pf; a.b2 = p.be2;
+  a.ln_g = p.eln_g; a.ln_b = p.eln_b; a.mask = mask; a.W1cat = p.imgW1cat; a.W2 = p.imgW2; a.W3cat = p.imgW3cat;
+  a.tiles = M * w.JB;
+  const int grid = (int)std::min<long long>(ctx->num_sms, a.tiles);
+  tc::et_fused_kernel<<<grid, 192, tc::et_smem_bytes(), st>>>(a);
+  LAUNCH_CHECK();
   return FDPT_OK;
 }
 
@@ -493,6 +491,20 @@ int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_o
   return FDPT_OK;
 }
 
+// fp32 [B,N,N,128] <-> fp16 tile images (unit entry points only; the hot path keeps z in image form)
+int z_fp32_to_image(fdpt_ctx* ctx, int B, int N, const float* z, cudaStream_t st) {
+  const long long chunks = (long long)B * N * ctx->ws.JB * 128 * 16;
+  tc::z_to_image_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(B, N, ctx->ws.JB, z, ctx->ws.z);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+int z_image_to_fp32(fdpt_ctx* ctx, int B, int N, float* z, cudaStream_t st) {
+  const long long chunks = (long long)B * N * ctx->ws.JB * 128 * 16;
+  tc::image_to_z_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(B, N, ctx->ws.JB, ctx->ws.z, z);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+
 __global__ void set_step_kernel(int B, int step, const float* __restrict__ t_emb_tab, const double* __restrict__ sched,
                                 float* __restrict__ t_emb_b, float* __restrict__ t32_b, double* __restrict__ sigma_b) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,7 +545,10 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   ctx->cfg = *cfg;
   ctx->device = device;
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
   cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::et_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et_smem_bytes());
+  cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::tc_linear_smem_bytes(512));
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
   float lower[NBINS];
   {
@@ -561,6 +576,11 @@ int fdpt_destroy(fdpt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (auto& kv : ctx->params) cudaFree(kv.second.dev);
+  for (auto& b : ctx->blk) {
+    cudaFree(b.imgW1cat);
+    cudaFree(b.imgW2);
+    cudaFree(b.imgW3cat);
+  }
   cudaFree(ctx->ws.base);
   cudaFree(ctx->bin_lower);
   cudaFree(ctx->ideal);
@@ -641,8 +661,25 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
       p.We1 = P(et + ".trunk.0.weight"); p.be1 = P(et + ".trunk.0.bias"); p.We2 = P(et + ".trunk.2.weight"); p.be2 = P(et + ".trunk.2.bias");
       p.Wef = P(et + ".final_layer.weight"); p.bef = P(et + ".final_layer.bias");
       p.eln_g = P(et + ".layer_norm.weight"); p.eln_b = P(et + ".layer_norm.bias");
+      // fp16 swizzled images: W1cat = [W1[:,0:128] | W1[:,256:384]] (384 x 256), W2 (384 x 384),
+      // W3cat = [Wf | Wf[:,0:128] | Wf[:,256:384]] (128 x 640); image layout [k-block][rows][128 B]
+      if (!p.imgW1cat) CK(cudaMalloc(&p.imgW1cat, sizeof(__half) * ET_HID * 256));
+      if (!p.imgW2) CK(cudaMalloc(&p.imgW2, sizeof(__half) * ET_HID * ET_HID));
+      if (!p.imgW3cat) CK(cudaMalloc(&p.imgW3cat, sizeof(__half) * C_Z * 640));
+      auto pack = [&](const float* W, int ldw, int Nrows, int K, __half* img_kb0) {
+        const long long chunks = (long long)Nrows * (K / 8);
+        tc::pack_weight_image_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(W, ldw, Nrows, K, K, img_kb0);
+      };
+      pack(p.We1, ET_HID, ET_HID, 128, p.imgW1cat);
+      pack(p.We1 + 2 * C_Z, ET_HID, ET_HID, 128, p.imgW1cat + (size_t)2 * ET_HID * 64);
+      pack(p.We2, ET_HID, ET_HID, ET_HID, p.imgW2);
+      pack(p.Wef, ET_HID, C_Z, ET_HID, p.imgW3cat);
+      pack(p.Wef, ET_HID, C_Z, 128, p.imgW3cat + (size_t)6 * C_Z * 64);
+      pack(p.Wef + 2 * C_Z, ET_HID, C_Z, 128, p.imgW3cat + (size_t)8 * C_Z * 64);
+      CK(cudaGetLastError());
     }
   }
+  CK(cudaDeviceSynchronize());
   ctx->finalized = true;
   return FDPT_OK;
 }
@@ -846,7 +883,8 @@ int fdpt_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* 
   if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
   cudaSetDevice(ctx->device);
   RET(reserve_ws(ctx, B, N));
-  return run_ipa(ctx, blk, B, N, s, z, quats, trans, mask, out, C_S, nullptr, nullptr, (cudaStream_t)stream);
+  RET(z_fp32_to_image(ctx, B, N, z, (cudaStream_t)stream));
+  return run_ipa(ctx, blk, B, N, s, ctx->ws.z, quats, trans, mask, out, C_S, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int fdpt_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* z_in, const float* mask, float* z_out,
@@ -855,7 +893,9 @@ int fdpt_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node
   if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
   cudaSetDevice(ctx->device);
   RET(reserve_ws(ctx, B, N));
-  return run_edge_transition(ctx, blk, B, N, node, z_in, mask, z_out, (cudaStream_t)stream);
+  RET(z_fp32_to_image(ctx, B, N, z_in, (cudaStream_t)stream));
+  RET(run_edge_transition(ctx, blk, B, N, node, ctx->ws.z, mask, ctx->ws.z, (cudaStream_t)stream));
+  return z_image_to_fp32(ctx, B, N, z_out, (cudaStream_t)stream);
 }
 
 int fdpt_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, float* edge_out, void* stream) {
@@ -863,7 +903,8 @@ int fdpt_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_ou
   if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
   cudaSetDevice(ctx->device);
   RET(reserve_ws(ctx, B, N));
-  return run_embed(ctx, B, N, in, node_out, edge_out, (cudaStream_t)stream);
+  RET(run_embed(ctx, B, N, in, node_out, ctx->ws.z, (cudaStream_t)stream));
+  return z_image_to_fp32(ctx, B, N, edge_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

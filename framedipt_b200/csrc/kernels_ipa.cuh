@@ -14,6 +14,8 @@
 // z[b,i,:,:] (N x 512 B, contiguous) is streamed from HBM once per (b,i); the second use (o_pair) re-reads it
 // while it is still L2 resident.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace fdpt {
@@ -57,7 +59,8 @@ __global__ void ipa_points_kernel(int M, const float* __restrict__ qp_raw, const
 struct IpaCoreArgs {
   int B, N;
   float* S;                 // [B,H,N,N] in: q.k ; out: attention probabilities
-  const float* z;           // [B,N,N,128]
+  const __half* z;          // fp16 tile images [B][N][JB][2 k-blocks][128 rows][128 B, 128B-swizzled] (et_fused.cuh)
+  int JB;
   const float* q_pts;       // [B,N,H,PQ,3]
   const float* k_pts;       // [B,N,H,PQ,3]
   const float* v_pts;       // [B,N,H,PV,3]
@@ -98,17 +101,29 @@ __global__ void __launch_bounds__(256) ipa_core_kernel(IpaCoreArgs a) {
   const float s_qk = sqrtf(1.0f / (3.f * C_HID)), s_b = sqrtf(1.0f / 3.f);
   const float bbh = a.bb[h];
   float* Srow = a.S + (((long long)b * NH + h) * N + i) * N;
-  const float* zrow = a.z + m * (long long)N * C_Z;
+  const uint8_t* zrow = reinterpret_cast<const uint8_t*>(a.z) + (size_t)m * a.JB * 32768;
   __syncthreads();
 
   // ---- pass 1: logits -------------------------------------------------------------------------
   for (int j0 = 0; j0 < N; j0 += IPA_JC) {
     const int nj = min(IPA_JC, N - j0);
-    for (int k = tid; k < IPA_JC * (C_Z / 4); k += 256) {
-      const int jj = k / (C_Z / 4), c4 = k % (C_Z / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (jj < nj) v = *reinterpret_cast<const float4*>(zrow + (long long)(j0 + jj) * C_Z + c4 * 4);
-      *reinterpret_cast<float4*>(zt + jj * IPA_ZLD + c4 * 4) = v;
+    for (int k = tid; k < IPA_JC * (C_Z / 8); k += 256) {  // one 16-byte chunk (8 halfs) per iteration
+      const int jj = k / (C_Z / 8), kc = k % (C_Z / 8);
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (jj < nj) {
+        const int j = j0 + jj, r = j & 127;
+        const uint8_t* src = zrow + (size_t)(j >> 7) * 32768 + (kc >> 3) * 16384 + r * 128 + (((kc & 7) ^ (r & 7)) << 4);
+        const uint4 u = *reinterpret_cast<const uint4*>(src);
+        const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t2 = __half22float2(hh[e]);
+          f[2 * e] = t2.x;
+          f[2 * e + 1] = t2.y;
+        }
+      }
+      *reinterpret_cast<float4*>(zt + jj * IPA_ZLD + kc * 8) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(zt + jj * IPA_ZLD + kc * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
     }
     const float* kpg = a.k_pts + ((long long)b * N + j0) * (NH * PQ * 3);
     for (int k = tid; k < IPA_JC * NH * PQ * 3; k += 256) {
@@ -173,11 +188,23 @@ __global__ void __launch_bounds__(256) ipa_core_kernel(IpaCoreArgs a) {
   for (int k = 0; k < PV * 3; ++k) pt[k] = 0.f;
   for (int j0 = 0; j0 < N; j0 += IPA_JC) {
     const int nj = min(IPA_JC, N - j0);
-    for (int k = tid; k < IPA_JC * (C_Z / 4); k += 256) {
-      const int jj = k / (C_Z / 4), c4 = k % (C_Z / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (jj < nj) v = *reinterpret_cast<const float4*>(zrow + (long long)(j0 + jj) * C_Z + c4 * 4);
-      *reinterpret_cast<float4*>(zt + jj * IPA_ZLD + c4 * 4) = v;
+    for (int k = tid; k < IPA_JC * (C_Z / 8); k += 256) {  // one 16-byte chunk (8 halfs) per iteration
+      const int jj = k / (C_Z / 8), kc = k % (C_Z / 8);
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (jj < nj) {
+        const int j = j0 + jj, r = j & 127;
+        const uint8_t* src = zrow + (size_t)(j >> 7) * 32768 + (kc >> 3) * 16384 + r * 128 + (((kc & 7) ^ (r & 7)) << 4);
+        const uint4 u = *reinterpret_cast<const uint4*>(src);
+        const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t2 = __half22float2(hh[e]);
+          f[2 * e] = t2.x;
+          f[2 * e + 1] = t2.y;
+        }
+      }
+      *reinterpret_cast<float4*>(zt + jj * IPA_ZLD + kc * 8) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(zt + jj * IPA_ZLD + kc * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
     }
     __syncthreads();
     for (int jj = 0; jj < nj; ++jj) {

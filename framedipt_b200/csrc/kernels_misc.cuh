@@ -1,5 +1,7 @@
 // kernels_misc.cuh — LayerNorm, feature building, frame algebra, small elementwise kernels.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace fdpt {
@@ -50,6 +52,45 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, float* y
     const int c = lane + 32 * i;
     yr[c] = ((v[i] - mean) * rstd * gamma[c] + beta[c]) * m;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pair LayerNorm (C = 128) writing the fp16 tile-image layout of z used by the tcgen05 pair kernels (et_fused.cuh):
+//   image[(b*N+i)][jb][k-block][row j%128][128 B swizzled];  y = LN(x) * gamma + beta, times m[b,i] m[b,j].
+// One warp per pair row; lane covers channels 4*lane .. 4*lane+3.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pair_ln_image_kernel(const float* __restrict__ x, __half* __restrict__ img,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            long long rows, const float* __restrict__ mask, int nres, int JB,
+                                                            long long row0) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4 v4 = *reinterpret_cast<const float4*>(x + row * C_Z + lane * 4);
+  float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.f / C_Z);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C_Z) + 1e-5f);
+  const long long p = row0 + row;
+  const long long nn = (long long)nres * nres;
+  const long long b = p / nn;
+  const int rem = (int)(p - b * nn);
+  const int i = rem / nres, j = rem - i * nres;
+  const float m = mask[b * nres + i] * mask[b * nres + j];
+  const float4 g4 = *reinterpret_cast<const float4*>(gamma + lane * 4);
+  const float4 b4 = *reinterpret_cast<const float4*>(beta + lane * 4);
+  const float o0 = ((v[0] - mean) * rstd * g4.x + b4.x) * m, o1 = ((v[1] - mean) * rstd * g4.y + b4.y) * m;
+  const float o2 = ((v[2] - mean) * rstd * g4.z + b4.z) * m, o3 = ((v[3] - mean) * rstd * g4.w + b4.w) * m;
+  const __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
+  const int c = lane * 4, r = j & 127;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(img) + ((b * nres + i) * (long long)JB + (j >> 7)) * 32768 + (c >> 6) * 16384 + r * 128 +
+                 ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2;
+  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -80,7 +80,9 @@ def test_embed_ipa_edge_kernels(golden_dir, model, ctx, name):
     valid = g["in_res_mask"].astype(bool)
     em = valid[:, :, None] & valid[:, None, :]
     assert np.abs(node.cpu().numpy() - g["tap_node_embed_raw"])[valid].max() < 2e-4
-    assert np.abs(edge.cpu().numpy() - g["tap_edge_embed_raw"])[em].max() < 5e-4
+    # z is stored as fp16 (10-bit mantissa, |z| <~ 11 after LayerNorm): storage rounding <= 2^-11 relative
+    e_ref = g["tap_edge_embed_raw"]
+    assert (np.abs(edge.cpu().numpy() - e_ref)[em] <= 5e-4 + 6e-4 * np.abs(e_ref)[em]).all()
     assert np.all(edge.cpu().numpy()[~em] == 0)
     # IPA block 0 on the reference's own inputs
     mask = torch.tensor(g["in_res_mask"], dtype=torch.float32).cuda()
@@ -93,7 +95,11 @@ def test_embed_ipa_edge_kernels(golden_dir, model, ctx, name):
     # edge transition block 0
     node_in = torch.tensor(g["tap_node_transition_0"]).cuda() * mask[..., None]
     zo = ctx.edge_transition(0, node_in.contiguous(), z.contiguous(), mask.contiguous())
-    assert np.abs(zo.cpu().numpy() - g["tap_edge_transition_0"])[em].max() < 1e-3
+    # fused tcgen05 EdgeTransition: fp16 operands (TF32-class mantissa), fp32 accumulation, fp16 storage of z
+    z_ref = g["tap_edge_transition_0"]
+    err = np.abs(zo.cpu().numpy() - z_ref)[em]
+    assert err.max() < 2e-2 and err.mean() < 2e-3, (err.max(), err.mean())
+    assert np.all(zo.cpu().numpy()[~em] == 0)
 
 
 @pytest.mark.parametrize("name", ["forward_small.npz", "forward_small_padded.npz"])
