@@ -183,16 +183,11 @@ def main():
     # weights: rank 0 owns them, NCCL broadcast of the packed blob over NVLink (C1 in SURVEY §7)
     sd = synthetic_state_dict(0, with_aatype=not wl.de_novo)
     if world > 1:
-        keys = sorted(sd)
-        blob = torch.cat([sd[k].reshape(-1) for k in keys]).to(dev)
+        from framedipt_b200 import sharding
+
         if rank != 0:
-            blob.zero_()
-        dist.broadcast(blob, 0)
-        off = 0
-        for k in keys:
-            n = sd[k].numel()
-            sd[k] = blob[off:off + n].reshape(sd[k].shape).cpu()
-            off += n
+            sd = {k: torch.zeros_like(v) for k, v in sd.items()}
+        sd = sharding.broadcast_state_dict(sd, dist, 0, dev)
     model.load_state_dict(sd)
     model = model.to(dev).eval()
     ctx = model.context(dev)
@@ -266,9 +261,10 @@ def main():
     if dist is not None:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
         # final gather of the finished samples' coordinates (C2 in SURVEY §7), outside the step loop
-        fin = o2["prot_traj"][0].contiguous()
-        gathered = [torch.empty_like(fin) for _ in range(world)] if rank == 0 else None
-        dist.gather(fin, gathered, dst=0)
+        from framedipt_b200 import sharding
+
+        gathered = sharding.gather_samples(o2["prot_traj"][0].contiguous(), dist, 0)
+        assert rank != 0 or gathered.shape[0] == world * B
     e2e_value = world * B * N * K / float(t_all.item())
     h2d = int(2 * B * N * 3 * 8)
     d2h = int(B * N * (15 + 15 + 7 + 3) * 4)
