@@ -18,6 +18,7 @@
 #include "kernels_misc.cuh"
 #include "et_fused.cuh"
 #include "tc_linear.cuh"
+#include "gemm_tc.cuh"
 #include "backbone_tables.inc"
 
 using namespace fdpt;
@@ -42,6 +43,10 @@ struct BlockParams {
   const float *Wie, *bie, *We1, *be1, *We2, *be2, *Wef, *bef, *eln_g, *eln_b;
   // fp16 128B-swizzled weight images for the fused tcgen05 EdgeTransition kernel (et_fused.cuh)
   __half *imgW1cat = nullptr, *imgW2 = nullptr, *imgW3cat = nullptr;
+  // IPA (kernels_ipa.cuh): fused projection weight [6816,256] / bias with per-head contiguous rows, linear_out.weight with columns
+  // in cat' order, fp16 hi|lo operand image of linear_b.weight
+  float *Wcat = nullptr, *bcat = nullptr, *Wout_perm = nullptr;
+  __half* imgWb = nullptr;
 };
 
 struct Workspace {
@@ -52,7 +57,8 @@ struct Workspace {
   // node side
   float *node_feat, *feat1d, *node0, *node, *tmpA, *tmpB, *tmpC;  // tmp: [M,320]-capable
   float *PA, *PB, *RelProj;
-  float *q, *kv, *qp_raw, *kvp_raw, *q_pts, *k_pts, *v_pts, *cat;
+  float *proj, *kn, *cat;  // IPA: fused projections [M,6816], -gamma/2 |k_pts|^2 [M,8], concat [M,2688]
+  int ldS;
   float *tf_x, *qkv, *att_o;
   float *upd, *quats, *trans, *dmask;
   float *n_emb, *U, *V, *Pf, *Qf;
@@ -84,6 +90,8 @@ struct fdpt_ctx {
   Workspace ws;
   int64_t launches = 0;
   int max_smem_optin = 0, num_sms = 148;
+  int gemm_tc = 1;   // node-side GEMMs on tcgen05 (3-term split TF32); 0 = SIMT fp32 kernel (bring-up / A-B switch)
+  int mn_swap = 0;   // bring-up knob of the MN-major descriptor
   // live profiling (event pairs per slot)
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int slot; };
@@ -101,6 +109,11 @@ int fail(fdpt_ctx* c, int code, const char* fmt, ...) {
   va_end(ap);
   if (c) c->err = buf;
   return code;
+}
+
+cudaError_t gemm_dispatch(fdpt_ctx* c, const GemmArgs& g, bool b_kmajor, int batch, cudaStream_t st) {
+  if (c->gemm_tc) return tc::launch_gemm_tc(g, b_kmajor, batch, st, c->num_sms, c->mn_swap);
+  return launch_gemm(g, b_kmajor, batch, st);
 }
 
 #define CK(call)                                                                                                   \
@@ -192,6 +205,66 @@ bool is_unused_key(const std::string& k) {
   return k.find(".linear_rbf.") != std::string::npos || k.find("torsion_pred.linear_3.") != std::string::npos;
 }
 
+// One-time repack of the IPA parameters of a block (host side; kernels_ipa.cuh header describes the layouts).
+int pack_ipa_params(fdpt_ctx* ctx, BlockParams& p) {
+  std::vector<float> Wq((size_t)NH * C_HID * C_S), bq(NH * C_HID), Wkv((size_t)2 * NH * C_HID * C_S), bkv(2 * NH * C_HID);
+  std::vector<float> Wqp((size_t)NH * PQ * 3 * C_S), bqp(NH * PQ * 3), Wkvp((size_t)NH * (PQ + PV) * 3 * C_S), bkvp(NH * (PQ + PV) * 3);
+  std::vector<float> Wout((size_t)C_S * CAT), Wb((size_t)NH * C_Z);
+  auto d2h = [&](std::vector<float>& h, const float* d) { return cudaMemcpy(h.data(), d, h.size() * sizeof(float), cudaMemcpyDeviceToHost); };
+  CK(d2h(Wq, p.Wq)); CK(d2h(bq, p.bq)); CK(d2h(Wkv, p.Wkv)); CK(d2h(bkv, p.bkv)); CK(d2h(Wqp, p.Wqp)); CK(d2h(bqp, p.bqp));
+  CK(d2h(Wkvp, p.Wkvp)); CK(d2h(bkvp, p.bkvp)); CK(d2h(Wout, p.Wout)); CK(d2h(Wb, p.Wb));
+  std::vector<float> Wcat((size_t)PROJ_W * C_S), bcat(PROJ_W), Wop((size_t)C_S * CAT);
+  auto put = [&](int dst_row, const std::vector<float>& W, const std::vector<float>& b, int src_row) {
+    memcpy(&Wcat[(size_t)dst_row * C_S], &W[(size_t)src_row * C_S], C_S * sizeof(float));
+    bcat[dst_row] = b[src_row];
+  };
+  const int NKV = PQ + PV;
+  for (int h = 0; h < NH; ++h) {
+    for (int c = 0; c < C_HID; ++c) {
+      put(PROJ_Q + h * QK_W + c, Wq, bq, h * C_HID + c);                 // linear_q: [H, C] (ipa_pytorch.py:201-204)
+      put(PROJ_K + h * QK_W + c, Wkv, bkv, h * 2 * C_HID + c);           // linear_kv: [H, 2C], k = first C (208-211)
+      put(PROJ_V + h * V_W + c, Wkv, bkv, h * 2 * C_HID + C_HID + c);
+    }
+    for (int ax = 0; ax < 3; ++ax) {  // points: output split in 3 chunks x | y | z, each [H, P] (214-239)
+      for (int q = 0; q < PQ; ++q) {
+        put(PROJ_Q + h * QK_W + C_HID + ax * PQ + q, Wqp, bqp, ax * NH * PQ + h * PQ + q);
+        put(PROJ_K + h * QK_W + C_HID + ax * PQ + q, Wkvp, bkvp, ax * NH * NKV + h * NKV + q);
+      }
+      for (int q = 0; q < PV; ++q) put(PROJ_V + h * V_W + C_HID + ax * PV + q, Wkvp, bkvp, ax * NH * NKV + h * NKV + PQ + q);
+    }
+  }
+  // linear_out columns: reference concat [o (H*C) | o_pt x | y | z (H*PV each) | norms | o_pair]  ->  cat' order
+  std::vector<int> src_col(CAT);
+  for (int h = 0; h < NH; ++h) {
+    for (int c = 0; c < C_HID; ++c) src_col[h * V_W + c] = h * C_HID + c;
+    for (int ax = 0; ax < 3; ++ax)
+      for (int q = 0; q < PV; ++q) src_col[h * V_W + C_HID + ax * PV + q] = CAT_OPT + ax * NH * PV + h * PV + q;
+  }
+  for (int k = CATP_NRM; k < CAT; ++k) src_col[k] = k;  // norms and o_pair keep their places
+  for (int n = 0; n < C_S; ++n)
+    for (int k = 0; k < CAT; ++k) Wop[(size_t)n * CAT + k] = Wout[(size_t)n * CAT + src_col[k]];
+  // linear_b operand image: [2 k-blocks][16 rows][128 B swizzled]; rows 0-7 = fp16(W_b), rows 8-15 = fp16(W_b - fp16(W_b))
+  std::vector<__half> img(2 * 16 * 64);
+  for (int kb = 0; kb < 2; ++kb)
+    for (int n = 0; n < 16; ++n)
+      for (int c = 0; c < 8; ++c)
+        for (int e = 0; e < 8; ++e) {
+          const float wv = Wb[(size_t)(n & 7) * C_Z + kb * 64 + c * 8 + e];
+          const __half hi = __float2half_rn(wv);
+          const __half v = n < 8 ? hi : __float2half_rn(wv - __half2float(hi));
+          img[(size_t)kb * 1024 + n * 64 + ((c ^ (n & 7)) << 3) + e] = v;
+        }
+  if (!p.Wcat) CK(cudaMalloc(&p.Wcat, Wcat.size() * sizeof(float)));
+  if (!p.bcat) CK(cudaMalloc(&p.bcat, bcat.size() * sizeof(float)));
+  if (!p.Wout_perm) CK(cudaMalloc(&p.Wout_perm, Wop.size() * sizeof(float)));
+  if (!p.imgWb) CK(cudaMalloc(&p.imgWb, img.size() * sizeof(__half)));
+  CK(cudaMemcpy(p.Wcat, Wcat.data(), Wcat.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p.bcat, bcat.data(), bcat.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p.Wout_perm, Wop.data(), Wop.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p.imgWb, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return FDPT_OK;
+}
+
 // ---- workspace ---------------------------------------------------------------------------------------
 template <typename T>
 T* carve(char*& p, size_t n) {
@@ -215,9 +288,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.node0 = carve<float>(p, M * C_S); w.node = carve<float>(p, M * C_S);
     w.tmpA = carve<float>(p, M * ET_HID); w.tmpB = carve<float>(p, M * ET_HID); w.tmpC = carve<float>(p, M * ET_HID);
     w.PA = carve<float>(p, M * C_Z); w.PB = carve<float>(p, M * C_Z); w.RelProj = carve<float>(p, (size_t)R * C_Z);
-    w.q = carve<float>(p, M * NH * C_HID); w.kv = carve<float>(p, M * 2 * NH * C_HID);
-    w.qp_raw = carve<float>(p, M * NH * PQ * 3); w.kvp_raw = carve<float>(p, M * NH * (PQ + PV) * 3);
-    w.q_pts = carve<float>(p, M * NH * PQ * 3); w.k_pts = carve<float>(p, M * NH * PQ * 3); w.v_pts = carve<float>(p, M * NH * PV * 3);
+    w.proj = carve<float>(p, M * PROJ_W); w.kn = carve<float>(p, M * NH);
     w.cat = carve<float>(p, M * CAT);
     w.tf_x = carve<float>(p, M * TF_D); w.qkv = carve<float>(p, M * 3 * TF_D); w.att_o = carve<float>(p, M * TF_D);
     w.upd = carve<float>(p, M * 8); w.quats = carve<float>(p, M * 4); w.trans = carve<float>(p, M * 4); w.dmask = carve<float>(p, M);
@@ -225,7 +296,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.Pf = carve<float>(p, M * C_Z); w.Qf = carve<float>(p, M * C_Z); w.tors_u = carve<float>(p, M * 2);
     const size_t JB = (size_t)(N + 127) / 128;
     w.z = carve<__half>(p, M * JB * 16384); w.n_img = carve<__half>(p, (size_t)B * JB * 16384);
-    w.zf32 = nullptr; w.S = carve<float>(p, P * NH);
+    w.zf32 = nullptr; w.S = carve<float>(p, M * NH * (size_t)((N + 3) & ~3));
     w.h1 = carve<float>(p, (size_t)chunk * ET_HID); w.h2 = carve<float>(p, (size_t)chunk * ET_HID); w.ho = carve<float>(p, (size_t)chunk * C_Z);
     w.pred_rigids = carve<float>(p, M * 7); w.trans_score = carve<float>(p, M * 3); w.psi = carve<float>(p, M * 2);
     w.rig_cur = carve<float>(p, M * 7); w.rig_next = carve<float>(p, M * 7); w.sc_ca = carve<float>(p, M * 3);
@@ -236,7 +307,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
       CK(cudaMalloc(&w.base, w.bytes));
     }
   }
-  w.capB = B; w.capN = N; w.pair_chunk = chunk; w.JB = (N + 127) / 128;
+  w.capB = B; w.capN = N; w.pair_chunk = chunk; w.JB = (N + 127) / 128; w.ldS = (N + 3) & ~3;
   CK(cudaMemset(w.z, 0, sizeof(__half) * M * w.JB * 16384));  // padded rows (j >= N) of the tile images stay zero
   return FDPT_OK;
 }
@@ -251,7 +322,7 @@ struct Lin {
     GemmArgs g;
     g.A = x; g.lda = lda; g.B = W; g.ldb = ldb; g.C = y; g.ldc = ldc; g.M = (int)M; g.N = N; g.K = K;
     g.bias = bias; g.relu = relu; g.residual = residual; g.ldr = ldr; g.rowmask = rowmask; g.accumulate = accumulate;
-    cudaError_t e = launch_gemm(g, true, 1, st);
+    cudaError_t e = gemm_dispatch(ctx, g, true, 1, st);
     ctx->launches++;
     if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
     return FDPT_OK;
@@ -310,7 +381,7 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
   return FDPT_OK;
 }
 
-// ---- IPA ---------------------------------------------------------------------------------------------------
+// ---- IPA (kernels_ipa.cuh) ------------------------------------------------------------------------------------
 int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* z, const float* quats, const float* trans,
             const float* mask, float* out, int ldo, const float* residual, const float* outmask, cudaStream_t st) {
   ProfScope ps(ctx, FDPT_PROF_IPA_TOTAL, st);
@@ -318,42 +389,43 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
   const BlockParams& p = ctx->blk[blk];
   const long long M = (long long)B * N;
   Lin lin{ctx, st};
-  RET(lin(s, C_S, p.Wq, C_S, p.bq, w.q, NH * C_HID, M, NH * C_HID, C_S));
-  RET(lin(s, C_S, p.Wkv, C_S, p.bkv, w.kv, 2 * NH * C_HID, M, 2 * NH * C_HID, C_S));
-  RET(lin(s, C_S, p.Wqp, C_S, p.bqp, w.qp_raw, NH * PQ * 3, M, NH * PQ * 3, C_S));
-  RET(lin(s, C_S, p.Wkvp, C_S, p.bkvp, w.kvp_raw, NH * (PQ + PV) * 3, M, NH * (PQ + PV) * 3, C_S));
-  ipa_points_kernel<<<(unsigned)M, 128, 0, st>>>((int)M, w.qp_raw, w.kvp_raw, quats, trans, w.q_pts, w.k_pts, w.v_pts);
+  if (w.JB > IPA_MAX_JB) return fail(ctx, FDPT_ERR_INVALID, "N=%d: the IPA kernel supports N <= %d", N, IPA_MAX_JB * 128);
+  // q | q_pts, k | k_pts, v | v_pts of every head in one GEMM, then the frames applied in place
+  RET(lin(s, C_S, p.Wcat, C_S, p.bcat, w.proj, PROJ_W, M, PROJ_W, C_S));
+  ipa_prep_kernel<<<(unsigned)M, 256, 0, st>>>((int)M, w.proj, quats, trans, p.head_w, w.kn);
   LAUNCH_CHECK();
-  {  // S[b,h] = Q_h K_h^T
+  {  // S[b,h] = s_qk * [q | g q_pts] . [k | k_pts]^T
     GemmArgs g;
-    g.A = w.q; g.lda = NH * C_HID; g.sA1 = (long long)N * NH * C_HID; g.sA2 = C_HID;
-    g.B = w.kv; g.ldb = 2 * NH * C_HID; g.sB1 = (long long)N * 2 * NH * C_HID; g.sB2 = 2 * C_HID;
-    g.C = w.S; g.ldc = N; g.sC1 = (long long)NH * N * N; g.sC2 = (long long)N * N;
-    g.M = N; g.N = N; g.K = C_HID; g.batch2 = NH;
-    CK(launch_gemm(g, true, B * NH, st));
+    g.A = w.proj + PROJ_Q; g.lda = PROJ_W; g.sA1 = (long long)N * PROJ_W; g.sA2 = QK_W;
+    g.B = w.proj + PROJ_K; g.ldb = PROJ_W; g.sB1 = (long long)N * PROJ_W; g.sB2 = QK_W;
+    g.C = w.S; g.ldc = w.ldS; g.sC1 = (long long)NH * N * w.ldS; g.sC2 = (long long)N * w.ldS;
+    g.M = N; g.N = N; g.K = QK_W; g.batch2 = NH; g.alpha = sqrtf(1.0f / (3.f * C_HID));
+    CK(gemm_dispatch(ctx, g, true, B * NH, st));
     ctx->launches++;
   }
   {
+    const IpaSmemPlan plan = ipa_core_plan(N, ctx->max_smem_optin);
+    if (plan.rz < 1) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs more shared memory than available in ipa_core", N);
     IpaCoreArgs a;
-    a.B = B; a.N = N; a.S = w.S; a.z = z; a.JB = w.JB; a.q_pts = w.q_pts; a.k_pts = w.k_pts; a.v_pts = w.v_pts; a.quats = quats; a.trans = trans;
-    a.mask = mask; a.Wb = p.Wb; a.bb = p.bb; a.head_w = p.head_w; a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat;
-    const size_t smem = ipa_core_smem_bytes(N);
-    if ((int)smem > ctx->max_smem_optin) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs %zu B of shared memory in ipa_core", N, smem);
+    a.B = B; a.N = N; a.JB = w.JB; a.ldS = w.ldS; a.S = w.S; a.z = z; a.kn = w.kn; a.mask = mask; a.Wb_img = p.imgWb; a.bb = p.bb;
+    a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat; a.rz = plan.rz; a.resident = plan.resident; a.rows = (int)M; a.mn_swap = ctx->mn_swap;
     ProfScope pc(ctx, FDPT_PROF_IPA_CORE, st);
-    ipa_core_kernel<<<dim3(N, B), 256, smem, st>>>(a);
+    ipa_core_kernel<<<(unsigned)std::min<long long>(ctx->num_sms, M), 192, plan.bytes, st>>>(a);
     LAUNCH_CHECK();
   }
-  {  // o[b,:,h,:] = A_h V_h  -> cat[:, h*256 : (h+1)*256]
+  {  // [o | o_pt (global frame)][b,:,h,:] = A_h [V_h | v_pts_h]  -> cat'[:, h*292 : (h+1)*292]
     GemmArgs g;
-    g.A = w.S; g.lda = N; g.sA1 = (long long)NH * N * N; g.sA2 = (long long)N * N;
-    g.B = w.kv + C_HID; g.ldb = 2 * NH * C_HID; g.sB1 = (long long)N * 2 * NH * C_HID; g.sB2 = 2 * C_HID;
-    g.C = w.cat; g.ldc = CAT; g.sC1 = (long long)N * CAT; g.sC2 = C_HID;
-    g.M = N; g.N = C_HID; g.K = N; g.batch2 = NH;
-    CK(launch_gemm(g, false, B * NH, st));
+    g.A = w.S; g.lda = w.ldS; g.sA1 = (long long)NH * N * w.ldS; g.sA2 = (long long)N * w.ldS;
+    g.B = w.proj + PROJ_V; g.ldb = PROJ_W; g.sB1 = (long long)N * PROJ_W; g.sB2 = V_W;
+    g.C = w.cat; g.ldc = CAT; g.sC1 = (long long)N * CAT; g.sC2 = V_W;
+    g.M = N; g.N = V_W; g.K = N; g.batch2 = NH;
+    CK(gemm_dispatch(ctx, g, false, B * NH, st));
     ctx->launches++;
   }
+  ipa_opt_kernel<<<(unsigned)M, NH * PV, 0, st>>>((int)M, w.cat, quats, trans);
+  LAUNCH_CHECK();
   // linear_out (+ mask, + residual)
-  RET(lin(w.cat, CAT, p.Wout, CAT, p.bout, out, ldo, M, C_S, CAT, 0, residual, C_S, outmask));
+  RET(lin(w.cat, CAT, p.Wout_perm, CAT, p.bout, out, ldo, M, C_S, CAT, 0, residual, C_S, outmask));
   return FDPT_OK;
 }
 
@@ -404,7 +476,7 @@ int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaSt
       g.B = w.qkv + TF_D; g.ldb = 3 * TF_D; g.sB1 = (long long)N * 3 * TF_D; g.sB2 = TF_DH;
       g.C = w.S; g.ldc = N; g.sC1 = (long long)TF_H * N * N; g.sC2 = (long long)N * N;
       g.M = N; g.N = N; g.K = TF_DH; g.batch2 = TF_H;
-      CK(launch_gemm(g, true, B * TF_H, st));
+      CK(gemm_dispatch(ctx, g, true, B * TF_H, st));
       ctx->launches++;
     }
     {
@@ -418,7 +490,7 @@ int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaSt
       g.B = w.qkv + 2 * TF_D; g.ldb = 3 * TF_D; g.sB1 = (long long)N * 3 * TF_D; g.sB2 = TF_DH;
       g.C = w.att_o; g.ldc = TF_D; g.sC1 = (long long)N * TF_D; g.sC2 = TF_DH;
       g.M = N; g.N = TF_DH; g.K = N; g.batch2 = TF_H;
-      CK(launch_gemm(g, false, B * TF_H, st));
+      CK(gemm_dispatch(ctx, g, false, B * TF_H, st));
       ctx->launches++;
     }
     RET(lin(w.att_o, TF_D, L.Wo, TF_D, L.bo, w.tmpA, TF_D, M, TF_D, TF_D, 0, w.tf_x, TF_D));
@@ -549,6 +621,7 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::et_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et_smem_bytes());
   cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::tc_linear_smem_bytes(512));
+  cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_tc_smem_bytes(128));
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
   float lower[NBINS];
   {
@@ -580,6 +653,10 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaFree(b.imgW1cat);
     cudaFree(b.imgW2);
     cudaFree(b.imgW3cat);
+    cudaFree(b.Wcat);
+    cudaFree(b.bcat);
+    cudaFree(b.Wout_perm);
+    cudaFree(b.imgWb);
   }
   cudaFree(ctx->ws.base);
   cudaFree(ctx->bin_lower);
@@ -640,6 +717,7 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
     p.Wkvp = P(ip + ".linear_kv_points.weight"); p.bkvp = P(ip + ".linear_kv_points.bias");
     p.Wb = P(ip + ".linear_b.weight"); p.bb = P(ip + ".linear_b.bias"); p.Wd = P(ip + ".down_z.weight"); p.bd = P(ip + ".down_z.bias");
     p.Wout = P(ip + ".linear_out.weight"); p.bout = P(ip + ".linear_out.bias");
+    RET(pack_ipa_params(ctx, p));
     p.ln_g = P(t + "ipa_ln_" + bs + ".weight"); p.ln_b = P(t + "ipa_ln_" + bs + ".bias");
     p.Wskip = P(t + "skip_embed_" + bs + ".weight"); p.bskip = P(t + "skip_embed_" + bs + ".bias");
     for (int l = 0; l < TF_LAYERS; ++l) {
@@ -855,6 +933,27 @@ int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float*
   cudaSetDevice(ctx->device);
   Lin lin{ctx, (cudaStream_t)stream};
   return lin(x, K, w, K, bias, y, N, M, N, K, act);
+}
+
+int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
+  if (!ctx) return FDPT_ERR_INVALID;
+  switch (option) {
+    case FDPT_OPT_GEMM_TC: ctx->gemm_tc = value != 0; return FDPT_OK;
+    case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
+    default: return fail(ctx, FDPT_ERR_INVALID, "unknown option %d", option);
+  }
+}
+
+int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, int lda, long long sa, const float* b, int ldb, long long sb,
+                int b_kmajor, float alpha, float* c, int ldc, long long sc, void* stream) {
+  if (!ctx || !a || !b || !c || batch <= 0) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  GemmArgs g;
+  g.A = a; g.lda = lda; g.sA1 = sa; g.B = b; g.ldb = ldb; g.sB1 = sb; g.C = c; g.ldc = ldc; g.sC1 = sc;
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha;
+  CK(gemm_dispatch(ctx, g, b_kmajor != 0, batch, (cudaStream_t)stream));
+  ctx->launches++;
+  return FDPT_OK;
 }
 
 int fdpt_tc_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act, float* y,

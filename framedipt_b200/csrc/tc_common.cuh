@@ -82,6 +82,16 @@ FDPT_DEVINL void tmem_ld32(uint32_t taddr, float v[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+FDPT_DEVINL void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 FDPT_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ----------------------------------------------------------------------------------------
@@ -93,6 +103,18 @@ FDPT_DEVINL uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// SWIZZLE_128B descriptor with explicit leading / stride byte offsets.  MN-major operands (16-bit types) use both:
+//   LBO = byte stride between 128-byte atoms along M/N (64 halfs), SBO = byte stride between 8-row atoms along K
+//   (verified on B200 with the tf32 MN-major operand of gemm_tc.cuh: LBO steps along M/N, SBO along K).
+FDPT_DEVINL uint64_t make_sw128_desc_ls(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;

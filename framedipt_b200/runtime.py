@@ -89,6 +89,9 @@ def lib() -> C.CDLL:
         L.fdpt_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_void_p]
         L.fdpt_tc_linear.argtypes = L.fdpt_linear.argtypes
+        L.fdpt_matmul.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_int,
+                                  C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]
+        L.fdpt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.fdpt_ipa.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.fdpt_edge_transition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.fdpt_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -287,6 +290,18 @@ class Context:
         y = torch.empty(M, Nn, device=self.device)
         self._ck(lib().fdpt_linear(self._h, M, Nn, K, _ptr(x), _ptr(w), _ptr(b), act, _ptr(y), self.stream))
         return y
+
+    def set_option(self, option: int, value: int):
+        self._ck(lib().fdpt_set_option(self._h, option, value))
+
+    def matmul(self, a, b, b_kmajor=True, alpha=1.0):
+        """Batched a[Bt,M,K] @ (b[Bt,N,K]^T if b_kmajor else b[Bt,K,N]) on the node-side GEMM kernel."""
+        Bt, M, K = a.shape
+        Nn = b.shape[1] if b_kmajor else b.shape[2]
+        c = torch.empty(Bt, M, Nn, device=self.device)
+        self._ck(lib().fdpt_matmul(self._h, Bt, M, Nn, K, _ptr(a), a.stride(1), a.stride(0), _ptr(b), b.stride(1), b.stride(0),
+                                   int(b_kmajor), alpha, _ptr(c), Nn, M * Nn, self.stream))
+        return c
 
     def tc_linear(self, x, w, b, act=0):
         M, K = x.shape

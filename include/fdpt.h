@@ -170,6 +170,14 @@ int fdpt_profile_read(fdpt_ctx* ctx, int slot, int* count, double* total_ms);
 /* y[M,N] = act(x[M,K] @ w[N,K]^T + bias) ; act: 0 none, 1 relu */
 int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act,
                 float* y, void* stream);
+/* c[b] = alpha * a[b] @ op(b[b]) for b < batch (strides sa/sb/sc in elements); b_kmajor=1: b is [N,K] (like a weight),
+ * 0: b is [K,N] row-major.  Runs the node-side GEMM kernel the hot path uses: tcgen05 3-term split TF32 (fp32-class),
+ * or the SIMT fp32 kernel for N < 16 / when FDPT_OPT_GEMM_TC is 0. */
+int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, int lda, long long sa, const float* b,
+                int ldb, long long sb, int b_kmajor, float alpha, float* c, int ldc, long long sc, void* stream);
+/* bring-up / A-B switches (not needed by integrators) */
+enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1 };
+int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
 /* same contract on the tcgen05 tensor cores (fp16 operands, fp32 accumulate): K multiple of 64 (<= 512), N multiple of 128.
  * Bring-up / unit entry of the building blocks the fused pair-side kernels use. */
 int fdpt_tc_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act,
