@@ -6,13 +6,13 @@
 // so every operand x is split on the fly into x_hi = x with the 13 low mantissa bits cleared (exactly representable in TF32)
 // and x_lo = x - x_hi (exact in fp32), and   A·B ~= A_lo·B_hi + A_hi·B_lo + A_hi·B_hi   (dropped term ~2^-22 relative).
 //
-// CTA = one 128 x BN output tile (BN = 128 or 64), 160 threads:
-//   warps 0-3  producers: cp.async (LDGSTS) of the raw fp32 A / B k-block (32 fp32 = 128 B per row) straight into the swizzled
+// CTA = one 128 x BN output tile (BN = 128 or 64), 288 threads:
+//   warps 0-7  producers: cp.async (LDGSTS) of the raw fp32 A / B k-block (32 fp32 = 128 B per row) straight into the swizzled
 //              K-major operand image, two k-blocks ahead; then an in-place split into the hi / lo images (B may also be
 //              [K,N] row-major = MN-major operand in the SWIZZLE_128B_BASE32B layout, used by P·V); later the epilogue
 //              (tcgen05.ld of both accumulators -> bias / relu / mask / residual -> global).
-//   warp 4     MMA issuer (one elected lane) + TMEM owner.
-// 3-stage smem ring (64 KB / stage at BN=128) with full/empty mbarriers; arbitrary M, N, K (zero-filled edges), row strides and
+//   warp 8     MMA issuer (one elected lane) + TMEM owner.
+// 5-deep raw/hi ring + 2-deep lo ring (224 KB at BN=128) with full/done mbarriers; the split of k-block kb overlaps the MMAs of kb-1; arbitrary M, N, K (zero-filled edges), row strides and
 // two batch strides, so the same kernel serves Linear layers, per-head Q·K^T and P·V.
 #pragma once
 #include "gemm_simt.cuh"
@@ -21,7 +21,9 @@
 namespace fdpt {
 namespace tc {
 
-constexpr int GT_STAGES = 3;
+constexpr int GT_STAGES = 5;       // raw/hi ring depth (the lo images have their own 2-deep ring)
+constexpr int GT_PRODUCERS = 256;  // producer / epilogue threads (8 warps); warp 8 issues the MMAs
+constexpr int GT_THREADS = GT_PRODUCERS + 32;
 constexpr int GT_BM = 128;
 constexpr int GT_KB = 32;  // fp32 elements per k-block row (128 B)
 
@@ -100,17 +102,32 @@ FDPT_DEVINL uint64_t make_mn32_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint
   return d;
 }
 
-__global__ void __launch_bounds__(160) gemm_tc_kernel(GemmTcArgs a) {
+// per-thread copy plan of one operand: `iters` chunks per k-block, affine in the iteration index
+struct ChunkPlan {
+  const float* src;        // first chunk of k-block 0
+  long long it_stride;     // elements between consecutive iterations
+  long long kb_stride;     // elements between consecutive k-blocks
+  uint32_t dst, dst_it_stride;  // byte offset inside the operand image
+  int iters;
+  int kmajor;              // 1: validity along the chunk = K tail, per-iteration = row;  0: chunk = N tail, per-iteration = k row
+  int row0, row_step, row_lim;  // row (m / n) or k index of iteration 0, its step, and its limit
+  int col0, col_lim;            // first element index along the chunk direction and its limit
+  int vec;
+};
+
+__global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(GemmTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const GemmArgs& g = a.g;
   const int BN = a.bn;
   const uint32_t a_bytes = GT_BM * 128, b_bytes = (uint32_t)BN * 128;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GT_STAGES * stage_bytes);
-  uint64_t* full = bars;                 // [GT_STAGES] 128 producer arrivals
-  uint64_t* empty = bars + GT_STAGES;    // [GT_STAGES] tcgen05.commit
-  uint64_t* acc_full = empty + GT_STAGES;
+  const uint32_t stage_bytes = a_bytes + b_bytes;          // one k-block of A and B (raw -> hi in place; or lo)
+  uint8_t* raw_ring = smem;                                // GT_STAGES stages
+  uint8_t* lo_ring = smem + GT_STAGES * stage_bytes;       // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lo_ring + 2 * stage_bytes);
+  uint64_t* full = bars;                 // [GT_STAGES] GT_PRODUCERS arrivals: hi and lo images of k-block kb are ready
+  uint64_t* done = bars + GT_STAGES;     // [GT_STAGES] tcgen05.commit: the MMAs of k-block kb have completed
+  uint64_t* acc_full = done + GT_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -124,21 +141,21 @@ __global__ void __launch_bounds__(160) gemm_tc_kernel(GemmTcArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < GT_STAGES; ++s) {
-      mbar_init(&full[s], 128);
-      mbar_init(&empty[s], 1);
+      mbar_init(&full[s], GT_PRODUCERS);
+      mbar_init(&done[s], 1);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   // two accumulators: [0,BN) hi*hi, [BN,2BN) the two cross terms (2^-11 smaller, so the tensor core's truncating fp32
   // accumulation costs 2^-11 less there and the main accumulator sees a third of the additions)
-  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)(2 * BN));
+  if (warp == GT_PRODUCERS / 32) tmem_alloc(tmem_slot, (uint32_t)(2 * BN));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == GT_PRODUCERS / 32) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(GT_BM, BN, a.b_kmajor ? 0 : 1);
@@ -147,8 +164,8 @@ __global__ void __launch_bounds__(160) gemm_tc_kernel(GemmTcArgs a) {
         const int s = kb % GT_STAGES;
         mbar_wait(&full[s], (kb / GT_STAGES) & 1);
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * stage_bytes);
-        const uint32_t ah = base, al = base + a_bytes, bh = base + 2 * a_bytes, bl = bh + b_bytes;
+        const uint32_t ah = smem_u32(raw_ring + s * stage_bytes), bh = ah + a_bytes;
+        const uint32_t al = smem_u32(lo_ring + (kb & 1) * stage_bytes), bl = al + a_bytes;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // 4 x k8 per 128-byte k-block
           const uint64_t dah = make_sw128_desc(ah + k * 32), dal = make_sw128_desc(al + k * 32);
@@ -158,89 +175,93 @@ __global__ void __launch_bounds__(160) gemm_tc_kernel(GemmTcArgs a) {
             dbl = make_sw128_desc(bl + k * 32);
           } else {
             const uint32_t koff = (uint32_t)(2 * k * mn_atoms) * 512, lbo = 512, sbo = (uint32_t)mn_atoms * 512;
-            dbh = make_mn32_desc(bh + koff, a.mn_swap ? sbo : lbo, a.mn_swap ? lbo : sbo);
-            dbl = make_mn32_desc(bl + koff, a.mn_swap ? sbo : lbo, a.mn_swap ? lbo : sbo);
+            dbh = make_mn32_desc(bh + koff, lbo, sbo);
+            dbl = make_mn32_desc(bl + koff, lbo, sbo);
           }
           const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
           umma_tf32(acc_x, dal, dbh, idesc, first);
           umma_tf32(acc_x, dah, dbl, idesc, 1u);
           umma_tf32(acc_main, dah, dbh, idesc, first);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&done[s]);
       }
       umma_commit(acc_full);
     }
   } else {
-    // ============================ producers (128 threads) ============================
+    // ============================ producers (256 threads) ============================
     // chunk ownership is fixed per thread, so a thread only ever splits chunks it copied itself (cp.async.wait_group suffices)
-    const int b_iters = a.b_kmajor ? BN / 16 : (8 * BN) / 128;
-    auto issue = [&](int kb) {
-      const int s = kb % GT_STAGES;
-      const uint32_t Ah = smem_u32(smem + s * stage_bytes), Bh = Ah + 2 * a_bytes;
-      const int k0 = kb * GT_KB;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 128 + tid, r = idx >> 3, c = idx & 7;
-        const int m = m0 + r, k = k0 + 4 * c;
-        copy_chunk(Ah + sw128_chunk_off(r, c), A, A + (long long)m * g.lda + k, m < g.M ? g.K - k : 0, a.a_vec);
-      }
+    ChunkPlan pa, pb;
+    {
+      const int r0 = tid >> 3, c = tid & 7;
+      pa.src = A + (long long)(m0 + r0) * g.lda + 4 * c;
+      pa.it_stride = 32LL * g.lda; pa.kb_stride = GT_KB;
+      pa.dst = sw128_chunk_off(r0, c); pa.dst_it_stride = 32 * 128;
+      pa.iters = GT_BM / 32; pa.kmajor = 1;
+      pa.row0 = m0 + r0; pa.row_step = 32; pa.row_lim = g.M; pa.col0 = 4 * c; pa.col_lim = g.K; pa.vec = a.a_vec;
       if (a.b_kmajor) {
-        for (int it = 0; it < b_iters; ++it) {
-          const int idx = it * 128 + tid, r = idx >> 3, c = idx & 7;
-          const int n = n0 + r, k = k0 + 4 * c;
-          copy_chunk(Bh + sw128_chunk_off(r, c), B, B + (long long)n * g.ldb + k, n < g.N ? g.K - k : 0, a.b_vec);
-        }
+        pb.src = B + (long long)(n0 + r0) * g.ldb + 4 * c;
+        pb.it_stride = 32LL * g.ldb; pb.kb_stride = GT_KB;
+        pb.dst = a_bytes + sw128_chunk_off(r0, c); pb.dst_it_stride = 32 * 128;
+        pb.iters = BN / 32; pb.kmajor = 1;
+        pb.row0 = n0 + r0; pb.row_step = 32; pb.row_lim = g.N; pb.col0 = 4 * c; pb.col_lim = g.K; pb.vec = a.b_vec;
       } else {
-        const int cpr = BN / 4;  // 16-byte chunks per k-row
-        for (int it = 0; it < b_iters; ++it) {
-          const int idx = it * 128 + tid, kk = idx / cpr, c = idx % cpr;
-          const int k = k0 + kk, n = n0 + 4 * c;
-          copy_chunk(Bh + mn32_chunk_off(kk, c, mn_atoms), B, B + (long long)k * g.ldb + n, k < g.K ? g.N - n : 0, a.b_vec);
+        const int cpr = BN / 4, kk0 = tid / cpr, cc = tid % cpr, kstep = GT_PRODUCERS / cpr;
+        pb.src = B + (long long)kk0 * g.ldb + n0 + 4 * cc;
+        pb.it_stride = (long long)kstep * g.ldb; pb.kb_stride = (long long)GT_KB * g.ldb;
+        pb.dst = a_bytes + mn32_chunk_off(kk0, cc, mn_atoms); pb.dst_it_stride = (uint32_t)(kstep / 4) * mn_atoms * 512;
+        pb.iters = 32 / kstep; pb.kmajor = 0;
+        pb.row0 = kk0; pb.row_step = kstep; pb.row_lim = g.K; pb.col0 = n0 + 4 * cc; pb.col_lim = g.N; pb.vec = a.b_vec;
+      }
+    }
+    auto issue_op = [&](const ChunkPlan& p, uint32_t stage_u32, int kb, const float* base) {
+      const float* src = p.src + (long long)kb * p.kb_stride;
+      const int cvalid = p.kmajor ? p.col_lim - (kb * GT_KB + p.col0) : p.col_lim - p.col0;
+      const int roff = p.kmajor ? 0 : kb * GT_KB;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (it < p.iters) {
+          const bool rv = (p.row0 + roff + it * p.row_step) < p.row_lim;
+          copy_chunk(stage_u32 + p.dst + it * p.dst_it_stride, base, src + it * p.it_stride, rv ? cvalid : 0, p.vec);
         }
       }
     };
-    for (int kb = 0; kb < GT_STAGES - 1; ++kb) {
+    auto split_op = [&](const ChunkPlan& p, uint8_t* hi, uint8_t* lo) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+        if (it < p.iters) split_chunk(hi, lo, p.dst + it * p.dst_it_stride);
+    };
+    auto issue = [&](int kb) {
+      const uint32_t st = smem_u32(raw_ring + (kb % GT_STAGES) * stage_bytes);
+      issue_op(pa, st, kb, A);
+      issue_op(pb, st, kb, B);
+    };
+    // prefetch distance GT_STAGES - 2: the split of k-block kb overlaps the MMAs of kb-1; a raw slot (and the lo slot of the same
+    // parity) is recycled once the MMAs of k-block kb-2 are done
+    for (int kb = 0; kb < GT_STAGES - 2; ++kb) {
       if (kb < nkb) issue(kb);
       cp_async_commit();
     }
     for (int kb = 0; kb < nkb; ++kb) {
-      const int kn = kb + GT_STAGES - 1;
-      if (kn < nkb) {
-        mbar_wait(&empty[kn % GT_STAGES], ((kn / GT_STAGES) & 1) ^ 1);
-        issue(kn);
-      }
+      if (kb >= 2) mbar_wait(&done[(kb - 2) % GT_STAGES], ((kb - 2) / GT_STAGES) & 1);
+      const int kn = kb + GT_STAGES - 2;
+      if (kn < nkb) issue(kn);
       cp_async_commit();
-      cp_async_wait<GT_STAGES - 1>();
-      const int s = kb % GT_STAGES;
-      uint8_t* st = smem + s * stage_bytes;
-      uint8_t *Ah = st, *Al = st + a_bytes, *Bh = st + 2 * a_bytes, *Bl = Bh + b_bytes;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 128 + tid;
-        split_chunk(Ah, Al, sw128_chunk_off(idx >> 3, idx & 7));
-      }
-      if (a.b_kmajor) {
-        for (int it = 0; it < b_iters; ++it) {
-          const int idx = it * 128 + tid;
-          split_chunk(Bh, Bl, sw128_chunk_off(idx >> 3, idx & 7));
-        }
-      } else {
-        const int cpr = BN / 4;
-        for (int it = 0; it < b_iters; ++it) {
-          const int idx = it * 128 + tid;
-          split_chunk(Bh, Bl, mn32_chunk_off(idx / cpr, idx % cpr, mn_atoms));
-        }
-      }
+      cp_async_wait<GT_STAGES - 2>();
+      uint8_t* hi = raw_ring + (kb % GT_STAGES) * stage_bytes;
+      uint8_t* lo = lo_ring + (kb & 1) * stage_bytes;
+      split_op(pa, hi, lo);
+      split_op(pb, hi, lo);
       fence_proxy_async();
-      mbar_arrive(&full[s]);
+      mbar_arrive(&full[kb % GT_STAGES]);
     }
-    // ============================ epilogue ============================
+    // ============================ epilogue (warps w and w+4 share TMEM lanes, each takes half of the columns) ============
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int r = warp * 32 + lane, m = m0 + r;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int r = (warp & 3) * 32 + lane, m = m0 + r;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float rm = (g.rowmask && m < g.M) ? g.rowmask[m] : 1.f;
-    for (int cb = 0; cb < BN; cb += 32) {
+    const int c_begin = (warp >> 2) * (BN / 2), c_end = c_begin + BN / 2;
+    for (int cb = c_begin; cb < c_end; cb += 32) {
       float v[32], x2[32];
       tmem_ld32(tmem_base + lane_base + cb, v);
       tmem_ld32(tmem_base + lane_base + BN + cb, x2);
@@ -286,10 +307,10 @@ __global__ void __launch_bounds__(160) gemm_tc_kernel(GemmTcArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)(2 * BN));
+  if (warp == GT_PRODUCERS / 32) tmem_dealloc(tmem_base, (uint32_t)(2 * BN));
 }
 
-inline size_t gemm_tc_smem_bytes(int bn) { return 1024 + (size_t)GT_STAGES * (2 * GT_BM * 128 + 2 * (size_t)bn * 128) + 64; }
+inline size_t gemm_tc_smem_bytes(int bn) { return 1024 + (size_t)(GT_STAGES + 2) * (GT_BM * 128 + (size_t)bn * 128) + 128; }
 
 inline bool aligned16(const void* p, long long ld, long long s1, long long s2) {
   return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0) && (s1 % 4 == 0) && (s2 % 4 == 0);
@@ -310,7 +331,7 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, bool b_kmajor, int batch, c
   a.c_vec = aligned16(g.C, g.ldc, g.sC1, g.sC2) && (!g.residual || aligned16(g.residual, g.ldr, 0, 0));
   a.mn_swap = mn_swap;
   dim3 grid((g.M + GT_BM - 1) / GT_BM, (g.N + a.bn - 1) / a.bn, batch);
-  gemm_tc_kernel<<<grid, 160, gemm_tc_smem_bytes(a.bn), st>>>(a);
+  gemm_tc_kernel<<<grid, GT_THREADS, gemm_tc_smem_bytes(a.bn), st>>>(a);
   return cudaGetLastError();
 }
 
