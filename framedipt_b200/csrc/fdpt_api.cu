@@ -112,7 +112,7 @@ int fail(fdpt_ctx* c, int code, const char* fmt, ...) {
 }
 
 cudaError_t gemm_dispatch(fdpt_ctx* c, const GemmArgs& g, bool b_kmajor, int batch, cudaStream_t st) {
-  if (c->gemm_tc) return tc::launch_gemm_tc(g, b_kmajor, batch, st, c->num_sms, c->mn_swap);
+  if (c->gemm_tc) return tc::launch_gemm_tc(g, b_kmajor, batch, st, c->num_sms);
   return launch_gemm(g, b_kmajor, batch, st);
 }
 
