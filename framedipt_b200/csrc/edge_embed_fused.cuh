@@ -1,0 +1,341 @@
+// edge_embed_fused.cuh — the pair half of Embedder.forward (score_network.py:114-127, 153-197; data/utils.py:541-550) as ONE persistent
+// tcgen05 kernel: pair features are built on the fly, the 3-layer MLP is chained through TMEM / shared memory, LayerNorm + mask in
+// the epilogue, and z0 is written once as fp16 tile images (256 B / pair).  Nothing else pair-sized touches HBM.
+//
+//   x_ij = [f_i (54) | f_j (54) | idx_emb(seq_i - seq_j) (32) | onehot22(bin(|ca_i - ca_j|))]            (162 columns of edge_embedder.0)
+//   layer 1 is factorised:  W0 x = A f_i + b0   (per residue, fp32-class GEMM outside: PA_i, enters as an
+//                                                        epilogue vector of the tile, all 128 pairs of a tile share i)
+//                                                      + B f_j       (k-block 1 of GEMM0: an fp16 image per (b, j-block) shared by all i)
+//                                                      + [C | D] [emb | onehot]   (k-block 0 of GEMM0, built per tile by the workers)
+//   GEMM0  D0[128 x 128] = [emb | onehot | f_j] (K = 128) . [C | D | B]^T      E0: h1 = relu(D0 + PA_i)            -> fp16 A1
+//   GEMM1  D1 = h1 . W2^T                                                        E1: h2 = relu(D1 + b2)              -> fp16 A2
+//   GEMM2  D2 = h2 . W4^T                                                        E2: z0 = LN(D2 + b4) * m_i m_j      -> fp16 tile image
+//
+// All three weight matrices (96 KB as fp16 swizzled images) stay resident in shared memory.  Warps 0-3: workers (thread <-> pair row
+// <-> TMEM lane), warp 4: MMA issuer + TMEM owner, warp 5: loader.  MMA issue order G0(t+1) between G1(t) and G2(t), so the first GEMM
+// of the next tile is already done when the workers get there.  fp16 operands (10-bit mantissa = TF32 class, which the pair side
+// tolerates: SURVEY §7 hard part 1), fp32 accumulate, positional tables evaluated on the host and gathered here.
+#pragma once
+#include "tc_common.cuh"
+
+namespace fdpt {
+namespace tc {
+
+struct EeArgs {
+  int B, N, JB;
+  __half* z_out;              // tile images [B][N][JB][32 KB]
+  const __half* f_img;        // [B][JB][16 KB] k-block image of the per-residue features f_j (zero padded to 64 columns / 128 rows)
+  const float* PA;            // [B*N, 128]  A f_i + b0
+  const __half* rel_tab;      // [rel_count][32] fp16 idx_emb(rel_min + r)
+  const int32_t* seq_idx;     // [B*N]
+  int rel_min, rel_count;
+  const float* sc_ca;         // [B*N, 3]
+  const float* bin_lower;     // [22]
+  const float* b2; const float* b4; const float* ln_g; const float* ln_b;  // [128]
+  const float* mask;          // [B*N]
+  const __half* W0img;        // image [2 kb][128][128 B]: kb0 = [C | D | 0], kb1 = [B | 0]
+  const __half* W2img;        // image [2 kb][128][128 B]
+  const __half* W4img;
+  long long tiles;            // B*N*JB
+};
+
+constexpr int EE_W_BYTES = 32768;
+
+__global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* W0s = smem;                      // 32 KB
+  uint8_t* W2s = W0s + EE_W_BYTES;          // 32 KB
+  uint8_t* W4s = W2s + EE_W_BYTES;          // 32 KB
+  uint8_t* A0t = W4s + EE_W_BYTES;          // 2 x 16 KB per-tile k-block [emb | onehot]
+  uint8_t* A0f = A0t + 2 * 16384;           // 16 KB per-(b, j-block) k-block f_j
+  uint8_t* A1 = A0f + 16384;                // 32 KB h1 (also staging of the output tile)
+  uint8_t* A2 = A1 + 32768;                 // 32 KB h2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(A2 + 32768);
+  uint64_t* w_full = bars;          // [1]
+  uint64_t* an_full = bars + 1;     // [1]
+  uint64_t* an_free = bars + 2;     // [1]
+  uint64_t* a0_full = bars + 3;     // [2]
+  uint64_t* d0_full = bars + 5;     // [1]
+  uint64_t* a1_full = bars + 6;     // [1]
+  uint64_t* d1_full = bars + 7;     // [1]
+  uint64_t* a2_full = bars + 8;     // [1]
+  uint64_t* d2_full = bars + 9;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* PA_s = reinterpret_cast<float*>(tmem_slot + 4);  // [128]
+  float* b2_s = PA_s + 128;
+  float* b4_s = b2_s + 128;
+  float* g_s = b4_s + 128;
+  float* be_s = g_s + 128;
+  float* lower_s = be_s + 128;  // [24]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long per = (a.tiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * per;
+  const long long t_end = min(a.tiles, t_begin + per);
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(an_full, 1);
+    mbar_init(an_free, 1);
+    mbar_init(&a0_full[0], 128);
+    mbar_init(&a0_full[1], 128);
+    mbar_init(d0_full, 1);
+    mbar_init(a1_full, 128);
+    mbar_init(d1_full, 1);
+    mbar_init(a2_full, 128);
+    mbar_init(d2_full, 1);
+    fence_barrier_init();
+  }
+  for (int k = threadIdx.x; k < 128; k += blockDim.x) {
+    b2_s[k] = a.b2[k];
+    b4_s[k] = a.b4[k];
+    g_s[k] = a.ln_g[k];
+    be_s[k] = a.ln_b[k];
+  }
+  if (threadIdx.x < 24) lower_s[threadIdx.x] = threadIdx.x < NBINS ? a.bin_lower[threadIdx.x] : 1e8f;  // [22] = top edge 1e8
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t D0 = tmem_base, D1 = tmem_base + 128, D2 = tmem_base + 256;
+
+  // tiles are ordered (b, jb, i) with i fastest; the f_j image changes when (b, jb) changes
+  auto tile_bjb = [&](long long t) -> long long { return t / a.N; };
+  auto tile_m = [&](long long t, int& jb, int& b) -> long long {
+    const long long bjb = t / a.N;
+    const int i = (int)(t - bjb * a.N);
+    b = (int)(bjb / a.JB);
+    jb = (int)(bjb - (long long)b * a.JB);
+    return (long long)b * a.N + i;
+  };
+
+  if (warp == 5) {
+    // ============================ loader ============================
+    if (lane == 0 && t_begin < t_end) {
+      mbar_arrive_expect_tx(w_full, 3 * EE_W_BYTES);
+      bulk_g2s(W0s, a.W0img, EE_W_BYTES, w_full);
+      bulk_g2s(W2s, a.W2img, EE_W_BYTES, w_full);
+      bulk_g2s(W4s, a.W4img, EE_W_BYTES, w_full);
+      auto load_f = [&](long long t) {
+        mbar_arrive_expect_tx(an_full, 16384);
+        bulk_g2s(A0f, reinterpret_cast<const uint8_t*>(a.f_img) + tile_bjb(t) * 16384LL, 16384, an_full);
+      };
+      load_f(t_begin);
+      uint32_t nfree = 0;
+      for (long long t = t_begin; t + 1 < t_end; ++t) {
+        if (tile_bjb(t + 1) != tile_bjb(t)) {
+          mbar_wait(an_free, nfree & 1);  // GEMM0 of tile t (last reader of the old image) has completed
+          ++nfree;
+          load_f(t + 1);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ============================ MMA issuer ============================
+    if (lane == 0 && t_begin < t_end) {
+      const uint32_t idesc = make_idesc_f16(128, 128);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      const uint32_t w0 = smem_u32(W0s), w2 = smem_u32(W2s), w4 = smem_u32(W4s);
+      const uint32_t a0t = smem_u32(A0t), a0f = smem_u32(A0f), a1 = smem_u32(A1), a2 = smem_u32(A2);
+      uint32_t an_f = 0;
+      auto gemm128 = [&](uint32_t d, uint32_t a_kb0, uint32_t a_kb1, uint32_t w) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, make_sw128_desc(a_kb0 + k * 32), make_sw128_desc(w + k * 32), idesc, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, make_sw128_desc(a_kb1 + k * 32), make_sw128_desc(w + 16384 + k * 32), idesc, 1u);
+      };
+      auto G0 = [&](long long t) {
+        const uint32_t n = (uint32_t)(t - t_begin);
+        if (t == t_begin || tile_bjb(t) != tile_bjb(t - 1)) {
+          mbar_wait(an_full, an_f & 1);
+          ++an_f;
+        }
+        mbar_wait(&a0_full[n & 1], (n >> 1) & 1);
+        tc_fence_after();
+        gemm128(D0, a0t + (n & 1) * 16384, a0f, w0);
+        umma_commit(d0_full);
+        if (t + 1 < t_end && tile_bjb(t + 1) != tile_bjb(t)) umma_commit(an_free);
+      };
+      G0(t_begin);
+      for (long long t = t_begin; t < t_end; ++t) {
+        const uint32_t ph = (uint32_t)(t - t_begin) & 1;
+        mbar_wait(a1_full, ph);
+        tc_fence_after();
+        gemm128(D1, a1, a1 + 16384, w2);
+        umma_commit(d1_full);
+        if (t + 1 < t_end) G0(t + 1);
+        mbar_wait(a2_full, ph);
+        tc_fence_after();
+        gemm128(D2, a2, a2 + 16384, w4);
+        umma_commit(d2_full);
+      }
+    }
+  } else {
+    // ============================ workers (128 threads) ============================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    auto store_chunks = [&](uint8_t* buf, const float* v /*[128]*/) {  // fp16, swizzled, two k-blocks x 8 chunks of row `row`
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float* p = v + kb * 64 + c * 8;
+          const uint4 u = make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
+          *reinterpret_cast<uint4*>(buf + kb * 16384 + sw128_chunk_off(row, c)) = u;
+        }
+      }
+    };
+    // per-tile k-block [emb(rel) 32 | onehot(bin) 22 | 0 x 10] of row `row`
+    auto build_a0 = [&](long long t) {
+      int jb, b;
+      const long long m = tile_m(t, jb, b);
+      const int j = jb * 128 + row;
+      uint8_t* dst = A0t + ((t - t_begin) & 1) * 16384;
+      uint4 ch[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ch[c] = make_uint4(0, 0, 0, 0);
+      if (j < a.N) {
+        const long long mj = (long long)b * a.N + j;
+        int rel = a.seq_idx[m] - a.seq_idx[mj] - a.rel_min;
+        rel = min(max(rel, 0), a.rel_count - 1);
+        const uint4* e = reinterpret_cast<const uint4*>(a.rel_tab + (long long)rel * EMB);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ch[c] = __ldg(e + c);
+        const float dx = a.sc_ca[m * 3 + 0] - a.sc_ca[mj * 3 + 0];
+        const float dy = a.sc_ca[m * 3 + 1] - a.sc_ca[mj * 3 + 1];
+        const float dz = a.sc_ca[m * 3 + 2] - a.sc_ca[mj * 3 + 2];
+        const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        int bin = -1;
+#pragma unroll
+        for (int k = 0; k < NBINS; ++k)
+          if (d > lower_s[k] && d < lower_s[k + 1]) bin = k;  // strict on both sides (data/utils.py:547-549)
+        if (bin >= 0) {
+          const uint32_t one = (bin & 1) ? 0x3C000000u : 0x00003C00u;  // fp16 1.0 in the high / low half
+          uint32_t w[12];
+#pragma unroll
+          for (int k = 0; k < 12; ++k) w[k] = (k == (bin >> 1)) ? one : 0u;
+          ch[4] = make_uint4(w[0], w[1], w[2], w[3]);
+          ch[5] = make_uint4(w[4], w[5], w[6], w[7]);
+          ch[6] = make_uint4(w[8], w[9], w[10], w[11]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + sw128_chunk_off(row, c)) = ch[c];
+      fence_proxy_async();
+      mbar_arrive(&a0_full[(t - t_begin) & 1]);
+    };
+
+    if (t_begin < t_end) build_a0(t_begin);
+    for (long long t = t_begin; t < t_end; ++t) {
+      const uint32_t ph = (uint32_t)(t - t_begin) & 1;
+      int jb, b;
+      const long long m = tile_m(t, jb, b);
+      const int j = jb * 128 + row;
+      if (t + 1 < t_end) build_a0(t + 1);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of PA_s are done
+      PA_s[threadIdx.x] = a.PA[m * 128 + threadIdx.x];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float v[128];
+      // ---- E0
+      mbar_wait(d0_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tmem_ld32(D0 + lane_base + q * 32, v + q * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+#pragma unroll
+      for (int n = 0; n < 128; ++n) v[n] = fmaxf(v[n] + PA_s[n], 0.f);
+      store_chunks(A1, v);
+      fence_proxy_async();
+      mbar_arrive(a1_full);
+      // ---- E1
+      mbar_wait(d1_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tmem_ld32(D1 + lane_base + q * 32, v + q * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+#pragma unroll
+      for (int n = 0; n < 128; ++n) v[n] = fmaxf(v[n] + b2_s[n], 0.f);
+      store_chunks(A2, v);
+      fence_proxy_async();
+      mbar_arrive(a2_full);
+      // ---- E2: LayerNorm + mask -> fp16 tile image (staged in A1, free since GEMM1 of this tile has completed) -> bulk store
+      mbar_wait(d2_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tmem_ld32(D2 + lane_base + q * 32, v + q * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      float s = 0.f;
+#pragma unroll
+      for (int n = 0; n < 128; ++n) {
+        v[n] += b4_s[n];
+        s += v[n];
+      }
+      const float mean = s * (1.f / 128.f);
+      float q2 = 0.f;
+#pragma unroll
+      for (int n = 0; n < 128; ++n) {
+        const float d = v[n] - mean;
+        q2 += d * d;
+      }
+      const float rstd = rsqrtf(q2 * (1.f / 128.f) + 1e-5f);
+      float mk = 0.f;
+      if (j < a.N) mk = a.mask[m] * a.mask[(long long)b * a.N + j];
+#pragma unroll
+      for (int n = 0; n < 128; ++n) v[n] = ((v[n] - mean) * rstd * g_s[n] + be_s[n]) * mk;
+      store_chunks(A1, v);
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * 32768LL);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(A1)), "r"(32768) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // A1 may be overwritten by the next tile's E0
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+inline size_t ee_smem_bytes() { return 1024 + 3 * (size_t)EE_W_BYTES + 3 * 16384 + 2 * 32768 + 10 * 8 + 16 + (5 * 128 + 24) * 4 + 64; }
+
+// per-residue features feat1d [B*N, F1] fp32 -> per-(b, j-block) fp16 k-block images [B][JB][128 rows][128 B] (columns >= F1 and rows >= N zero)
+__global__ void f_to_image_kernel(int B, int N, int JB, int F1, const float* __restrict__ feat1d, __half* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk
+  const long long total = (long long)B * JB * 128 * 8;
+  if (idx >= total) return;
+  const int c = (int)(idx & 7);
+  const int r = (int)((idx >> 3) & 127);
+  const long long tile = idx >> 10;  // b*JB + jb
+  const int jb = (int)(tile % JB);
+  const long long b = tile / JB;
+  const int j = jb * 128 + r;
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (j < N) {
+    const float* src = feat1d + (b * N + j) * F1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = c * 8 + 2 * e;
+      w[e] = pack_half2(k < F1 ? src[k] : 0.f, k + 1 < F1 ? src[k + 1] : 0.f);
+    }
+  }
+  uint8_t* dst = reinterpret_cast<uint8_t*>(img) + tile * 16384 + sw128_chunk_off(r, c);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void f32_to_f16_kernel(long long n, const float* __restrict__ x, __half* __restrict__ y) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) y[idx] = __float2half_rn(x[idx]);
+}
+
+}  // namespace tc
+}  // namespace fdpt

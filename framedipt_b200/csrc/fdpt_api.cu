@@ -17,6 +17,7 @@
 #include "kernels_ipa.cuh"
 #include "kernels_misc.cuh"
 #include "et_fused.cuh"
+#include "edge_embed_fused.cuh"
 #include "tc_linear.cuh"
 #include "gemm_tc.cuh"
 #include "backbone_tables.inc"
@@ -53,10 +54,9 @@ struct Workspace {
   char* base = nullptr;
   size_t bytes = 0;
   int capB = 0, capN = 0;
-  long long pair_chunk = 0;
   // node side
   float *node_feat, *feat1d, *node0, *node, *tmpA, *tmpB, *tmpC;  // tmp: [M,320]-capable
-  float *PA, *PB, *RelProj;
+  float *PA;  // edge embedder layer-1 per-residue partial A f_i + b0
   float *proj, *kn, *cat;  // IPA: fused projections [M,6816], -gamma/2 |k_pts|^2 [M,8], concat [M,2688]
   int ldS;
   float *tf_x, *qkv, *att_o;
@@ -64,8 +64,9 @@ struct Workspace {
   float *n_emb, *U, *V, *Pf, *Qf;
   float *tors_u;
   // pair side
-  float *zf32, *S, *h1, *h2, *ho;  // zf32: fp32 [P,128] scratch used only by the unit entry points
+  float* S;  // [B,H,N,ldS] attention logits / probabilities (IPA and sequence transformer)
   __half *z, *n_img;               // z: fp16 tile images [B][N][JB][32 KB]; n_img: [B][JB][32 KB]
+  __half *f_img, *rel_tab;         // edge embedder: f_j k-block images [B][JB][16 KB]; fp16 relative-offset embedding table
   int JB;
   // outputs / sampling state
   float *pred_rigids, *trans_score, *psi, *rig_cur, *rig_next, *sc_ca, *t_emb_b, *t32_b, *bb_tmp;
@@ -85,6 +86,7 @@ struct fdpt_ctx {
     const float *nW0, *nb0, *nW2, *nb2, *nW4, *nb4, *nln_g, *nln_b;
     const float *eW0, *eb0, *eW2, *eb2, *eW4, *eb4, *eln_g, *eln_b;
     const float *tW1, *tb1, *tW2, *tb2, *tWf, *tbf;
+    __half *imgE0 = nullptr, *imgE2 = nullptr, *imgE4 = nullptr;  // edge embedder weights as fp16 operand images (edge_embed_fused.cuh)
   } top;
   float *bin_lower = nullptr, *ideal = nullptr, *psi_frame = nullptr, *atom_mask = nullptr;
   Workspace ws;
@@ -279,15 +281,14 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
   CK(cudaDeviceSynchronize());
   if (w.base) CK(cudaFree(w.base));
   w = Workspace();
-  const size_t M = (size_t)B * N, P = M * N;
-  const long long chunk = (long long)std::min<size_t>(P, (size_t)1 << 20);
+  const size_t M = (size_t)B * N;
   const int R = 4 * 4096;  // capacity of the relative-offset table
   for (int pass = 0; pass < 2; ++pass) {
     char* p = pass ? w.base : nullptr;
     w.node_feat = carve<float>(p, M * 96); w.feat1d = carve<float>(p, M * 64);
     w.node0 = carve<float>(p, M * C_S); w.node = carve<float>(p, M * C_S);
     w.tmpA = carve<float>(p, M * ET_HID); w.tmpB = carve<float>(p, M * ET_HID); w.tmpC = carve<float>(p, M * ET_HID);
-    w.PA = carve<float>(p, M * C_Z); w.PB = carve<float>(p, M * C_Z); w.RelProj = carve<float>(p, (size_t)R * C_Z);
+    w.PA = carve<float>(p, M * C_Z);
     w.proj = carve<float>(p, M * PROJ_W); w.kn = carve<float>(p, M * NH);
     w.cat = carve<float>(p, M * CAT);
     w.tf_x = carve<float>(p, M * TF_D); w.qkv = carve<float>(p, M * 3 * TF_D); w.att_o = carve<float>(p, M * TF_D);
@@ -296,8 +297,8 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.Pf = carve<float>(p, M * C_Z); w.Qf = carve<float>(p, M * C_Z); w.tors_u = carve<float>(p, M * 2);
     const size_t JB = (size_t)(N + 127) / 128;
     w.z = carve<__half>(p, M * JB * 16384); w.n_img = carve<__half>(p, (size_t)B * JB * 16384);
-    w.zf32 = nullptr; w.S = carve<float>(p, M * NH * (size_t)((N + 3) & ~3));
-    w.h1 = carve<float>(p, (size_t)chunk * ET_HID); w.h2 = carve<float>(p, (size_t)chunk * ET_HID); w.ho = carve<float>(p, (size_t)chunk * C_Z);
+    w.f_img = carve<__half>(p, (size_t)B * JB * 8192); w.rel_tab = carve<__half>(p, (size_t)R * EMB);
+    w.S = carve<float>(p, M * NH * (size_t)((N + 3) & ~3));
     w.pred_rigids = carve<float>(p, M * 7); w.trans_score = carve<float>(p, M * 3); w.psi = carve<float>(p, M * 2);
     w.rig_cur = carve<float>(p, M * 7); w.rig_next = carve<float>(p, M * 7); w.sc_ca = carve<float>(p, M * 3);
     w.t_emb_b = carve<float>(p, (size_t)B * EMB); w.t32_b = carve<float>(p, B); w.bb_tmp = carve<float>(p, M * 15);
@@ -307,7 +308,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
       CK(cudaMalloc(&w.base, w.bytes));
     }
   }
-  w.capB = B; w.capN = N; w.pair_chunk = chunk; w.JB = (N + 127) / 128; w.ldS = (N + 3) & ~3;
+  w.capB = B; w.capN = N; w.JB = (N + 127) / 128; w.ldS = (N + 3) & ~3;
   CK(cudaMemset(w.z, 0, sizeof(__half) * M * w.JB * 16384));  // padded rows (j >= N) of the tile images stay zero
   return FDPT_OK;
 }
@@ -364,20 +365,25 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
   RET(lin(w.tmpA, C_S, T.nW2, C_S, T.nb2, w.tmpB, C_S, M, C_S, C_S, 1));
   RET(lin(w.tmpB, C_S, T.nW4, C_S, T.nb4, w.tmpA, C_S, M, C_S, C_S, 0));
   RET(layernorm<C_S>(ctx, st, w.tmpA, node_out, T.nln_g, T.nln_b, M, in->res_mask));
-  // edge layer-1 partials: W0 = [A (F1) | B (F1) | C (32) | D (22)]
+  // edge embedder (edge_embed_fused.cuh): W0 = [A (F1) | B (F1) | C (32) | D (22)];  PA_i = A f_i + b0 per residue (fp32 class),
+  // everything pair-sized inside one fused tcgen05 kernel
   RET(lin(w.feat1d, F1, T.eW0, EIN, T.eb0, w.PA, C_Z, M, C_Z, F1, 0));
-  RET(lin(w.feat1d, F1, T.eW0 + F1, EIN, nullptr, w.PB, C_Z, M, C_Z, F1, 0));
-  RET(lin(in->rel_emb, EMB, T.eW0 + 2 * F1, EIN, nullptr, w.RelProj, C_Z, in->rel_count, C_Z, EMB, 0));
-  for (long long r0 = 0; r0 < P; r0 += w.pair_chunk) {
-    const long long rows = std::min<long long>(w.pair_chunk, P - r0);
-    edge_l1_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(r0, rows, N, w.PA, w.PB, w.RelProj, in->seq_idx, in->rel_min, in->rel_count,
-                                                                in->sc_ca_t, ctx->bin_lower, T.eW0, EIN, 2 * F1 + EMB, w.h1);
+  {
+    const long long chunks = (long long)B * w.JB * 128 * 8;
+    tc::f_to_image_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(B, N, w.JB, F1, w.feat1d, w.f_img);
     LAUNCH_CHECK();
-    RET(lin(w.h1, C_Z, T.eW2, C_Z, T.eb2, w.h2, C_Z, rows, C_Z, C_Z, 1));
-    RET(lin(w.h2, C_Z, T.eW4, C_Z, T.eb4, w.ho, C_Z, rows, C_Z, C_Z, 0));
-    pair_ln_image_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.ho, z_out, T.eln_g, T.eln_b, rows, in->res_mask, N, w.JB, r0);
+    const long long nrel = (long long)in->rel_count * EMB;
+    tc::f32_to_f16_kernel<<<(unsigned)((nrel + 255) / 256), 256, 0, st>>>(nrel, in->rel_emb, w.rel_tab);
     LAUNCH_CHECK();
   }
+  tc::EeArgs a;
+  a.B = B; a.N = N; a.JB = w.JB; a.z_out = z_out; a.f_img = w.f_img; a.PA = w.PA; a.rel_tab = w.rel_tab; a.seq_idx = in->seq_idx;
+  a.rel_min = in->rel_min; a.rel_count = in->rel_count; a.sc_ca = in->sc_ca_t; a.bin_lower = ctx->bin_lower; a.b2 = T.eb2; a.b4 = T.eb4;
+  a.ln_g = T.eln_g; a.ln_b = T.eln_b; a.mask = in->res_mask; a.W0img = T.imgE0; a.W2img = T.imgE2; a.W4img = T.imgE4;
+  a.tiles = M * w.JB;
+  (void)P;
+  tc::ee_fused_kernel<<<(unsigned)std::min<long long>(ctx->num_sms, a.tiles), 192, tc::ee_smem_bytes(), st>>>(a);
+  LAUNCH_CHECK();
   return FDPT_OK;
 }
 
@@ -620,6 +626,7 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
   cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::et_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et_smem_bytes());
+  cudaFuncSetAttribute(tc::ee_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ee_smem_bytes());
   cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::tc_linear_smem_bytes(512));
   cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_tc_smem_bytes(128));
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
@@ -658,6 +665,9 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaFree(b.Wout_perm);
     cudaFree(b.imgWb);
   }
+  cudaFree(ctx->top.imgE0);
+  cudaFree(ctx->top.imgE2);
+  cudaFree(ctx->top.imgE4);
   cudaFree(ctx->ws.base);
   cudaFree(ctx->bin_lower);
   cudaFree(ctx->ideal);
@@ -708,6 +718,21 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
   const std::string tp = "score_model.torsion_pred";
   T.tW1 = P(tp + ".linear_1.weight"); T.tb1 = P(tp + ".linear_1.bias"); T.tW2 = P(tp + ".linear_2.weight"); T.tb2 = P(tp + ".linear_2.bias");
   T.tWf = P(tp + ".linear_final.weight"); T.tbf = P(tp + ".linear_final.bias");
+  {
+    const int F1 = f1_dim(ctx), EIN = 2 * F1 + EMB + NBINS;
+    if (!T.imgE0) CK(cudaMalloc(&T.imgE0, 32768));
+    if (!T.imgE2) CK(cudaMalloc(&T.imgE2, 32768));
+    if (!T.imgE4) CK(cudaMalloc(&T.imgE4, 32768));
+    auto pack = [&](const float* W, int ldw, int K, int Kvalid, __half* img) {
+      const long long chunks = (long long)C_Z * (K / 8);
+      tc::pack_weight_image_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(W, ldw, C_Z, K, Kvalid, img);
+    };
+    pack(T.eW0 + 2 * F1, EIN, 64, EMB + NBINS, T.imgE0);   // k-block 0: [C | D | 0]
+    pack(T.eW0 + F1, EIN, 64, F1, T.imgE0 + 8192);          // k-block 1: [B | 0]
+    pack(T.eW2, C_Z, C_Z, C_Z, T.imgE2);
+    pack(T.eW4, C_Z, C_Z, C_Z, T.imgE4);
+    CK(cudaGetLastError());
+  }
   for (int b = 0; b < NBLK; ++b) {
     BlockParams& p = ctx->blk[b];
     const std::string bs = std::to_string(b), ip = t + "ipa_" + bs;
