@@ -11,8 +11,9 @@
 //   GEMM1  D1 = h1 . W2^T                                                        E1: h2 = relu(D1 + b2)              -> fp16 A2
 //   GEMM2  D2 = h2 . W4^T                                                        E2: z0 = LN(D2 + b4) * m_i m_j      -> fp16 tile image
 //
-// All three weight matrices (96 KB as fp16 swizzled images) stay resident in shared memory.  Warps 0-3: workers (thread <-> pair row
-// <-> TMEM lane), warp 4: MMA issuer + TMEM owner, warp 5: loader.  MMA issue order G0(t+1) between G1(t) and G2(t), so the first GEMM
+// All three weight matrices (96 KB as fp16 swizzled images) stay resident in shared memory.  Warps 0-7: workers in two groups of 128
+// (thread <-> pair row <-> TMEM lane; group g owns columns [64g, 64g+64) = k-block g of every buffer it writes; group 0 builds the
+// idx_emb half of the per-tile feature block, group 1 the distogram half), warp 8: MMA issuer + TMEM owner, warp 9: loader.  MMA issue order G0(t+1) between G1(t) and G2(t), so the first GEMM
 // of the next tile is already done when the workers get there.  fp16 operands (10-bit mantissa = TF32 class, which the pair side
 // tolerates: SURVEY §7 hard part 1), fp32 accumulate, positional tables evaluated on the host and gathered here.
 #pragma once
@@ -40,8 +41,10 @@ struct EeArgs {
 };
 
 constexpr int EE_W_BYTES = 32768;
+constexpr int EE_WORKERS = 256;
+constexpr int EE_THREADS = EE_WORKERS + 64;
 
-__global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
+__global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* W0s = smem;                      // 32 KB
@@ -68,6 +71,8 @@ __global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
   float* g_s = b4_s + 128;
   float* be_s = g_s + 128;
   float* lower_s = be_s + 128;  // [24]
+  float* red_s = lower_s + 24;  // [2][128] LayerNorm partial sums of the two worker groups
+  float* red_q = red_s + 256;   // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long per = (a.tiles + gridDim.x - 1) / gridDim.x;
@@ -78,12 +83,12 @@ __global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
     mbar_init(w_full, 1);
     mbar_init(an_full, 1);
     mbar_init(an_free, 1);
-    mbar_init(&a0_full[0], 128);
-    mbar_init(&a0_full[1], 128);
+    mbar_init(&a0_full[0], EE_WORKERS);
+    mbar_init(&a0_full[1], EE_WORKERS);
     mbar_init(d0_full, 1);
-    mbar_init(a1_full, 128);
+    mbar_init(a1_full, EE_WORKERS);
     mbar_init(d1_full, 1);
-    mbar_init(a2_full, 128);
+    mbar_init(a2_full, EE_WORKERS);
     mbar_init(d2_full, 1);
     fence_barrier_init();
   }
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
     be_s[k] = a.ln_b[k];
   }
   if (threadIdx.x < 24) lower_s[threadIdx.x] = threadIdx.x < NBINS ? a.bin_lower[threadIdx.x] : 1e8f;  // [22] = top edge 1e8
-  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
     return (long long)b * a.N + i;
   };
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ============================ loader ============================
     if (lane == 0 && t_begin < t_end) {
       mbar_arrive_expect_tx(w_full, 3 * EE_W_BYTES);
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ============================ MMA issuer ============================
     if (lane == 0 && t_begin < t_end) {
       const uint32_t idesc = make_idesc_f16(128, 128);
@@ -174,56 +179,63 @@ __global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
       }
     }
   } else {
-    // ============================ workers (128 threads) ============================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    auto store_chunks = [&](uint8_t* buf, const float* v /*[128]*/) {  // fp16, swizzled, two k-blocks x 8 chunks of row `row`
+    // ============================ workers (2 groups x 128 threads) ============================
+    const int wg = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const int cg = wg * 64;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    auto store_half = [&](uint8_t* buf, const float* v /*[64]*/) {  // fp16, swizzled, k-block `wg`, 8 chunks of row `row`
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float* p = v + kb * 64 + c * 8;
-          const uint4 u = make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
-          *reinterpret_cast<uint4*>(buf + kb * 16384 + sw128_chunk_off(row, c)) = u;
-        }
+      for (int c = 0; c < 8; ++c) {
+        const float* p = v + c * 8;
+        const uint4 u = make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
+        *reinterpret_cast<uint4*>(buf + wg * 16384 + sw128_chunk_off(row, c)) = u;
       }
     };
-    // per-tile k-block [emb(rel) 32 | onehot(bin) 22 | 0 x 10] of row `row`
+    auto load_half = [&](uint32_t taddr, float* v /*[64]*/) {
+      tmem_ld32(taddr + lane_base + cg, v);
+      tmem_ld32(taddr + lane_base + cg + 32, v + 32);
+      tmem_ld_wait();
+    };
+    // per-tile k-block [emb(rel) 32 | onehot(bin) 22 | 0 x 10] of row `row`: group 0 writes chunks 0-3, group 1 chunks 4-7
     auto build_a0 = [&](long long t) {
       int jb, b;
       const long long m = tile_m(t, jb, b);
       const int j = jb * 128 + row;
       uint8_t* dst = A0t + ((t - t_begin) & 1) * 16384;
-      uint4 ch[8];
+      uint4 ch[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) ch[c] = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < 4; ++c) ch[c] = make_uint4(0, 0, 0, 0);
       if (j < a.N) {
         const long long mj = (long long)b * a.N + j;
-        int rel = a.seq_idx[m] - a.seq_idx[mj] - a.rel_min;
-        rel = min(max(rel, 0), a.rel_count - 1);
-        const uint4* e = reinterpret_cast<const uint4*>(a.rel_tab + (long long)rel * EMB);
+        if (wg == 0) {
+          int rel = a.seq_idx[m] - a.seq_idx[mj] - a.rel_min;
+          rel = min(max(rel, 0), a.rel_count - 1);
+          const uint4* e = reinterpret_cast<const uint4*>(a.rel_tab + (long long)rel * EMB);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) ch[c] = __ldg(e + c);
-        const float dx = a.sc_ca[m * 3 + 0] - a.sc_ca[mj * 3 + 0];
-        const float dy = a.sc_ca[m * 3 + 1] - a.sc_ca[mj * 3 + 1];
-        const float dz = a.sc_ca[m * 3 + 2] - a.sc_ca[mj * 3 + 2];
-        const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-        int bin = -1;
+          for (int c = 0; c < 4; ++c) ch[c] = __ldg(e + c);
+        } else {
+          const float dx = a.sc_ca[m * 3 + 0] - a.sc_ca[mj * 3 + 0];
+          const float dy = a.sc_ca[m * 3 + 1] - a.sc_ca[mj * 3 + 1];
+          const float dz = a.sc_ca[m * 3 + 2] - a.sc_ca[mj * 3 + 2];
+          const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+          int bin = -1;
 #pragma unroll
-        for (int k = 0; k < NBINS; ++k)
-          if (d > lower_s[k] && d < lower_s[k + 1]) bin = k;  // strict on both sides (data/utils.py:547-549)
-        if (bin >= 0) {
-          const uint32_t one = (bin & 1) ? 0x3C000000u : 0x00003C00u;  // fp16 1.0 in the high / low half
-          uint32_t w[12];
+          for (int k = 0; k < NBINS; ++k)
+            if (d > lower_s[k] && d < lower_s[k + 1]) bin = k;  // strict on both sides (data/utils.py:547-549)
+          if (bin >= 0) {
+            const uint32_t one = (bin & 1) ? 0x3C000000u : 0x00003C00u;  // fp16 1.0 in the high / low half
+            uint32_t w[12];
 #pragma unroll
-          for (int k = 0; k < 12; ++k) w[k] = (k == (bin >> 1)) ? one : 0u;
-          ch[4] = make_uint4(w[0], w[1], w[2], w[3]);
-          ch[5] = make_uint4(w[4], w[5], w[6], w[7]);
-          ch[6] = make_uint4(w[8], w[9], w[10], w[11]);
+            for (int k = 0; k < 12; ++k) w[k] = (k == (bin >> 1)) ? one : 0u;
+            ch[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            ch[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            ch[2] = make_uint4(w[8], w[9], w[10], w[11]);
+          }
         }
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + sw128_chunk_off(row, c)) = ch[c];
+      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + sw128_chunk_off(row, wg * 4 + c)) = ch[c];
       fence_proxy_async();
       mbar_arrive(&a0_full[(t - t_begin) & 1]);
     };
@@ -235,78 +247,76 @@ __global__ void __launch_bounds__(192, 1) ee_fused_kernel(EeArgs a) {
       const long long m = tile_m(t, jb, b);
       const int j = jb * 128 + row;
       if (t + 1 < t_end) build_a0(t + 1);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of PA_s are done
-      PA_s[threadIdx.x] = a.PA[m * 128 + threadIdx.x];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float v[128];
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers of PA_s are done
+      if (threadIdx.x < 128) PA_s[threadIdx.x] = a.PA[m * 128 + threadIdx.x];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float v[64];
       // ---- E0
       mbar_wait(d0_full, ph);
       tc_fence_after();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tmem_ld32(D0 + lane_base + q * 32, v + q * 32);
-      tmem_ld_wait();
+      load_half(D0, v);
       tc_fence_before();
 #pragma unroll
-      for (int n = 0; n < 128; ++n) v[n] = fmaxf(v[n] + PA_s[n], 0.f);
-      store_chunks(A1, v);
+      for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + PA_s[cg + n], 0.f);
+      store_half(A1, v);
       fence_proxy_async();
       mbar_arrive(a1_full);
       // ---- E1
       mbar_wait(d1_full, ph);
       tc_fence_after();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tmem_ld32(D1 + lane_base + q * 32, v + q * 32);
-      tmem_ld_wait();
+      load_half(D1, v);
       tc_fence_before();
 #pragma unroll
-      for (int n = 0; n < 128; ++n) v[n] = fmaxf(v[n] + b2_s[n], 0.f);
-      store_chunks(A2, v);
+      for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + b2_s[cg + n], 0.f);
+      store_half(A2, v);
       fence_proxy_async();
       mbar_arrive(a2_full);
       // ---- E2: LayerNorm + mask -> fp16 tile image (staged in A1, free since GEMM1 of this tile has completed) -> bulk store
       mbar_wait(d2_full, ph);
       tc_fence_after();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tmem_ld32(D2 + lane_base + q * 32, v + q * 32);
-      tmem_ld_wait();
+      load_half(D2, v);
       tc_fence_before();
       float s = 0.f;
 #pragma unroll
-      for (int n = 0; n < 128; ++n) {
-        v[n] += b4_s[n];
+      for (int n = 0; n < 64; ++n) {
+        v[n] += b4_s[cg + n];
         s += v[n];
       }
-      const float mean = s * (1.f / 128.f);
+      red_s[wg * 128 + row] = s;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mean = (red_s[row] + red_s[128 + row]) * (1.f / 128.f);
       float q2 = 0.f;
 #pragma unroll
-      for (int n = 0; n < 128; ++n) {
+      for (int n = 0; n < 64; ++n) {
         const float d = v[n] - mean;
         q2 += d * d;
       }
-      const float rstd = rsqrtf(q2 * (1.f / 128.f) + 1e-5f);
+      red_q[wg * 128 + row] = q2;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float rstd = rsqrtf((red_q[row] + red_q[128 + row]) * (1.f / 128.f) + 1e-5f);
       float mk = 0.f;
       if (j < a.N) mk = a.mask[m] * a.mask[(long long)b * a.N + j];
 #pragma unroll
-      for (int n = 0; n < 128; ++n) v[n] = ((v[n] - mean) * rstd * g_s[n] + be_s[n]) * mk;
-      store_chunks(A1, v);
+      for (int n = 0; n < 64; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
+      store_half(A1, v);
       fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) {
         uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * 32768LL);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(A1)), "r"(32768) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // A1 may be overwritten by the next tile's E0
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // A1 may be overwritten by the next tile's E0
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-inline size_t ee_smem_bytes() { return 1024 + 3 * (size_t)EE_W_BYTES + 3 * 16384 + 2 * 32768 + 10 * 8 + 16 + (5 * 128 + 24) * 4 + 64; }
+inline size_t ee_smem_bytes() { return 1024 + 3 * (size_t)EE_W_BYTES + 3 * 16384 + 2 * 32768 + 10 * 8 + 16 + (5 * 128 + 24 + 512) * 4 + 64; }
 
 // per-residue features feat1d [B*N, F1] fp32 -> per-(b, j-block) fp16 k-block images [B][JB][128 rows][128 B] (columns >= F1 and rows >= N zero)
 __global__ void f_to_image_kernel(int B, int N, int JB, int F1, const float* __restrict__ feat1d, __half* __restrict__ img) {

@@ -17,7 +17,10 @@
 //
 // TMEM: columns [0,384) = D2, [384,512) = D1 chunk stage / D3.   Shared memory (224 KB): A0z x2 (64 KB, bulk-copied,
 // double buffered across tiles), A0n (32 KB), two 32 KB chunk buffers (h1 / r2 / output staging), 4-stage weight ring.
-// Warps 0-3: epilogue workers (thread <-> tile row <-> TMEM lane); warp 4: MMA issuer + TMEM owner; warp 5: loader.
+// Warps 0-7: epilogue workers in two groups of 128 (thread <-> tile row <-> TMEM lane; group g owns columns [64g, 64g+64) of every
+// 128-column chunk = k-block g of the chunk it writes, which halves the latency of each epilogue step); warp 8: MMA issuer + TMEM
+// owner; warp 9: weight / z / n_j loader; warp 10: prefetches the per-tile epilogue vectors (U_i, Pf_i) of the next tile into a
+// double-buffered shared-memory slot so that the workers never wait on a global load between tiles.
 // All operands fp16 (10-bit mantissa = TF32 precision, which the pair side tolerates: SURVEY §7 hard part 1), fp32 accumulate.
 #pragma once
 #include "tc_common.cuh"
@@ -43,13 +46,22 @@ struct EtArgs {
   const __half* W2;             // image [6 kb][384][128 B]
   const __half* W3cat;          // image [10 kb][128][128 B]
   long long tiles;              // B*N*JB
+  long long* dbg;               // optional clock64 timeline of CTA 0 (bring-up / profiling aid): [tile][48] stamps, or nullptr
 };
+
+#define ET_TS(id)                                                                                  \
+  do {                                                                                             \
+    if (a.dbg && blockIdx.x == 0 && (t - t_begin) < 8) a.dbg[(t - t_begin) * 48 + (id)] = clock64(); \
+  } while (0)
 
 struct EtPhase {  // phase counters of one role
   uint32_t w = 0, az[2] = {0, 0}, an = 0, ds_full = 0, ds_empty = 0, buf_full[2] = {0, 0}, buf_free[2] = {0, 0}, d2_full = 0, d2_empty = 0;
 };
 
-__global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
+constexpr int ET_WORKERS = 256;
+constexpr int ET_THREADS = ET_WORKERS + 96;  // + MMA warp, weight loader warp, epilogue-vector prefetch warp
+
+__global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* A0z = smem;                                 // 2 x 32 KB
@@ -68,12 +80,17 @@ __global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
   uint64_t* buf_free = buf_full + 2;         // [2]
   uint64_t* d2_full = buf_free + 2;          // [1]
   uint64_t* d2_empty = d2_full + 1;          // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_empty + 1);
-  float* Ui_s = reinterpret_cast<float*>(tmem_slot + 4);  // [384]
-  float* Pf_s = Ui_s + 384;                                // [128]
-  float* b2_s = Pf_s + 128;                                // [384]
+  uint64_t* vec_full = d2_empty + 1;         // [2]
+  uint64_t* vec_free = vec_full + 2;         // [2]
+  uint64_t* stg_full = vec_free + 2;         // [1] all workers have written their part of the output tile into BUF[1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_full + 1);
+  float* Ui_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][384]
+  float* Pf_s = Ui_s + 2 * 384;                            // [2][128]
+  float* b2_s = Pf_s + 2 * 128;                            // [384]
   float* g_s = b2_s + 384;                                 // [128]
   float* be_s = g_s + 128;                                 // [128]
+  float* red_s = be_s + 128;                               // [2][128] LayerNorm partial sums of the two worker groups
+  float* red_q = red_s + 256;                              // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long per = (a.tiles + gridDim.x - 1) / gridDim.x;
@@ -88,14 +105,19 @@ __global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&az_full[s], 1);
       mbar_init(&az_empty[s], 1);
-      mbar_init(&buf_full[s], 128);
+      mbar_init(&buf_full[s], ET_WORKERS);
       mbar_init(&buf_free[s], 1);
     }
     mbar_init(an_full, 1);
     mbar_init(ds_full, 1);
-    mbar_init(ds_empty, 128);
+    mbar_init(ds_empty, ET_WORKERS);
     mbar_init(d2_full, 1);
-    mbar_init(d2_empty, 128);
+    mbar_init(d2_empty, ET_WORKERS);
+    mbar_init(stg_full, ET_WORKERS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&vec_full[s], 32);
+      mbar_init(&vec_free[s], ET_WORKERS);
+    }
     fence_barrier_init();
   }
   for (int k = threadIdx.x; k < 384; k += blockDim.x) b2_s[k] = a.b2[k];
@@ -103,7 +125,7 @@ __global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
     g_s[k] = a.ln_g[k];
     be_s[k] = a.ln_b[k];
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -111,16 +133,20 @@ __global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
   const uint32_t D2 = tmem_base, DS = tmem_base + 384;
 
   // tile -> (b*N+i, jb); the n_j image changes when (b, jb) changes. Tiles are ordered (b, jb, i) with i fastest.
-  auto tile_bjb = [&](long long t) -> long long { return t / a.N; };          // b*JB + jb
-  auto tile_m = [&](long long t, int& jb) -> long long {                      // returns b*N + i
-    const long long bjb = t / a.N;
-    const int i = (int)(t - bjb * a.N);
-    const long long b = bjb / a.JB;
-    jb = (int)(bjb - b * a.JB);
-    return b * a.N + i;
+  auto tile_bjb = [&](long long t) -> long long { return (long long)((unsigned)t / (unsigned)a.N); };  // b*JB + jb (tiles < 2^31)
+  auto tile_mb = [&](long long t, int& jb, int& b) -> long long {             // returns b*N + i
+    const unsigned bjb = (unsigned)t / (unsigned)a.N;
+    const int i = (int)((unsigned)t - bjb * (unsigned)a.N);
+    b = (int)(bjb / (unsigned)a.JB);
+    jb = (int)(bjb - (unsigned)b * (unsigned)a.JB);
+    return (long long)b * a.N + i;
+  };
+  auto tile_m = [&](long long t, int& jb) -> long long {
+    int b;
+    return tile_mb(t, jb, b);
   };
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ============================ loader ============================
     if (lane == 0 && t_begin < t_end) {
       uint32_t wit = 0;      // weight stage counter
@@ -168,7 +194,18 @@ __global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 10) {
+    // ============================ epilogue-vector prefetcher ============================
+    for (long long t = t_begin; t < t_end; ++t) {
+      const uint32_t n = (uint32_t)(t - t_begin), buf = n & 1;
+      mbar_wait(&vec_free[buf], ((n >> 1) & 1) ^ 1);
+      int jb;
+      const long long m = tile_m(t, jb);
+      for (int k = lane; k < 384; k += 32) Ui_s[buf * 384 + k] = a.Ui[m * 384 + k];
+      for (int k = lane; k < 128; k += 32) Pf_s[buf * 128 + k] = a.Pf[m * 128 + k];
+      mbar_arrive(&vec_full[buf]);
+    }
+  } else if (warp == 8) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, 128);
@@ -194,6 +231,7 @@ __global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
           ++an_f;
         }
         tc_fence_after();
+        ET_TS(0);
         const uint32_t az = smem_u32(A0z + zs * ET_TILE_BYTES), an = smem_u32(A0n);
         const uint32_t bufa[2] = {smem_u32(BUF), smem_u32(BUF + ET_TILE_BYTES)};
         auto a0_kb = [&](int kb) { return kb < 2 ? az + kb * 16384 : an + (kb - 2) * 16384; };
@@ -220,143 +258,183 @@ __global__ void __launch_bounds__(192, 1) et_fused_kernel(EtArgs a) {
           if (c == 2) umma_commit(d2_full);
         };
         G1(0);
+        ET_TS(1);
         G1(1);
+        ET_TS(2);
         G2(0);
+        ET_TS(3);
         G1(2);
+        ET_TS(4);
         G2(1);
+        ET_TS(5);
         G2(2);
+        ET_TS(6);
         // G3 static part: [z | n_j] . W3cat[:, 384:640]^T  -> DS (after E1(2) has drained it)
         mbar_wait(ds_empty, (ds_e & 1) ^ 1);
         ++ds_e;
         tc_fence_after();
         for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
         umma_commit(&az_empty[zs]);
+        ET_TS(7);
         for (int c = 0; c < 3; ++c) {
           const int b = c & 1;
           mbar_wait(&buf_full[b], bf[b] & 1);
           ++bf[b];
           tc_fence_after();
+          ET_TS(11 + c);
           for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, DS, false);
-          umma_commit(&buf_free[b]);
+          if (c != 1) umma_commit(&buf_free[b]);  // BUF[1] becomes the output staging buffer: released by worker thread 0
+          ET_TS(8 + c);
         }
         umma_commit(ds_full);
       }
     }
   } else {
-    // ============================ epilogue workers (128 threads) ============================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ============================ epilogue workers (2 groups x 128 threads) ============================
+    const int wg = warp >> 2;                         // column half owned by this group
+    const int row = (warp & 3) * 32 + lane;
+    const int cg = wg * 64;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ds_f = 0, fr[2] = {0, 0}, d2_f = 0;
     auto wait_free = [&](int b) {
       mbar_wait(&buf_free[b], (fr[b] & 1) ^ 1);
       ++fr[b];
     };
-    // relu(v + add) -> fp16 -> swizzled chunk buffer row `row` (two k-blocks x 8 chunks)
-    auto store_chunk = [&](uint8_t* buf, const float* v /*[128]*/) {
+    // 64 values -> fp16 -> k-block `wg` of a swizzled chunk buffer, row `row` (8 chunks of 16 bytes)
+    auto store_half = [&](uint8_t* buf, const float* v /*[64]*/) {
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float* p = v + kb * 64 + c * 8;
-          const uint4 u = make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
-          *reinterpret_cast<uint4*>(buf + kb * 16384 + sw128_chunk_off(row, c)) = u;
-        }
+      for (int c = 0; c < 8; ++c) {
+        const float* p = v + c * 8;
+        const uint4 u = make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
+        *reinterpret_cast<uint4*>(buf + wg * 16384 + sw128_chunk_off(row, c)) = u;
       }
     };
+    auto load_half = [&](uint32_t taddr, float* v /*[64]*/) {
+      tmem_ld32(taddr + lane_base + cg, v);
+      tmem_ld32(taddr + lane_base + cg + 32, v + 32);
+      tmem_ld_wait();
+    };
     for (long long t = t_begin; t < t_end; ++t) {
-      int jb;
-      const long long m = tile_m(t, jb);
+      int jb, bsamp;
+      const long long m = tile_mb(t, jb, bsamp);
       const int j = jb * 128 + row;
-      // per-tile epilogue vectors (same i for the whole tile)
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of Ui_s/Pf_s are done
-      for (int k = threadIdx.x; k < 384; k += 128) Ui_s[k] = a.Ui[m * 384 + k];
-      Pf_s[threadIdx.x] = a.Pf[m * 128 + threadIdx.x];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float v[128];
+      // per-tile epilogue vectors (same i for the whole tile), prefetched by warp 10
+      const uint32_t vn = (uint32_t)(t - t_begin), vbuf = vn & 1;
+      const float* Ui_t = Ui_s + vbuf * 384;
+      const float* Pf_t = Pf_s + vbuf * 128;
+      float mk = 0.f;
+      if (j < a.N) mk = a.mask[m] * a.mask[(long long)bsamp * a.N + j];
+      mbar_wait(&vec_full[vbuf], (vn >> 1) & 1);
+      float v[64];
+      if (threadIdx.x == 0) ET_TS(16);
       // ---- E1: three chunks of h1
       for (int c = 0; c < 3; ++c) {
+        if (c == 1 && threadIdx.x == 0 && t != t_begin) {  // BUF[1] staged the previous tile's output: its bulk store has finished reading by now
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&buf_free[1]);
+        }
         mbar_wait(ds_full, ds_f & 1);
         ++ds_f;
         tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_ld32(DS + lane_base + q * 32, v + q * 32);
-        tmem_ld_wait();
+        if (threadIdx.x == 0) ET_TS(17 + 3 * c);
+        load_half(DS, v);
         tc_fence_before();
         mbar_arrive(ds_empty);
 #pragma unroll
-        for (int n = 0; n < 128; ++n) v[n] = fmaxf(v[n] + Ui_s[c * 128 + n], 0.f);
+        for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + Ui_t[c * 128 + cg + n], 0.f);
+        if (threadIdx.x == 0) ET_TS(18 + 3 * c);
         wait_free(c & 1);
-        store_chunk(BUF + (c & 1) * ET_TILE_BYTES, v);
+        store_half(BUF + (c & 1) * ET_TILE_BYTES, v);
         fence_proxy_async();
         mbar_arrive(&buf_full[c & 1]);
+        if (threadIdx.x == 0) ET_TS(19 + 3 * c);
       }
       // ---- E2: three chunks of r2
       mbar_wait(d2_full, d2_f & 1);
       ++d2_f;
       tc_fence_after();
+      if (threadIdx.x == 0) ET_TS(26);
       for (int c = 0; c < 3; ++c) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_ld32(D2 + lane_base + c * 128 + q * 32, v + q * 32);
-        tmem_ld_wait();
+        load_half(D2 + c * 128, v);
         if (c == 2) {
           tc_fence_before();
           mbar_arrive(d2_empty);
         }
 #pragma unroll
-        for (int n = 0; n < 128; ++n) v[n] = fmaxf(v[n] + b2_s[c * 128 + n], 0.f);
+        for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + b2_s[c * 128 + cg + n], 0.f);
         wait_free(c & 1);
-        store_chunk(BUF + (c & 1) * ET_TILE_BYTES, v);
+        store_half(BUF + (c & 1) * ET_TILE_BYTES, v);
         fence_proxy_async();
         mbar_arrive(&buf_full[c & 1]);
+        if (threadIdx.x == 0) ET_TS(27 + c);
       }
-      // ---- E3: LayerNorm + mask -> fp16 tile image -> bulk store
+      // ---- E3: LayerNorm + mask -> fp16 tile image -> bulk store staged in BUF[1] (free: its last reader, G3 partial 1, completed
+      //      before D3 did).  Every thread computes the statistics of its whole row -- the other group's 64 columns are re-read from
+      //      TMEM once, with the own-half mean as shift for the single-pass variance -- so the two groups never synchronise.
       mbar_wait(ds_full, ds_f & 1);
       ++ds_f;
       tc_fence_after();
+      if (threadIdx.x == 0) ET_TS(30);
+      load_half(DS, v);
+      float s0 = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tmem_ld32(DS + lane_base + q * 32, v + q * 32);
-      tmem_ld_wait();
+      for (int n = 0; n < 64; ++n) {
+        v[n] += Pf_t[cg + n];
+        s0 += v[n];
+      }
+      const float shift = s0 * (1.f / 64.f);
+      float sd = 0.f, sq = 0.f;
+#pragma unroll
+      for (int n = 0; n < 64; ++n) {
+        const float d = v[n] - shift;
+        sd += d;
+        sq += d * d;
+      }
+      const int og = 64 - cg;  // first column of the other group's half
+      {
+        float w[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld32(DS + lane_base + og + 32 * h, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int n = 0; n < 32; ++n) {
+            const float d = w[n] + Pf_t[og + 32 * h + n] - shift;
+            sd += d;
+            sq += d * d;
+          }
+        }
+      }
       tc_fence_before();
       mbar_arrive(ds_empty);
-      float s = 0.f;
+      const float dm = sd * (1.f / 128.f);
+      const float mean = shift + dm;
+      const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - dm * dm, 0.f) + 1e-5f);
 #pragma unroll
-      for (int n = 0; n < 128; ++n) {
-        v[n] += Pf_s[n];
-        s += v[n];
-      }
-      const float mean = s * (1.f / 128.f);
-      float q2 = 0.f;
-#pragma unroll
-      for (int n = 0; n < 128; ++n) {
-        const float d = v[n] - mean;
-        q2 += d * d;
-      }
-      const float rstd = rsqrtf(q2 * (1.f / 128.f) + 1e-5f);
-      float mk = 0.f;
-      if (j < a.N) mk = a.mask[m] * a.mask[(m / a.N) * a.N + j];
-#pragma unroll
-      for (int n = 0; n < 128; ++n) v[n] = ((v[n] - mean) * rstd * g_s[n] + be_s[n]) * mk;
-      wait_free(0);
-      store_chunk(BUF, v);
+      for (int n = 0; n < 64; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
+      mbar_arrive(&vec_free[vbuf]);
+      if (threadIdx.x == 0) ET_TS(31);
+      store_half(BUF + ET_TILE_BYTES, v);
       fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_arrive(stg_full);
       if (threadIdx.x == 0) {
+        mbar_wait(stg_full, vn & 1);
         uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * (long long)ET_TILE_BYTES);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(BUF)), "r"(ET_TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(BUF + ET_TILE_BYTES)), "r"(ET_TILE_BYTES)
+                     : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(&buf_free[0]);
+        ET_TS(32);
       }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 inline size_t et_smem_bytes() {
-  return 1024 + 5 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 32 * 8 + 16 + (384 + 128 + 384 + 128 + 128) * 4 + 64;
+  return 1024 + 5 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 40 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 512) * 4 + 64 + 32;
 }
 
 // ---- layout helpers --------------------------------------------------------------------------------------------------

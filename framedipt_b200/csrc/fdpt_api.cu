@@ -94,6 +94,7 @@ struct fdpt_ctx {
   int max_smem_optin = 0, num_sms = 148;
   int gemm_tc = 1;   // node-side GEMMs on tcgen05 (3-term split TF32); 0 = SIMT fp32 kernel (bring-up / A-B switch)
   int mn_swap = 0;   // bring-up knob of the MN-major descriptor
+  long long* et_dbg = nullptr;  // optional clock64 timeline buffer of the EdgeTransition kernel (FDPT_OPT_ET_TIMELINE)
   // live profiling (event pairs per slot)
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int slot; };
@@ -382,7 +383,7 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
   a.ln_g = T.eln_g; a.ln_b = T.eln_b; a.mask = in->res_mask; a.W0img = T.imgE0; a.W2img = T.imgE2; a.W4img = T.imgE4;
   a.tiles = M * w.JB;
   (void)P;
-  tc::ee_fused_kernel<<<(unsigned)std::min<long long>(ctx->num_sms, a.tiles), 192, tc::ee_smem_bytes(), st>>>(a);
+  tc::ee_fused_kernel<<<(unsigned)std::min<long long>(ctx->num_sms, a.tiles), tc::EE_THREADS, tc::ee_smem_bytes(), st>>>(a);
   LAUNCH_CHECK();
   return FDPT_OK;
 }
@@ -456,8 +457,9 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   a.B = B; a.N = N; a.JB = w.JB; a.z_in = z_in; a.z_out = z_out; a.n_img = w.n_img; a.Ui = w.U; a.Pf = w.Pf; a.b2 = p.be2;
   a.ln_g = p.eln_g; a.ln_b = p.eln_b; a.mask = mask; a.W1cat = p.imgW1cat; a.W2 = p.imgW2; a.W3cat = p.imgW3cat;
   a.tiles = M * w.JB;
+  a.dbg = ctx->et_dbg;
   const int grid = (int)std::min<long long>(ctx->num_sms, a.tiles);
-  tc::et_fused_kernel<<<grid, 192, tc::et_smem_bytes(), st>>>(a);
+  tc::et_fused_kernel<<<grid, tc::ET_THREADS, tc::et_smem_bytes(), st>>>(a);
   LAUNCH_CHECK();
   return FDPT_OK;
 }
@@ -665,6 +667,7 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaFree(b.Wout_perm);
     cudaFree(b.imgWb);
   }
+  cudaFree(ctx->et_dbg);
   cudaFree(ctx->top.imgE0);
   cudaFree(ctx->top.imgE2);
   cudaFree(ctx->top.imgE4);
@@ -965,8 +968,21 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
   switch (option) {
     case FDPT_OPT_GEMM_TC: ctx->gemm_tc = value != 0; return FDPT_OK;
     case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
+    case FDPT_OPT_ET_TIMELINE:
+      if (value && !ctx->et_dbg) {
+        CK(cudaMalloc(&ctx->et_dbg, 8 * 48 * sizeof(long long)));
+        CK(cudaMemset(ctx->et_dbg, 0, 8 * 48 * sizeof(long long)));
+      }
+      return FDPT_OK;
     default: return fail(ctx, FDPT_ERR_INVALID, "unknown option %d", option);
   }
+}
+
+int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n) {
+  if (!ctx || !out || !ctx->et_dbg || n > 8 * 48) return FDPT_ERR_INVALID;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, ctx->et_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  return FDPT_OK;
 }
 
 int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, int lda, long long sa, const float* b, int ldb, long long sb,

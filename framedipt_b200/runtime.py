@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
         L.fdpt_matmul.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_int,
                                   C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]
         L.fdpt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.fdpt_debug_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
         L.fdpt_ipa.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.fdpt_edge_transition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.fdpt_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -293,6 +294,11 @@ class Context:
 
     def set_option(self, option: int, value: int):
         self._ck(lib().fdpt_set_option(self._h, option, value))
+
+    def debug_read(self, n: int = 8 * 48) -> np.ndarray:
+        buf = (C.c_int64 * n)()
+        self._ck(lib().fdpt_debug_read(self._h, buf, n))
+        return np.array(buf[:], np.int64)
 
     def matmul(self, a, b, b_kmajor=True, alpha=1.0):
         """Batched a[Bt,M,K] @ (b[Bt,N,K]^T if b_kmajor else b[Bt,K,N]) on the node-side GEMM kernel."""

@@ -176,8 +176,10 @@ int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float*
 int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, int lda, long long sa, const float* b,
                 int ldb, long long sb, int b_kmajor, float alpha, float* c, int ldc, long long sc, void* stream);
 /* bring-up / A-B switches (not needed by integrators) */
-enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1 };
+enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2 };
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
+/* clock64 timeline of CTA 0 of the last EdgeTransition kernel ([tile][48] stamps; profiling aid, needs FDPT_OPT_ET_TIMELINE) */
+int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n);
 /* same contract on the tcgen05 tensor cores (fp16 operands, fp32 accumulate): K multiple of 64 (<= 512), N multiple of 128.
  * Bring-up / unit entry of the building blocks the fused pair-side kernels use. */
 int fdpt_tc_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act,
