@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "edge_embed_fused.cuh"
 #include "tc_linear.cuh"
 #include "gemm_tc.cuh"
+#include "lin_tc.cuh"
 #include "backbone_tables.inc"
 
 using namespace fdpt;
@@ -94,6 +96,10 @@ struct fdpt_ctx {
   int max_smem_optin = 0, num_sms = 148;
   int gemm_tc = 1;   // node-side GEMMs on tcgen05 (3-term split TF32); 0 = SIMT fp32 kernel (bring-up / A-B switch)
   int mn_swap = 0;   // bring-up knob of the MN-major descriptor
+  int dbg_flags = 0; // bring-up knob of lin_tc: bit 0 skip the epilogue stores, bit 1 skip the MMAs
+  // Linear weights pre-split into fp16 hi|lo operand images (lin_tc.cuh), keyed by (weight pointer, row stride, N, K)
+  struct PackedW { __half* img; int nkb, n_tiles; };
+  std::map<std::tuple<const float*, int, int, int>, PackedW> packed;
   long long* et_dbg = nullptr;  // optional clock64 timeline buffer of the EdgeTransition kernel (FDPT_OPT_ET_TIMELINE)
   // live profiling (event pairs per slot)
   bool prof_on = false;
@@ -206,6 +212,21 @@ std::vector<std::pair<std::string, std::vector<int64_t>>> expected_params(const 
 // keys that exist in the reference state_dict but are never used by the forward pass
 bool is_unused_key(const std::string& k) {
   return k.find(".linear_rbf.") != std::string::npos || k.find("torsion_pred.linear_3.") != std::string::npos;
+}
+
+// Split a Linear weight (K <= 320) into its fp16 hi|lo operand images once; Lin finds it again by (pointer, stride, N, K).
+int pack_linear(fdpt_ctx* ctx, const float* W, int ldw, int N, int K) {
+  if (K > tc::LT_MAX_KB * 64) return FDPT_OK;
+  const auto key = std::make_tuple(W, ldw, N, K);
+  fdpt_ctx::PackedW& pw = ctx->packed[key];
+  pw.nkb = (K + 63) / 64;
+  pw.n_tiles = (N + 127) / 128;
+  const size_t bytes = (size_t)pw.n_tiles * pw.nkb * tc::LT_STAGE_BYTES;
+  if (!pw.img) CK(cudaMalloc(&pw.img, bytes));
+  const long long chunks = (long long)pw.n_tiles * pw.nkb * 128 * 8;
+  tc::pack_weight_split_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(W, ldw, N, K, pw.nkb, pw.n_tiles, pw.img);
+  CK(cudaGetLastError());
+  return FDPT_OK;
 }
 
 // One-time repack of the IPA parameters of a block (host side; kernels_ipa.cuh header describes the layouts).
@@ -321,6 +342,28 @@ struct Lin {
   // y[M,N] (ldc) = epi(x[M,K] (lda) @ W[N,K]^T (ldb))
   int operator()(const float* x, int lda, const float* W, int ldb, const float* bias, float* y, int ldc, long long M, int N, int K,
                  int relu = 0, const float* residual = nullptr, int ldr = 0, const float* rowmask = nullptr, int accumulate = 0) const {
+    if (ctx->gemm_tc && !accumulate && M > 0) {
+      auto it = ctx->packed.find(std::make_tuple(W, ldb, N, K));
+      if (it != ctx->packed.end()) {
+        const auto& pw = it->second;
+        tc::LinTcArgs a;
+        a.X = x; a.ldx = lda; a.M = (int)M; a.K = K; a.N = N; a.Wimg = pw.img; a.nkb = pw.nkb; a.n_tiles = pw.n_tiles;
+        const int m_tiles = (int)((M + 127) / 128);
+        a.tiles_per_cta = std::min(pw.n_tiles, std::max(1, (m_tiles * pw.n_tiles + ctx->num_sms - 1) / ctx->num_sms));
+        a.stg_cols = pw.nkb <= 4 ? 32 : 16;
+        a.units = std::min(8, (int)((ctx->max_smem_optin - tc::lin_tc_fixed_bytes(pw.nkb, a.stg_cols)) / tc::LT_UNIT_BYTES));
+        a.bias = bias; a.relu = relu; a.rowmask = rowmask; a.residual = residual; a.ldr = ldr; a.Y = y; a.ldy = ldc;
+        a.dbg_flags = ctx->dbg_flags;
+        a.x_vec = tc::aligned16(x, lda, 0, 0);
+        a.y_vec = 0;
+        dim3 grid(m_tiles, (pw.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta);
+        tc::lin_tc_kernel<<<grid, tc::LT_THREADS, tc::lin_tc_smem_bytes(pw.nkb, a.units, a.stg_cols), st>>>(a);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "lin_tc launch: %s", cudaGetErrorString(e));
+        return FDPT_OK;
+      }
+    }
     GemmArgs g;
     g.A = x; g.lda = lda; g.B = W; g.ldb = ldb; g.C = y; g.ldc = ldc; g.M = (int)M; g.N = N; g.K = K;
     g.bias = bias; g.relu = relu; g.residual = residual; g.ldr = ldr; g.rowmask = rowmask; g.accumulate = accumulate;
@@ -631,6 +674,7 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaFuncSetAttribute(tc::ee_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ee_smem_bytes());
   cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::tc_linear_smem_bytes(512));
   cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_tc_smem_bytes(128));
+  cudaFuncSetAttribute(tc::lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
   float lower[NBINS];
   {
@@ -668,6 +712,7 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaFree(b.imgWb);
   }
   cudaFree(ctx->et_dbg);
+  for (auto& kv : ctx->packed) cudaFree(kv.second.img);
   cudaFree(ctx->top.imgE0);
   cudaFree(ctx->top.imgE2);
   cudaFree(ctx->top.imgE4);
@@ -783,6 +828,28 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
       pack(p.Wef, ET_HID, C_Z, 128, p.imgW3cat + (size_t)6 * C_Z * 64);
       pack(p.Wef + 2 * C_Z, ET_HID, C_Z, 128, p.imgW3cat + (size_t)8 * C_Z * 64);
       CK(cudaGetLastError());
+    }
+  }
+  {  // pre-split every Linear weight the node side multiplies with (lin_tc.cuh)
+    const int F1 = f1_dim(ctx), FN = F1 + EMB, EIN = 2 * F1 + EMB + NBINS;
+    RET(pack_linear(ctx, T.nW0, FN, C_S, FN)); RET(pack_linear(ctx, T.nW2, C_S, C_S, C_S)); RET(pack_linear(ctx, T.nW4, C_S, C_S, C_S));
+    RET(pack_linear(ctx, T.eW0, EIN, C_Z, F1));
+    RET(pack_linear(ctx, T.tW1, C_S, C_S, C_S)); RET(pack_linear(ctx, T.tW2, C_S, C_S, C_S)); RET(pack_linear(ctx, T.tWf, C_S, 2, C_S));
+    for (int b = 0; b < NBLK; ++b) {
+      BlockParams& p = ctx->blk[b];
+      RET(pack_linear(ctx, p.Wcat, C_S, PROJ_W, C_S)); RET(pack_linear(ctx, p.Wskip, C_S, C_SKIP, C_S));
+      for (int l = 0; l < TF_LAYERS; ++l) {
+        auto& L = p.tf[l];
+        RET(pack_linear(ctx, L.Win, TF_D, 3 * TF_D, TF_D)); RET(pack_linear(ctx, L.Wo, TF_D, TF_D, TF_D));
+        RET(pack_linear(ctx, L.W1, TF_D, TF_D, TF_D)); RET(pack_linear(ctx, L.W2, TF_D, TF_D, TF_D));
+      }
+      RET(pack_linear(ctx, p.Wpost, TF_D, C_S, TF_D));
+      RET(pack_linear(ctx, p.Wt1, C_S, C_S, C_S)); RET(pack_linear(ctx, p.Wt2, C_S, C_S, C_S)); RET(pack_linear(ctx, p.Wt3, C_S, C_S, C_S));
+      RET(pack_linear(ctx, p.Wbb, C_S, 6, C_S));
+      if (b < NBLK - 1) {
+        RET(pack_linear(ctx, p.Wie, C_S, C_Z, C_S)); RET(pack_linear(ctx, p.We1 + C_Z, ET_HID, ET_HID, C_Z));
+        RET(pack_linear(ctx, p.Wef + C_Z, ET_HID, C_Z, C_Z));
+      }
     }
   }
   CK(cudaDeviceSynchronize());
@@ -959,6 +1026,13 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
 int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act, float* y, void* stream) {
   if (!ctx || !x || !w || !y) return FDPT_ERR_INVALID;
   cudaSetDevice(ctx->device);
+  // unit entry: Linear layers run on lin_tc with pre-split weights, so split this weight too (re-done on every call: the caller's
+  // buffer is not a registered parameter and may have changed)
+  if (ctx->gemm_tc) {
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    RET(pack_linear(ctx, w, K, N, K));
+    CK(cudaDeviceSynchronize());
+  }
   Lin lin{ctx, (cudaStream_t)stream};
   return lin(x, K, w, K, bias, y, N, M, N, K, act);
 }
@@ -968,6 +1042,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
   switch (option) {
     case FDPT_OPT_GEMM_TC: ctx->gemm_tc = value != 0; return FDPT_OK;
     case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
+    case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {
         CK(cudaMalloc(&ctx->et_dbg, 8 * 48 * sizeof(long long)));
@@ -994,6 +1069,29 @@ int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, i
   g.M = M; g.N = N; g.K = K; g.alpha = alpha;
   CK(gemm_dispatch(ctx, g, b_kmajor != 0, batch, (cudaStream_t)stream));
   ctx->launches++;
+  return FDPT_OK;
+}
+
+int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, float* y, int reps,
+                      float* ms_per_call) {
+  if (!ctx || !x || !w || !y || !ms_per_call || reps <= 0) return FDPT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CK(cudaDeviceSynchronize());
+  RET(pack_linear(ctx, w, K, N, K));
+  Lin lin{ctx, nullptr};
+  for (int i = 0; i < 3; ++i) RET(lin(x, K, w, K, bias, y, N, M, N, K, 0));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, nullptr));
+  for (int i = 0; i < reps; ++i) RET(lin(x, K, w, K, bias, y, N, M, N, K, 0));
+  CK(cudaEventRecord(e1, nullptr));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_call = ms / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return FDPT_OK;
 }
 

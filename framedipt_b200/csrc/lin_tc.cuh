@@ -1,0 +1,260 @@
+// lin_tc.cuh — fp32-class Linear layer  Y[M,N] = epi(X[M,K] @ W[N,K]^T)  for the node side, K <= 320, weights pre-packed.
+//
+// Same arithmetic as gemm_tc.cuh (2-term split fp16 with scaled low part, two TMEM accumulators; fp32-class accuracy), but organised
+// around what bounds the node-side GEMMs on B200: L2 -> SM operand traffic and per-CTA fixed latency, not tensor throughput.
+//   * weights are split ONCE (fdpt_finalize_params) into fp16 hi | lo operand images, laid out [n-tile][k-block][hi|lo][128 rows][128 B]
+//     so that one 32 KB bulk copy (TMA unit, no thread work, deep prefetch) lands a ready-to-multiply stage;
+//   * a CTA owns one 128-row tile of X for a contiguous range of n-tiles: X is loaded and split once into a resident operand image
+//     (K/64 k-blocks x 32 KB) and every weight stage streams past it ("A-stationary"), instead of re-loading and re-splitting X for
+//     every 64- or 128-column tile;
+//   * two accumulator pairs in TMEM (2 x (main 128 + cross 128) = 512 columns): the epilogue of n-tile t overlaps the MMAs of t+1;
+//   * the epilogue transposes each warp's 32 x 32 (or 32 x 16) accumulator block through a private padded shared-memory patch so that
+//     global stores are row-contiguous 128-byte (64-byte) segments: with the TMEM-native "one thread = one row" mapping every store
+//     instruction touched 32 different lines and the stores alone took 42 of 75 us on the IPA projection GEMM.
+// Warps 0-7: X staging, then epilogues (warps w and w+4 share TMEM lanes, 64 columns each); warp 8: MMA issuer + TMEM owner;
+// warp 9: weight loader.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace fdpt {
+namespace tc {
+
+constexpr int LT_STAGE_BYTES = 32768;   // one (n-tile, k-block): hi 16 KB | lo 16 KB
+constexpr int LT_UNIT_BYTES = 16384;    // ring granularity: the hi and the lo image of a k-block are separate ring units
+constexpr int LT_WORKERS = 256;
+constexpr int LT_THREADS = LT_WORKERS + 64;
+constexpr int LT_MAX_KB = 5;            // K <= 320
+
+struct LinTcArgs {
+  const float* X; int ldx; int M, K, N;
+  const __half* Wimg;          // [n_tiles][nkb][2][128][64] fp16 (swizzled rows)
+  int nkb, n_tiles, tiles_per_cta, units;   // units: 16 KB ring slots (<= 8)
+  int stg_cols;                             // epilogue staging width per warp: 32 or 16 columns
+  const float* bias; int relu;
+  const float* rowmask;
+  const float* residual; int ldr;
+  float* Y; int ldy;
+  int x_vec, y_vec;
+  int dbg_flags;               // bring-up: bit 0 skip the epilogue stores, bit 1 skip the MMAs
+};
+
+// Epilogue helper: this warp holds a 32 x 32 block with thread = row (v[j] = column j).  Transpose SW columns at a time through the
+// warp's private padded patch and store row-contiguous segments (lane = column): bias / relu / row mask / residual applied on the way.
+template <int SW>
+FDPT_DEVINL void store_transposed(const LinTcArgs& a, const float (&v)[32], float* stg, int lane, int mw, int c0) {
+  constexpr int SLD = SW + 1, RPI = 32 / SW, NIT = 32 / RPI;  // rows per store instruction, store instructions per pass
+  const int lrow = lane / SW, lcol = lane % SW;
+#pragma unroll
+  for (int h0 = 0; h0 < 32; h0 += SW) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SW; ++j) stg[lane * SLD + j] = v[h0 + j];
+    __syncwarp();
+    const int col = c0 + h0 + lcol;
+    const bool cok = col < a.N;
+    const float bs = (a.bias && cok) ? __ldg(a.bias + col) : 0.f;
+    float x[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) x[it] = stg[(it * RPI + lrow) * SLD + lcol] + bs;
+    if (a.relu) {
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) x[it] = fmaxf(x[it], 0.f);
+    }
+    if (a.rowmask) {
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int m = mw + it * RPI + lrow;
+        x[it] *= (m < a.M) ? __ldg(a.rowmask + m) : 0.f;
+      }
+    }
+    float* yp = a.Y + (long long)(mw + lrow) * a.ldy + col;
+    if (a.residual) {
+      const float* rp = a.residual + (long long)(mw + lrow) * a.ldr + col;
+      float rr[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) rr[it] = (cok && mw + it * RPI + lrow < a.M) ? rp[(long long)it * RPI * a.ldr] : 0.f;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) x[it] += rr[it];
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it)
+      if (cok && mw + it * RPI + lrow < a.M) yp[(long long)it * RPI * a.ldy] = x[it];
+  }
+}
+
+__global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Aimg = smem;                                        // nkb x [hi 16 KB | lo 16 KB]
+  uint8_t* Wst = Aimg + (size_t)a.nkb * LT_STAGE_BYTES;        // units x 16 KB
+  float* Stg = reinterpret_cast<float*>(Wst + (size_t)a.units * LT_UNIT_BYTES);  // 8 warps x 32 rows x (stg_cols + 1) floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Stg + 8 * 32 * (a.stg_cols + 1));
+  uint64_t* w_full = bars;                 // [8]
+  uint64_t* w_empty = bars + 8;            // [8]
+  uint64_t* a_full = bars + 16;            // [LT_MAX_KB]
+  uint64_t* acc_full = a_full + LT_MAX_KB; // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int m0 = blockIdx.x * 128;
+  const int nt_begin = blockIdx.y * a.tiles_per_cta;
+  const int nt_end = min(a.n_tiles, nt_begin + a.tiles_per_cta);
+  const int ntiles = nt_end - nt_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int k = 0; k < LT_MAX_KB; ++k) mbar_init(&a_full[k], LT_WORKERS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], LT_WORKERS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    // ============================ weight loader ============================
+    if (lane == 0) {
+      int it = 0;  // ring unit counter: 2 per k-block (hi, lo)
+      for (int nt = nt_begin; nt < nt_end; ++nt)
+        for (int kb = 0; kb < a.nkb; ++kb)
+          for (int hl = 0; hl < 2; ++hl, ++it) {
+            const int s = it % a.units;
+            mbar_wait(&w_empty[s], ((it / a.units) & 1) ^ 1);
+            mbar_arrive_expect_tx(&w_full[s], LT_UNIT_BYTES);
+            bulk_g2s(Wst + (size_t)s * LT_UNIT_BYTES,
+                     reinterpret_cast<const uint8_t*>(a.Wimg) + ((size_t)nt * a.nkb + kb) * LT_STAGE_BYTES + hl * LT_UNIT_BYTES, LT_UNIT_BYTES,
+                     &w_full[s]);
+          }
+    }
+  } else if (warp == 8) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 128);
+      int it = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int as = t & 1;
+        mbar_wait(&acc_empty[as], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc_main = tmem_base + as * 256, acc_x = acc_main + 128;
+        for (int kb = 0; kb < a.nkb; ++kb, it += 2) {
+          if (t == 0) mbar_wait(&a_full[kb], 0);
+          const int sh = it % a.units, sl = (it + 1) % a.units;
+          mbar_wait(&w_full[sh], (it / a.units) & 1);
+          mbar_wait(&w_full[sl], ((it + 1) / a.units) & 1);
+          tc_fence_after();
+          const uint32_t ah = smem_u32(Aimg + (size_t)kb * LT_STAGE_BYTES), al = ah + 16384;
+          const uint32_t bh = smem_u32(Wst + (size_t)sh * LT_UNIT_BYTES), bl = smem_u32(Wst + (size_t)sl * LT_UNIT_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dah = make_sw128_desc(ah + k * 32), dal = make_sw128_desc(al + k * 32);
+            const uint64_t dbh = make_sw128_desc(bh + k * 32), dbl = make_sw128_desc(bl + k * 32);
+            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+            if (a.dbg_flags & 2) continue;
+            umma_f16(acc_x, dal, dbh, idesc, first);
+            umma_f16(acc_x, dah, dbl, idesc, 1u);
+            umma_f16(acc_main, dah, dbh, idesc, first);
+          }
+          umma_commit(&w_empty[sh]);
+          umma_commit(&w_empty[sl]);
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ============================ workers: stage X once, then epilogues ============================
+    {
+      ChunkPlan pa;
+      const int r0 = tid >> 3, c = tid & 7;
+      pa.src = a.X + (long long)(m0 + r0) * a.ldx + 8 * c;
+      pa.it_stride = 32LL * a.ldx; pa.kb_stride = GT_KB;
+      pa.dst = sw128_chunk_off(r0, c); pa.dst_it_stride = 32 * 128; pa.lo_off = 16384;
+      pa.iters = 4; pa.kmajor = 1;
+      pa.row0 = m0 + r0; pa.row_step = 32; pa.row_lim = a.M; pa.col0 = 8 * c; pa.col_lim = a.K; pa.vec = a.x_vec;
+      RegTile ta[2];
+      load_tile(pa, 0, ta[0]);
+      for (int kb = 0; kb < a.nkb; kb += 2) {
+        if (kb + 1 < a.nkb) load_tile(pa, kb + 1, ta[1]);
+        store_tile(pa, Aimg + (size_t)kb * LT_STAGE_BYTES, ta[0]);
+        fence_proxy_async();
+        mbar_arrive(&a_full[kb]);
+        if (kb + 1 < a.nkb) {
+          if (kb + 2 < a.nkb) load_tile(pa, kb + 2, ta[0]);
+          store_tile(pa, Aimg + (size_t)(kb + 1) * LT_STAGE_BYTES, ta[1]);
+          fence_proxy_async();
+          mbar_arrive(&a_full[kb + 1]);
+        }
+      }
+    }
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int c_half = (warp >> 2) * 64;
+    const int sw = a.stg_cols, sld = sw + 1;           // staging width / padded row stride
+    float* stg = Stg + warp * 32 * sld;                // this warp's private patch
+    const int mw = m0 + (warp & 3) * 32;               // first row of this warp's block
+    for (int t = 0; t < ntiles; ++t) {
+      const int as = t & 1;
+      const int n0 = (nt_begin + t) * 128;
+      mbar_wait(&acc_full[as], (t >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int cb = c_half + q * 32;
+        float v[32], x2[32];
+        tmem_ld32(tmem_base + lane_base + as * 256 + cb, v);
+        tmem_ld32(tmem_base + lane_base + as * 256 + 128 + cb, x2);
+        tmem_ld_wait();
+        if (q == 1) {  // both halves of this thread's columns are in registers: the accumulator pair can be overwritten
+          tc_fence_before();
+          mbar_arrive(&acc_empty[as]);
+        }
+        if (n0 + cb >= a.N || (a.dbg_flags & 1)) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
+        if (sw == 32)
+          store_transposed<32>(a, v, stg, lane, mw, n0 + cb);
+        else
+          store_transposed<16>(a, v, stg, lane, mw, n0 + cb);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+inline size_t lin_tc_fixed_bytes(int nkb, int stg_cols) {
+  return 1024 + (size_t)nkb * LT_STAGE_BYTES + (size_t)8 * 32 * (stg_cols + 1) * 4 + (16 + LT_MAX_KB + 4) * 8 + 64;
+}
+inline size_t lin_tc_smem_bytes(int nkb, int units, int stg_cols) { return lin_tc_fixed_bytes(nkb, stg_cols) + (size_t)units * LT_UNIT_BYTES; }
+
+// W[n, k] fp32 (row stride ldw) -> split operand images [n_tiles][nkb][hi|lo][128 rows][128 B]; rows >= N and columns >= K are zero.
+__global__ void pack_weight_split_kernel(const float* __restrict__ W, int ldw, int N, int K, int nkb, int n_tiles, __half* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-element chunk
+  const long long total = (long long)n_tiles * nkb * 128 * 8;
+  if (idx >= total) return;
+  const int c = (int)(idx & 7);
+  const int r = (int)((idx >> 3) & 127);
+  const long long st = idx >> 10;  // nt * nkb + kb
+  const int kb = (int)(st % nkb);
+  const int nt = (int)(st / nkb);
+  const int n = nt * 128 + r, k0 = kb * 64 + c * 8;
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = (n < N && k0 + e < K) ? W[(long long)n * ldw + k0 + e] : 0.f;
+  uint4 hi, lo;
+  split8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), hi, lo);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(img) + st * LT_STAGE_BYTES + sw128_chunk_off(r, c);
+  *reinterpret_cast<uint4*>(dst) = hi;
+  *reinterpret_cast<uint4*>(dst + 16384) = lo;
+}
+
+}  // namespace tc
+}  // namespace fdpt

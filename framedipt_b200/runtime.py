@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
         L.fdpt_matmul.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_int,
                                   C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]
         L.fdpt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.fdpt_bench_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.POINTER(C.c_float)]
         L.fdpt_debug_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
         L.fdpt_ipa.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.fdpt_edge_transition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
@@ -294,6 +296,15 @@ class Context:
 
     def set_option(self, option: int, value: int):
         self._ck(lib().fdpt_set_option(self._h, option, value))
+
+    def bench_linear(self, x, w, b, reps=20) -> float:
+        """us per launch of the Linear kernel on x[M,K] @ w[N,K]^T (weights split once)."""
+        M, K = x.shape
+        Nn = w.shape[0]
+        y = torch.empty(M, Nn, device=self.device)
+        ms = C.c_float(0)
+        self._ck(lib().fdpt_bench_linear(self._h, M, Nn, K, _ptr(x), _ptr(w), _ptr(b), _ptr(y), reps, C.byref(ms)))
+        return ms.value * 1e3
 
     def debug_read(self, n: int = 8 * 48) -> np.ndarray:
         buf = (C.c_int64 * n)()

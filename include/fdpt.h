@@ -175,8 +175,11 @@ int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float*
  * or the SIMT fp32 kernel for N < 16 / when FDPT_OPT_GEMM_TC is 0. */
 int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, int lda, long long sa, const float* b,
                 int ldb, long long sb, int b_kmajor, float alpha, float* c, int ldc, long long sc, void* stream);
+/* times `reps` back-to-back launches of the Linear kernel (weights split once) with CUDA events: micro-benchmark aid */
+int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, float* y, int reps,
+                      float* ms_per_call);
 /* bring-up / A-B switches (not needed by integrators) */
-enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2 };
+enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3 };
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
 /* clock64 timeline of CTA 0 of the last EdgeTransition kernel ([tile][48] stamps; profiling aid, needs FDPT_OPT_ET_TIMELINE) */
 int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n);
