@@ -61,6 +61,68 @@ FDPT_DEVINL void split8(const float4& x0, const float4& x1, uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// ---- epilogue: row-contiguous global stores --------------------------------------------------------------------------
+// With the TMEM-native mapping (thread = accumulator row) every store instruction of a warp touches 32 different lines.  Each warp
+// therefore transposes its 32 x 32 block SW columns at a time through a private padded shared-memory patch and stores with
+// lane = column: 128-byte (SW = 32) or 2 x 64-byte (SW = 16) segments per instruction; bias / relu / row mask / residual on the way.
+struct EpiArgs {
+  int M, N;
+  float alpha;
+  const float* bias; int relu;
+  const float* rowmask;
+  const float* residual; int ldr;
+  int accumulate;
+  float* Y; int ldy;
+};
+template <int SW>
+FDPT_DEVINL void store_transposed(const EpiArgs& a, const float (&v)[32], float* stg, int lane, int mw, int c0) {
+  constexpr int SLD = SW + 1, RPI = 32 / SW, NIT = 32 / RPI;  // rows per store instruction, store instructions per pass
+  const int lrow = lane / SW, lcol = lane % SW;
+#pragma unroll
+  for (int h0 = 0; h0 < 32; h0 += SW) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SW; ++j) stg[lane * SLD + j] = v[h0 + j];
+    __syncwarp();
+    const int col = c0 + h0 + lcol;
+    const bool cok = col < a.N;
+    const float bs = (a.bias && cok) ? __ldg(a.bias + col) : 0.f;
+    float x[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) x[it] = fmaf(a.alpha, stg[(it * RPI + lrow) * SLD + lcol], bs);
+    if (a.relu) {
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) x[it] = fmaxf(x[it], 0.f);
+    }
+    if (a.rowmask) {
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int m = mw + it * RPI + lrow;
+        x[it] *= (m < a.M) ? __ldg(a.rowmask + m) : 0.f;
+      }
+    }
+    float* yp = a.Y + (long long)(mw + lrow) * a.ldy + col;
+    if (a.residual) {
+      const float* rp = a.residual + (long long)(mw + lrow) * a.ldr + col;
+      float rr[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) rr[it] = (cok && mw + it * RPI + lrow < a.M) ? rp[(long long)it * RPI * a.ldr] : 0.f;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) x[it] += rr[it];
+    }
+    if (a.accumulate) {
+      float rr[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) rr[it] = (cok && mw + it * RPI + lrow < a.M) ? yp[(long long)it * RPI * a.ldy] : 0.f;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) x[it] += rr[it];
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it)
+      if (cok && mw + it * RPI + lrow < a.M) yp[(long long)it * RPI * a.ldy] = x[it];
+  }
+}
+
 // per-thread copy plan of one operand: `iters` 8-element chunks per k-block, affine in the iteration index
 struct ChunkPlan {
   const float* src;        // first chunk of k-block 0
@@ -223,52 +285,23 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(GemmTcArgs a) {
     // ============================ epilogue ============================
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int r = (warp & 3) * 32 + lane, m = m0 + r;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const float rm = (g.rowmask && m < g.M) ? g.rowmask[m] : 1.f;
     const int c_begin = (warp >> 2) * (BN / 2), c_end = c_begin + BN / 2;
+    // all MMAs have completed, so the operand ring is idle: its first bytes become the per-warp transposition patches
+    float* stg = reinterpret_cast<float*>(smem) + warp * 32 * 33;
+    const int mw = m0 + (warp & 3) * 32;
+    EpiArgs ep;
+    ep.M = g.M; ep.N = g.N; ep.alpha = g.alpha; ep.bias = g.bias; ep.relu = g.relu; ep.rowmask = g.rowmask; ep.residual = g.residual;
+    ep.ldr = g.ldr; ep.accumulate = g.accumulate; ep.Y = C; ep.ldy = g.ldc;
     for (int cb = c_begin; cb < c_end; cb += 32) {
       float v[32], x2[32];
       tmem_ld32(tmem_base + lane_base + cb, v);
       tmem_ld32(tmem_base + lane_base + BN + cb, x2);
       tmem_ld_wait();
-      if (m >= g.M || n0 + cb >= g.N) continue;
-      const int nv = min(32, g.N - (n0 + cb));
-      float* crow = C + (long long)m * g.ldc + n0 + cb;
-      const float* rrow = g.residual ? g.residual + (long long)m * g.ldr + n0 + cb : nullptr;
+      if (n0 + cb >= g.N) continue;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = g.alpha * fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
-        if (g.bias && j < nv) x += __ldg(g.bias + n0 + cb + j);
-        if (g.relu) x = fmaxf(x, 0.f);
-        if (g.rowmask) x *= rm;
-        v[j] = x;
-      }
-      if (nv == 32 && a.c_vec) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (rrow) {
-            const float4 q = *reinterpret_cast<const float4*>(rrow + j);
-            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-          }
-          if (g.accumulate) {
-            const float4 q = *reinterpret_cast<const float4*>(crow + j);
-            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-          }
-          *reinterpret_cast<float4*>(crow + j) = o;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nv) {
-            float x = v[j];
-            if (rrow) x += rrow[j];
-            if (g.accumulate) x += crow[j];
-            crow[j] = x;
-          }
-        }
-      }
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
+      store_transposed<32>(ep, v, stg, lane, mw, n0 + cb);
     }
   }
   tc_fence_before();

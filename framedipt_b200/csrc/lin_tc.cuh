@@ -38,50 +38,6 @@ struct LinTcArgs {
   int dbg_flags;               // bring-up: bit 0 skip the epilogue stores, bit 1 skip the MMAs
 };
 
-// Epilogue helper: this warp holds a 32 x 32 block with thread = row (v[j] = column j).  Transpose SW columns at a time through the
-// warp's private padded patch and store row-contiguous segments (lane = column): bias / relu / row mask / residual applied on the way.
-template <int SW>
-FDPT_DEVINL void store_transposed(const LinTcArgs& a, const float (&v)[32], float* stg, int lane, int mw, int c0) {
-  constexpr int SLD = SW + 1, RPI = 32 / SW, NIT = 32 / RPI;  // rows per store instruction, store instructions per pass
-  const int lrow = lane / SW, lcol = lane % SW;
-#pragma unroll
-  for (int h0 = 0; h0 < 32; h0 += SW) {
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < SW; ++j) stg[lane * SLD + j] = v[h0 + j];
-    __syncwarp();
-    const int col = c0 + h0 + lcol;
-    const bool cok = col < a.N;
-    const float bs = (a.bias && cok) ? __ldg(a.bias + col) : 0.f;
-    float x[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) x[it] = stg[(it * RPI + lrow) * SLD + lcol] + bs;
-    if (a.relu) {
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) x[it] = fmaxf(x[it], 0.f);
-    }
-    if (a.rowmask) {
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const int m = mw + it * RPI + lrow;
-        x[it] *= (m < a.M) ? __ldg(a.rowmask + m) : 0.f;
-      }
-    }
-    float* yp = a.Y + (long long)(mw + lrow) * a.ldy + col;
-    if (a.residual) {
-      const float* rp = a.residual + (long long)(mw + lrow) * a.ldr + col;
-      float rr[NIT];
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) rr[it] = (cok && mw + it * RPI + lrow < a.M) ? rp[(long long)it * RPI * a.ldr] : 0.f;
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) x[it] += rr[it];
-    }
-#pragma unroll
-    for (int it = 0; it < NIT; ++it)
-      if (cok && mw + it * RPI + lrow < a.M) yp[(long long)it * RPI * a.ldy] = x[it];
-  }
-}
-
 __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -199,6 +155,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
     const int sw = a.stg_cols, sld = sw + 1;           // staging width / padded row stride
     float* stg = Stg + warp * 32 * sld;                // this warp's private patch
     const int mw = m0 + (warp & 3) * 32;               // first row of this warp's block
+    EpiArgs ep;
+    ep.M = a.M; ep.N = a.N; ep.alpha = 1.f; ep.bias = a.bias; ep.relu = a.relu; ep.rowmask = a.rowmask; ep.residual = a.residual;
+    ep.ldr = a.ldr; ep.accumulate = 0; ep.Y = a.Y; ep.ldy = a.ldy;
     for (int t = 0; t < ntiles; ++t) {
       const int as = t & 1;
       const int n0 = (nt_begin + t) * 128;
@@ -219,9 +178,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
         if (sw == 32)
-          store_transposed<32>(a, v, stg, lane, mw, n0 + cb);
+          store_transposed<32>(ep, v, stg, lane, mw, n0 + cb);
         else
-          store_transposed<16>(a, v, stg, lane, mw, n0 + cb);
+          store_transposed<16>(ep, v, stg, lane, mw, n0 + cb);
       }
     }
   }

@@ -216,3 +216,51 @@ def test_matmul_split_tf32(ctx):
         # accumulation truncates); single-pass TF32 would be ~5e-4
         # ... and its bias grows linearly with the number of k-steps: measured 7.7e-6 at K=2688 (linear_out)
         assert err < (2e-6 + 3e-9 * K) * ref.abs().max().item(), (Bt, M, N, K, kmajor, err)
+
+
+def _oracle_forward_case(wl_args, de_novo, seed, t_val):
+    """CUDA forward vs the CPU oracle (itself pinned to the reference fixtures) on a synthetic workload: covers shapes the committed
+    fixtures cannot (N > 128: several j-tiles per row, the ring-streaming mode of the IPA kernel, ragged last tiles; the de-novo
+    parameterisation without aatype)."""
+    from framedipt_b200 import SE3Diffuser, synthetic
+    from framedipt_b200.params import synthetic_state_dict
+    from framedipt_b200.score_network import ScoreNetwork
+    from oracle import framedipt_oracle as orc
+
+    conf = default_conf(input_aatype=not de_novo)
+    diffuser = SE3Diffuser(conf.diffuser)
+    sd = synthetic_state_dict(0, with_aatype=not de_novo)
+    m = ScoreNetwork(conf.model, diffuser, inpainting=not de_novo)
+    m.load_state_dict(sd)
+    m = m.to("cuda").eval()
+    wl = synthetic.Workload(*wl_args, de_novo=de_novo)
+    np.random.seed(seed)
+    feats = synthetic.make_features(wl, diffuser, seed=seed)
+    feats["t"] = t_val * torch.ones(wl.batch)
+    feats["sc_ca_t"] = feats["rigids_t"][..., 4:].float() + 0.3 * torch.randn(wl.batch, wl.n_res, 3, generator=torch.Generator().manual_seed(seed))
+    out = m({k: v.to("cuda") for k, v in feats.items()})
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = orc.score_network_forward(sd, feats, inpainting=not de_novo, input_aatype=not de_novo)
+    r, r_ref = out["rigids"].cpu().numpy(), ref["rigids"].float().numpy()
+    dt = np.abs(r[..., 4:] - r_ref[..., 4:]).max()
+    da = rot_angle_between(r[..., :4], r_ref[..., :4]).max()
+    ts_ref = ref["trans_score"].float().numpy()
+    dts = np.abs(out["trans_score"].cpu().numpy() - ts_ref).max() / np.abs(ts_ref).max()
+    dpsi = np.abs(out["psi"].cpu().numpy() - ref["psi"].float().numpy()).max()
+    print(f"N={wl.n_res} B={wl.batch} de_novo={de_novo}: |dtrans| {dt:.2e} A, rot {da:.2e} rad, trans_score rel {dts:.2e}, psi {dpsi:.2e}")
+    # the pair side runs with fp16 operands (TF32-class), so the single-forward bound is the looser one of SURVEY §8c step 2
+    # psi is a normalised 2-vector (ipa_pytorch.py:361-363): ill-conditioned where the raw torsion output is small, hence 2e-3
+    assert dt < 5e-4 and da < 5e-4 and dts < 5e-4 and dpsi < 2e-3
+
+
+def test_forward_vs_oracle_multi_tile():
+    _oracle_forward_case(("mt300", 2, (140, 160), ((60, 72), (200, 212)), 10), False, 11, 0.6)
+
+
+def test_forward_vs_oracle_ring_streaming():
+    _oracle_forward_case(("mt700", 1, (300, 400), ((100, 112), (500, 512)), 10), False, 12, 0.3)
+
+
+def test_forward_vs_oracle_de_novo():
+    _oracle_forward_case(("dn150", 2, (150,), (), 10), True, 13, 0.8)

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python tools/bench_lin.py 2>&1 | tee gpurun_out/bench_lin.log
+timeout 300 python tools/bench_gemm.py 2>&1 | head -12 | tee gpurun_out/bench_gemm.log
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log
