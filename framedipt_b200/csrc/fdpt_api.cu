@@ -93,7 +93,7 @@ struct fdpt_ctx {
   float *bin_lower = nullptr, *ideal = nullptr, *psi_frame = nullptr, *atom_mask = nullptr;
   Workspace ws;
   int64_t launches = 0;
-  int max_smem_optin = 0, num_sms = 148;
+  int max_smem_optin = 0, max_smem_sm = 0, num_sms = 148;
   int gemm_tc = 1;   // node-side GEMMs on tcgen05 (3-term split TF32); 0 = SIMT fp32 kernel (bring-up / A-B switch)
   int mn_swap = 0;   // bring-up knob of the MN-major descriptor
   int dbg_flags = 0; // bring-up knob of lin_tc: bit 0 skip the epilogue stores, bit 1 skip the MMAs
@@ -454,13 +454,13 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     ctx->launches++;
   }
   {
-    const IpaSmemPlan plan = ipa_core_plan(N, ctx->max_smem_optin);
+    const IpaSmemPlan plan = ipa_core_plan(N, ctx->max_smem_optin, ctx->max_smem_sm);
     if (plan.rz < 1) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs more shared memory than available in ipa_core", N);
     IpaCoreArgs a;
     a.B = B; a.N = N; a.JB = w.JB; a.ldS = w.ldS; a.S = w.S; a.z = z; a.kn = w.kn; a.mask = mask; a.Wb_img = p.imgWb; a.bb = p.bb;
     a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat; a.rz = plan.rz; a.resident = plan.resident; a.rows = (int)M; a.mn_swap = ctx->mn_swap;
     ProfScope pc(ctx, FDPT_PROF_IPA_CORE, st);
-    ipa_core_kernel<<<(unsigned)std::min<long long>(ctx->num_sms, M), 192, plan.bytes, st>>>(a);
+    ipa_core_kernel<<<(unsigned)std::min<long long>((long long)ctx->num_sms * plan.ctas_per_sm, M), 192, plan.bytes, st>>>(a);
     LAUNCH_CHECK();
   }
   {  // [o | o_pt (global frame)][b,:,h,:] = A_h [V_h | v_pts_h]  -> cat'[:, h*292 : (h+1)*292]
@@ -669,6 +669,7 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   ctx->device = device;
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&ctx->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
   cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::et_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et_smem_bytes());
   cudaFuncSetAttribute(tc::ee_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ee_smem_bytes());

@@ -132,22 +132,31 @@ constexpr int IPA_WDT_LD = 33;
 constexpr int IPA_MAX_RZ = 6, IPA_MAX_JB = 8;
 
 struct IpaSmemPlan {
-  int rz, resident;
+  int rz, resident, ctas_per_sm;
   size_t bytes;
 };
-inline IpaSmemPlan ipa_core_plan(int N, int max_smem) {
+// Shared-memory plan.  The kernel is latency-bound per row (load -> GEMM-b -> logits -> softmax -> GEMM-o -> down_z), so two CTAs per
+// SM are preferred whenever they fit (2-slot ring, second pass re-reads the row from L2); otherwise one CTA with the deepest ring.
+inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
   const int JB = (N + 127) / 128;
-  const size_t other = (size_t)JB * IPA_PIMG_TILE + 4096 + (size_t)NH * JB * 128 * 4 + NH * IPA_OZ_LD * 4 + C_Z * IPA_WDT_LD * 4 + 512 + 1024;
-  int rz = (int)(((size_t)max_smem - other) / IPA_TILE_BYTES);
-  if (rz > IPA_MAX_RZ) rz = IPA_MAX_RZ;
+  const size_t lbytes = (size_t)NH * (JB * 128 > IPA_OZ_LD ? JB * 128 : IPA_OZ_LD) * 4;  // logits [H][ldL], re-used as ozs [H][132]
+  const size_t other = (size_t)JB * IPA_PIMG_TILE + 4096 + lbytes + C_Z * IPA_WDT_LD * 4 + 512 + 1024;
   IpaSmemPlan p;
-  p.rz = rz;
-  p.resident = JB <= rz ? 1 : 0;
-  p.bytes = other + (size_t)rz * IPA_TILE_BYTES;
+  const size_t two = other + 2 * (size_t)IPA_TILE_BYTES;
+  if (2 * (two + 1024) <= (size_t)max_smem_per_sm) {
+    p.rz = 2;
+    p.ctas_per_sm = 2;
+  } else {
+    int rz = (int)(((size_t)max_smem - other) / IPA_TILE_BYTES);
+    p.rz = rz > IPA_MAX_RZ ? IPA_MAX_RZ : rz;
+    p.ctas_per_sm = 1;
+  }
+  p.resident = JB <= p.rz ? 1 : 0;
+  p.bytes = other + (size_t)p.rz * IPA_TILE_BYTES;
   return p;
 }
 
-__global__ void __launch_bounds__(192, 1) ipa_core_kernel(IpaCoreArgs a) {
+__global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -156,8 +165,8 @@ __global__ void __launch_bounds__(192, 1) ipa_core_kernel(IpaCoreArgs a) {
   uint8_t* Pimg = ring + (size_t)a.rz * IPA_TILE_BYTES;      // JB x 4 KB probability images (B operand of GEMM-o)
   uint8_t* Wbs = Pimg + (size_t)JB * IPA_PIMG_TILE;          // 4 KB
   float* L = reinterpret_cast<float*>(Wbs + 4096);           // [H][ldL] logits / exp
-  float* ozs = L + NH * ldL;                                 // [H][IPA_OZ_LD]
-  float* WdT = ozs + NH * IPA_OZ_LD;                         // [128][33] down_z.weight^T
+  float* ozs = L;                                            // [H][IPA_OZ_LD], aliases L (dead once the probabilities are written)
+  float* WdT = L + NH * (ldL > IPA_OZ_LD ? ldL : IPA_OZ_LD);  // [128][33] down_z.weight^T
   uint64_t* bars = reinterpret_cast<uint64_t*>(WdT + C_Z * IPA_WDT_LD);
   uint64_t* zfull = bars;                    // [IPA_MAX_RZ]
   uint64_t* zfree = zfull + IPA_MAX_RZ;      // [IPA_MAX_RZ]
@@ -360,6 +369,7 @@ __global__ void __launch_bounds__(192, 1) ipa_core_kernel(IpaCoreArgs a) {
         float* dst = a.cat + (long long)row * CAT + CATP_PAIR + hh_out * (C_Z / 4) + d0;
         *reinterpret_cast<float2*>(dst) = make_float2(acc0, acc1);
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // ozs aliases L: the next row's logits may not land before every thread is done
     }
   }
   tc_fence_before();
