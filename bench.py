@@ -44,19 +44,63 @@ def measured_peaks():
 
 
 class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU DURING the timed region from a background thread through NVML
+    (nvidia_ml_py); polling `nvidia-smi -lms` from a subprocess instead was measured to stall kernel launches of the
+    timed region (driver lock), so it is only the fallback when NVML cannot be imported."""
+
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, gpu: int, period_s: float = 0.02):
+        import threading
+
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self.p = self.f = self.th = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu)],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for k, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(k)
+                    except Exception:
+                        pass
+                    self._stop.wait(period_s)
+
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
         except Exception:
-            self.p = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu)],
+                                          stdout=self.f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.p = None
 
     def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": []}
+        if self.th is not None:
+            self._stop.set()
+            self.th.join(timeout=2)
+            if self.sm:
+                out["sm_mhz"] = float(np.median(self.sm))
+                out["samples"] = len(self.sm)
+            out["reasons"] = sorted(self.reasons)
+            out["source"] = "nvml"
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -81,6 +125,7 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(sm))
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
+        out["source"] = "nvidia-smi"
         return out
 
 
