@@ -73,6 +73,9 @@ struct Workspace {
   // outputs / sampling state
   float *pred_rigids, *trans_score, *psi, *rig_cur, *rig_next, *sc_ca, *t_emb_b, *t32_b, *bb_tmp;
   double *rot_score, *sigma_b, *sched_dev;
+  int* step_dev;  // [0] device step counter of the sampling loop, [1] number of steps T (the captured step graph reads both)
+  void** call_ptrs;  // per-call buffer bases read by the captured step: [0] noise, [1] prot_traj, [2] rigid_0_traj, [3] trans_traj, [4] rigid_traj
+  float* temb_tab;   // [4096, 32] this call's timestep-embedding table
 };
 
 }  // namespace
@@ -100,6 +103,16 @@ struct fdpt_ctx {
   // Linear weights pre-split into fp16 hi|lo operand images (lin_tc.cuh), keyed by (weight pointer, row stride, N, K)
   struct PackedW { __half* img; int nkb, n_tiles; };
   std::map<std::tuple<const float*, int, int, int>, PackedW> packed;
+  // CUDA graph of one (non-final) timestep of fdpt_sample, replayed with a device-side step counter; rebuilt when any baked
+  // pointer or size changes
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<unsigned char> key;
+    int64_t launches = 0;
+  } step_graph;
+  int use_graph = 1;
+  cudaStream_t own_stream = nullptr;   // the legacy default stream cannot be captured: fdpt_sample then runs on this stream,
+  cudaEvent_t fence_in = nullptr, fence_out = nullptr;  // fenced against the caller's stream with these events
   long long* et_dbg = nullptr;  // optional clock64 timeline buffer of the EdgeTransition kernel (FDPT_OPT_ET_TIMELINE)
   // live profiling (event pairs per slot)
   bool prof_on = false;
@@ -324,7 +337,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.pred_rigids = carve<float>(p, M * 7); w.trans_score = carve<float>(p, M * 3); w.psi = carve<float>(p, M * 2);
     w.rig_cur = carve<float>(p, M * 7); w.rig_next = carve<float>(p, M * 7); w.sc_ca = carve<float>(p, M * 3);
     w.t_emb_b = carve<float>(p, (size_t)B * EMB); w.t32_b = carve<float>(p, B); w.bb_tmp = carve<float>(p, M * 15);
-    w.rot_score = carve<double>(p, M * 3); w.sigma_b = carve<double>(p, B); w.sched_dev = carve<double>(p, 4096 * FDPT_SCHED_COLS);
+    w.rot_score = carve<double>(p, M * 3); w.sigma_b = carve<double>(p, B); w.sched_dev = carve<double>(p, 4096 * FDPT_SCHED_COLS); w.step_dev = carve<int>(p, 64); w.call_ptrs = carve<void*>(p, 16); w.temb_tab = carve<float>(p, 4096 * EMB);
     if (!pass) {
       w.bytes = (size_t)(p - (char*)nullptr);
       CK(cudaMalloc(&w.base, w.bytes));
@@ -442,7 +455,7 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
   if (w.JB > IPA_MAX_JB) return fail(ctx, FDPT_ERR_INVALID, "N=%d: the IPA kernel supports N <= %d", N, IPA_MAX_JB * 128);
   // q | q_pts, k | k_pts, v | v_pts of every head in one GEMM, then the frames applied in place
   RET(lin(s, C_S, p.Wcat, C_S, p.bcat, w.proj, PROJ_W, M, PROJ_W, C_S));
-  ipa_prep_kernel<<<(unsigned)M, 256, 0, st>>>((int)M, w.proj, quats, trans, p.head_w, w.kn);
+  ipa_prep_kernel<<<(unsigned)M, 256, 0, st>>>((int)M, w.proj, quats, trans, p.head_w, mask, N, w.kn);
   LAUNCH_CHECK();
   {  // S[b,h] = s_qk * [q | g q_pts] . [k | k_pts]^T
     GemmArgs g;
@@ -450,6 +463,7 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     g.B = w.proj + PROJ_K; g.ldb = PROJ_W; g.sB1 = (long long)N * PROJ_W; g.sB2 = QK_W;
     g.C = w.S; g.ldc = w.ldS; g.sC1 = (long long)NH * N * w.ldS; g.sC2 = (long long)N * w.ldS;
     g.M = N; g.N = N; g.K = QK_W; g.batch2 = NH; g.alpha = sqrtf(1.0f / (3.f * C_HID));
+    g.bias = w.kn; g.sBias1 = (long long)NH * N; g.sBias2 = N;  // kbias[b][h][j]
     CK(gemm_dispatch(ctx, g, true, B * NH, st));
     ctx->launches++;
   }
@@ -457,8 +471,8 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     const IpaSmemPlan plan = ipa_core_plan(N, ctx->max_smem_optin, ctx->max_smem_sm);
     if (plan.rz < 1) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs more shared memory than available in ipa_core", N);
     IpaCoreArgs a;
-    a.B = B; a.N = N; a.JB = w.JB; a.ldS = w.ldS; a.S = w.S; a.z = z; a.kn = w.kn; a.mask = mask; a.Wb_img = p.imgWb; a.bb = p.bb;
-    a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat; a.rz = plan.rz; a.resident = plan.resident; a.rows = (int)M; a.mn_swap = ctx->mn_swap;
+    a.B = B; a.N = N; a.JB = w.JB; a.ldS = w.ldS; a.S = w.S; a.z = z; a.Wb_img = p.imgWb; a.bb = p.bb;
+    a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat; a.rz = plan.rz; a.tmem_cols = plan.tmem_cols; a.rows = (int)M; a.mn_swap = ctx->mn_swap; a.dbg = (ctx->dbg_flags & 4) ? ctx->et_dbg : nullptr;
     ProfScope pc(ctx, FDPT_PROF_IPA_CORE, st);
     ipa_core_kernel<<<(unsigned)std::min<long long>((long long)ctx->num_sms * plan.ctas_per_sm, M), 192, plan.bytes, st>>>(a);
     LAUNCH_CHECK();
@@ -500,7 +514,7 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   a.B = B; a.N = N; a.JB = w.JB; a.z_in = z_in; a.z_out = z_out; a.n_img = w.n_img; a.Ui = w.U; a.Pf = w.Pf; a.b2 = p.be2;
   a.ln_g = p.eln_g; a.ln_b = p.eln_b; a.mask = mask; a.W1cat = p.imgW1cat; a.W2 = p.imgW2; a.W3cat = p.imgW3cat;
   a.tiles = M * w.JB;
-  a.dbg = ctx->et_dbg;
+  a.dbg = (ctx->dbg_flags & 4) ? nullptr : ctx->et_dbg;
   const int grid = (int)std::min<long long>(ctx->num_sms, a.tiles);
   tc::et_fused_kernel<<<grid, tc::ET_THREADS, tc::et_smem_bytes(), st>>>(a);
   LAUNCH_CHECK();
@@ -628,14 +642,28 @@ int z_image_to_fp32(fdpt_ctx* ctx, int B, int N, float* z, cudaStream_t st) {
   return FDPT_OK;
 }
 
-__global__ void set_step_kernel(int B, int step, const float* __restrict__ t_emb_tab, const double* __restrict__ sched,
+__global__ void set_step_kernel(int B, const int* __restrict__ step_ptr, const float* __restrict__ t_emb_tab, const double* __restrict__ sched,
                                 float* __restrict__ t_emb_b, float* __restrict__ t32_b, double* __restrict__ sigma_b) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int step = *step_ptr;
   if (idx < B * EMB) t_emb_b[idx] = t_emb_tab[step * EMB + (idx % EMB)];
   if (idx < B) {
     t32_b[idx] = (float)sched[step * FDPT_SCHED_COLS + FDPT_SCHED_T32];
     sigma_b[idx] = sched[step * FDPT_SCHED_COLS + FDPT_SCHED_SIGMA];
   }
+}
+
+// dst[step slice] = src (n floats)
+__global__ void copy_slot_kernel(long long n, const float* __restrict__ src, float* dst, StepRef ref) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) step_resolve(dst, ref)[idx] = src[idx];
+}
+
+// end of a timestep: x_t <- x_{t-1}; the last thread bumps the step counter (every other kernel of the step has read it already)
+__global__ void advance_state_kernel(long long n, const float* __restrict__ rig_next, float* __restrict__ rig_cur, int* __restrict__ step) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) rig_cur[idx] = rig_next[idx];
+  if (idx == 0) *step += 1;
 }
 
 __global__ void copy_trans_kernel(int M, const float* __restrict__ rig, float* __restrict__ ca) {
@@ -712,6 +740,12 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaFree(b.Wout_perm);
     cudaFree(b.imgWb);
   }
+  if (ctx->step_graph.exec) cudaGraphExecDestroy(ctx->step_graph.exec);
+  if (ctx->own_stream) {
+    cudaStreamDestroy(ctx->own_stream);
+    cudaEventDestroy(ctx->fence_in);
+    cudaEventDestroy(ctx->fence_out);
+  }
   cudaFree(ctx->et_dbg);
   for (auto& kv : ctx->packed) cudaFree(kv.second.img);
   cudaFree(ctx->top.imgE0);
@@ -748,6 +782,7 @@ int fdpt_load_param(fdpt_ctx* ctx, const char* key, const float* data, const int
   ps.shape.assign(shape, shape + ndim);
   CK(cudaMemcpy(ps.dev, data, n * sizeof(float), cudaMemcpyDefault));
   ctx->finalized = false;
+  ctx->step_graph.key.clear();  // weights are baked into the captured step
   return FDPT_OK;
 }
 
@@ -957,8 +992,19 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
   if (!ctx || !feats || !sched || !t_emb_tab || !out || num_t <= 0 || num_t > 4096) return FDPT_ERR_INVALID;
   if (num_t > 1 && !noise) return FDPT_ERR_INVALID;  /* noise rows are indexed by step: every step whose IS_LAST flag is 0 reads row s */
   cudaSetDevice(ctx->device);
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t user_st = (cudaStream_t)stream, st = user_st;
   RET(reserve_ws(ctx, B, N));
+  const bool fenced = ctx->use_graph && (user_st == nullptr || user_st == cudaStreamLegacy || user_st == cudaStreamPerThread);
+  if (fenced) {
+    if (!ctx->own_stream) {
+      CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ctx->fence_in, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ctx->fence_out, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(ctx->fence_in, user_st));
+    CK(cudaStreamWaitEvent(ctx->own_stream, ctx->fence_in, 0));
+    st = ctx->own_stream;
+  }
   Workspace& w = ctx->ws;
   const long long M = (long long)B * N;
   const int T = num_t;
@@ -972,54 +1018,130 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
   fdpt_out o;
   memset(&o, 0, sizeof(o));
   o.rigids = w.pred_rigids; o.rot_score = w.rot_score; o.trans_score = w.trans_score; o.psi = w.psi;
-  const unsigned gM3 = (unsigned)((M * 3 + 255) / 256), gM = (unsigned)((M + 127) / 128);
-  auto set_step = [&](int s) -> int {
-    set_step_kernel<<<(B * EMB + 255) / 256, 256, 0, st>>>(B, s, t_emb_tab, w.sched_dev, w.t_emb_b, w.t32_b, w.sigma_b);
+  const unsigned gM3 = (unsigned)((M * 3 + 255) / 256), gM = (unsigned)((M + 127) / 128), gM7 = (unsigned)((M * 7 + 255) / 256);
+  {  // per-call state read by the (possibly replayed) step: counter, T, buffer bases, timestep-embedding table
+    const int hdr[2] = {0, T};
+    void* ptrs[5] = {(void*)noise, (void*)out->prot_traj, (void*)out->rigid_0_traj, (void*)out->trans_traj, (void*)out->rigid_traj};
+    CK(cudaMemcpyAsync(w.step_dev, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w.call_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w.temb_tab, t_emb_tab, sizeof(float) * T * EMB, cudaMemcpyDeviceToDevice, st));
+    // (pageable host sources: the runtime stages them before returning, so the stack arrays may go out of scope)
+  }
+  auto set_step = [&]() -> int {
+    set_step_kernel<<<(B * EMB + 255) / 256, 256, 0, st>>>(B, w.step_dev, w.temb_tab, w.sched_dev, w.t_emb_b, w.t32_b, w.sigma_b);
     LAUNCH_CHECK();
     return FDPT_OK;
   };
-  if (self_condition) {  // experiments/utils.py:571-578
-    RET(set_step(0));
+  if (self_condition) {  // experiments/utils.py:571-578 (step counter = 0: t = 1.0)
+    RET(set_step());
     RET(forward_impl(ctx, B, N, &f, &o, st));
     copy_trans_kernel<<<gM3, 256, 0, st>>>((int)M, w.pred_rigids, w.sc_ca);
     LAUNCH_CHECK();
   }
   const int32_t* aat = ctx->cfg.with_aatype ? feats->aatype : nullptr;
-  for (int s = 0; s < T; ++s) {
-    const bool last = sched[s * FDPT_SCHED_COLS + FDPT_SCHED_IS_LAST] != 0.0;  // !(t > min_t)
-    RET(set_step(s));
+  // One timestep.  Per-step slices (noise, schedule row, trajectory slots) are resolved on the device from the step counter, so the
+  // same enqueue sequence -- and therefore one captured CUDA graph -- serves every step that does a reverse update.
+  auto enqueue_step = [&](bool last) -> int {
+    RET(set_step());
     RET(forward_impl(ctx, B, N, &f, &o, st));
     if (!last) {
       copy_trans_kernel<<<gM3, 256, 0, st>>>((int)M, w.pred_rigids, w.sc_ca);
       LAUNCH_CHECK();
       ReverseArgs a;
       a.N = N; a.rigids_t = w.rig_cur; a.rot_score = w.rot_score; a.trans_score = w.trans_score; a.dmask = w.dmask;
-      a.z_rot = noise + ((long long)s * 2 + 0) * M * 3; a.z_trans = noise + ((long long)s * 2 + 1) * M * 3;
-      a.sched = w.sched_dev + s * FDPT_SCHED_COLS; a.center = center; a.diffuse_rot = diffuse_rot; a.diffuse_trans = diffuse_trans;
+      a.z_rot = nullptr; a.z_trans = nullptr; a.noise_half = M * 3;
+      a.noise_ref.step = w.step_dev; a.noise_ref.stride = 2 * M * 3; a.noise_ref.base = w.call_ptrs + 0;
+      a.sched = w.sched_dev; a.sched_ref.step = w.step_dev; a.sched_ref.stride = FDPT_SCHED_COLS;
+      a.center = center; a.diffuse_rot = diffuse_rot; a.diffuse_trans = diffuse_trans;
       a.cs = ctx->cfg.coordinate_scaling; a.rigids_out = w.rig_next;
       reverse_kernel<<<B, 256, 0, st>>>(a);
       LAUNCH_CHECK();
     } else {
       CK(cudaMemcpyAsync(w.rig_next, w.pred_rigids, sizeof(float) * M * 7, cudaMemcpyDeviceToDevice, st));
     }
-    const long long slot = fo ? 0 : (T - 1 - s);
-    const bool write = !fo || s == T - 1;
+    // trajectory slot T-1-step (index 0 = final sample); final_only: only the last step writes, into slot 0
+    const bool write = !fo || last;
+    StepRef slot;
+    if (!fo) {
+      slot.step = w.step_dev; slot.T = w.step_dev + 1; slot.reversed = 1;
+    }
+    auto ref = [&](int ptr_slot, long long stride) {
+      StepRef r = slot;
+      r.stride = stride;
+      r.base = w.call_ptrs + ptr_slot;
+      return r;
+    };
     // backbone of x_{t-1} and of the x0 prediction (experiments/utils.py:396-410); always computed, like the reference
-    float* bb = (write && out->prot_traj) ? out->prot_traj + slot * M * 15 : w.bb_tmp;
-    backbone_kernel<<<gM, 128, 0, st>>>((int)M, w.rig_next, w.psi, aat, ctx->ideal, ctx->psi_frame, ctx->atom_mask, bb);
+    const bool wp = write && out->prot_traj, w0 = write && out->rigid_0_traj;
+    backbone_kernel<<<gM, 128, 0, st>>>((int)M, w.rig_next, w.psi, aat, ctx->ideal, ctx->psi_frame, ctx->atom_mask, w.bb_tmp,
+                                        wp ? ref(1, M * 15) : StepRef());
     LAUNCH_CHECK();
-    float* bb0 = (write && out->rigid_0_traj) ? out->rigid_0_traj + slot * M * 15 : w.bb_tmp;
-    backbone_kernel<<<gM, 128, 0, st>>>((int)M, w.pred_rigids, w.psi, aat, ctx->ideal, ctx->psi_frame, ctx->atom_mask, bb0);
+    backbone_kernel<<<gM, 128, 0, st>>>((int)M, w.pred_rigids, w.psi, aat, ctx->ideal, ctx->psi_frame, ctx->atom_mask, w.bb_tmp,
+                                        w0 ? ref(2, M * 15) : StepRef());
     LAUNCH_CHECK();
     if (write && out->trans_traj) {
-      trans0_kernel<<<gM, 128, 0, st>>>((int)M, w.pred_rigids, w.rig_next, feats->res_mask, feats->fixed_mask, out->trans_traj + slot * M * 3);
+      trans0_kernel<<<gM, 128, 0, st>>>((int)M, w.pred_rigids, w.rig_next, feats->res_mask, feats->fixed_mask, nullptr, ref(3, M * 3));
       LAUNCH_CHECK();
     }
-    if (write && out->rigid_traj) CK(cudaMemcpyAsync(out->rigid_traj + slot * M * 7, w.rig_next, sizeof(float) * M * 7, cudaMemcpyDeviceToDevice, st));
-    std::swap(w.rig_cur, w.rig_next);
-    f.rigids_t = w.rig_cur;
+    if (write && out->rigid_traj) {
+      copy_slot_kernel<<<gM7, 256, 0, st>>>(M * 7, w.rig_next, nullptr, ref(4, M * 7));
+      LAUNCH_CHECK();
+    }
+    advance_state_kernel<<<gM7, 256, 0, st>>>(M * 7, w.rig_next, w.rig_cur, w.step_dev);
+    LAUNCH_CHECK();
+    return FDPT_OK;
+  };
+  // graph key: everything the captured step bakes in
+  std::vector<unsigned char> key;
+  auto put = [&](const void* p, size_t n) { key.insert(key.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
+  {
+    const int ints[12] = {B, N, fo, center, diffuse_rot, diffuse_trans, ctx->gemm_tc, out->prot_traj != nullptr, out->rigid_0_traj != nullptr,
+                          out->trans_traj != nullptr, out->rigid_traj != nullptr, 0};
+    put(ints, sizeof(ints));
+    put(&f, sizeof(f));
+    put(&st, sizeof(st));
+    put(&w.base, sizeof(w.base));
+  }
+  int n_graph_steps = 0;
+  for (int s = 0; s < T; ++s) n_graph_steps += sched[s * FDPT_SCHED_COLS + FDPT_SCHED_IS_LAST] == 0.0;
+  const bool use_graph = ctx->use_graph && !ctx->prof_on && n_graph_steps >= 2;
+  for (int s = 0; s < T; ++s) {
+    const bool last = sched[s * FDPT_SCHED_COLS + FDPT_SCHED_IS_LAST] != 0.0;  // !(t > min_t)
+    if (last || !use_graph) {
+      RET(enqueue_step(last));
+      continue;
+    }
+    auto& sg = ctx->step_graph;
+    if (!sg.exec || sg.key != key) {
+      if (sg.exec) {
+        cudaGraphExecDestroy(sg.exec);
+        sg.exec = nullptr;
+      }
+      const int64_t l0 = ctx->launches;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue_step(false);
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (rc != FDPT_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+      }
+      if (ce != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "graph capture of a timestep failed: %s", cudaGetErrorString(ce));
+      sg.launches = ctx->launches - l0;
+      ctx->launches = l0;
+      const cudaError_t ie = cudaGraphInstantiate(&sg.exec, g, 0);
+      cudaGraphDestroy(g);
+      if (ie != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
+      sg.key = key;
+    }
+    CK(cudaGraphLaunch(sg.exec, st));
+    ctx->launches += sg.launches;
   }
   if (out->psi_pred) CK(cudaMemcpyAsync(out->psi_pred, w.psi, sizeof(float) * M * 2, cudaMemcpyDeviceToDevice, st));
+  if (fenced) {
+    CK(cudaEventRecord(ctx->fence_out, st));
+    CK(cudaStreamWaitEvent(user_st, ctx->fence_out, 0));
+  }
   return FDPT_OK;
 }
 
@@ -1043,7 +1165,8 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
   switch (option) {
     case FDPT_OPT_GEMM_TC: ctx->gemm_tc = value != 0; return FDPT_OK;
     case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
-    case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; return FDPT_OK;
+    case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); return FDPT_OK;
+    case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {
         CK(cudaMalloc(&ctx->et_dbg, 8 * 48 * sizeof(long long)));

@@ -17,7 +17,7 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0;
   int batch2 = 1;  // blockIdx.z = b1 * batch2 + b2
   float alpha = 1.f;
-  const float* bias = nullptr;
+  const float* bias = nullptr; long long sBias1 = 0, sBias2 = 0;  // per-column bias, optionally per batch
   const float* residual = nullptr; int ldr = 0;
   const float* rowmask = nullptr;
   // pair-broadcast add: global pair row p = row0 + r -> b = p / (nres*nres), i = (p / nres) % nres, j = p % nres
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
       const int n = n0 + tx * 4 + j;
       if (n >= g.N) continue;
       float v = g.alpha * acc[i][j];
-      if (g.bias) v += g.bias[n];
+      if (g.bias) v += g.bias[b1 * g.sBias1 + b2 * g.sBias2 + n];
       if (urow) v += urow[n] + vrow[n];
       if (g.relu) v = fmaxf(v, 0.f);
       if (g.rowmask) v *= rm;

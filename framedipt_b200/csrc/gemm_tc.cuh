@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(GemmTcArgs a) {
     float* stg = reinterpret_cast<float*>(smem) + warp * 32 * 33;
     const int mw = m0 + (warp & 3) * 32;
     EpiArgs ep;
-    ep.M = g.M; ep.N = g.N; ep.alpha = g.alpha; ep.bias = g.bias; ep.relu = g.relu; ep.rowmask = g.rowmask; ep.residual = g.residual;
+    ep.M = g.M; ep.N = g.N; ep.alpha = g.alpha; ep.bias = g.bias ? g.bias + b1 * g.sBias1 + b2 * g.sBias2 : nullptr; ep.relu = g.relu; ep.rowmask = g.rowmask; ep.residual = g.residual;
     ep.ldr = g.ldr; ep.accumulate = g.accumulate; ep.Y = C; ep.ldy = g.ldc;
     for (int cb = c_begin; cb < c_end; cb += 32) {
       float v[32], x2[32];

@@ -4,6 +4,26 @@
 
 namespace fdpt {
 
+// Reference to a per-step slice of a buffer, resolved ON THE DEVICE, so that one captured CUDA graph of a timestep can be replayed
+// for every step of every fdpt_sample call: the buffer base comes from a device-resident pointer slot (rewritten per call), the
+// offset is (reversed ? T-1-step : step) * stride elements with step and T read from device memory.  Default: no indirection.
+struct StepRef {
+  const int* step = nullptr;
+  const int* T = nullptr;
+  void* const* base = nullptr;
+  long long stride = 0;
+  int reversed = 0;
+};
+template <typename P>
+FDPT_DEVINL P* step_resolve(P* direct, const StepRef& r) {
+  P* p = r.base ? reinterpret_cast<P*>(*r.base) : direct;
+  if (r.step) {
+    const int s = *r.step;
+    p += (long long)(r.reversed ? (*r.T - 1 - s) : s) * r.stride;
+  }
+  return p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Rotation score  (SE3Diffuser.calc_rot_score se3_diffuser.py:281-292; transforms.quat_to_rotvec
 // transforms.py:53-69; SO3Diffuser.torch_score so3_diffuser.py:373-402; igso3_expansion 18-77; score 122-191).
@@ -163,10 +183,18 @@ struct ReverseArgs {
   int center, diffuse_rot, diffuse_trans;
   float cs;                   // coordinate scaling 0.1
   float* rigids_out;          // [B,N,7]
+  StepRef noise_ref, sched_ref;  // optional device-resolved per-step slices of the noise block and the schedule table
+  long long noise_half = 0;      // elements between the rot and the trans half of a step's noise block (indirect mode)
 };
 
 __global__ void __launch_bounds__(256) reverse_kernel(ReverseArgs a) {
   const int b = blockIdx.x, N = a.N;
+  {
+    const double* zr = step_resolve(a.z_rot, a.noise_ref);  // base of this step's [2][B,N,3] noise block when indirect
+    a.z_trans = a.noise_ref.base ? zr + a.noise_half : step_resolve(a.z_trans, a.noise_ref);
+    a.z_rot = zr;
+    a.sched = step_resolve(a.sched, a.sched_ref);
+  }
   const double g2dt = a.sched[2], gn = a.sched[3], b_t = a.sched[4], dt = a.sched[5], rn = a.sched[6];
   __shared__ double red[4][8];
   __shared__ double com[3];
@@ -277,9 +305,10 @@ __global__ void __launch_bounds__(256) reverse_kernel(ReverseArgs a) {
 __global__ void backbone_kernel(int M, const float* __restrict__ rigids, const float* __restrict__ psi,
                                 const int32_t* __restrict__ aatype, const float* __restrict__ ideal,
                                 const float* __restrict__ psi_frame, const float* __restrict__ atom_mask,
-                                float* __restrict__ out) {
+                                float* __restrict__ out, StepRef out_ref = StepRef()) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
+  out = step_resolve(out, out_ref);
   int aa = aatype ? aatype[m] : 0;
   if (aa >= 20 || aa < 0) aa = 0;
   float q[4] = {rigids[m * 7], rigids[m * 7 + 1], rigids[m * 7 + 2], rigids[m * 7 + 3]};
@@ -328,9 +357,10 @@ __global__ void backbone_kernel(int M, const float* __restrict__ rigids, const f
 // trans_traj row (experiments/utils.py:379-384): diffuse_mask * pred_trans + fixed*res_mask * rigids_{t-1} trans
 __global__ void trans0_kernel(int M, const float* __restrict__ rig_pred, const float* __restrict__ rig_next,
                               const float* __restrict__ res_mask, const float* __restrict__ fixed_mask,
-                              float* __restrict__ out) {
+                              float* __restrict__ out, StepRef out_ref = StepRef()) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
+  out = step_resolve(out, out_ref);
   const float dm = (1.f - fixed_mask[m]) * res_mask[m], fm = fixed_mask[m] * res_mask[m];
 #pragma unroll
   for (int k = 0; k < 3; ++k) out[m * 3 + k] = dm * rig_pred[m * 7 + 4 + k] + fm * rig_next[m * 7 + 4 + k];

@@ -3,17 +3,18 @@
 // Data flow of one IPA call (B samples, N residues, H=8 heads, C=256, Pq=8, Pv=12, c_z=128):
 //   proj [M, 6816]   <- s @ Wcat^T + bcat                (one split-TF32 GEMM; Wcat = the four projection weights with rows permuted
 //                                                          so that every head's q | q_pts, k | k_pts, v | v_pts are contiguous)
-//   ipa_prep_kernel  : points -> global frame in place (R_i p + t_i); q_pts additionally scaled by gamma_h / s_qk; kn[j,h] = -gamma_h/2 |k_pts|^2
-//   S[b,h,i,j]       <- s_qk * Q'_h . K'_h   (batched split-TF32 GEMM, K = 256 + 24):   s_qk q.k + gamma_h q_pts.k_pts
+//   ipa_prep_kernel  : points -> global frame in place (R_i p + t_i); q_pts additionally scaled by gamma_h / s_qk;
+//                      kbias[b,h,j] = -gamma_h/2 |k_pts_j|^2 + 1e5 (m_j - 1)
+//   S[b,h,i,j]       <- s_qk * Q'_h . K'_h + kbias[b,h,j]   (batched split-precision GEMM, K = 256 + 24, per-batch column bias)
 //                       ( -gamma/2 |q_p - k_p|^2 = gamma q_p.k_p - gamma/2 |k_p|^2 - gamma/2 |q_p|^2 ; the last term is constant in j
-//                         and cancels in the softmax )
-//   ipa_core_kernel  : logits = S + sqrt(1/3) (W_b z_ij + b_b) + kn[j,h] + 1e5 (m_i m_j - 1);  a = softmax_j;  a -> S (fp32);
+//                         and cancels in the softmax.  Mask term of the reference: 1e5 (m_i m_j - 1) = 1e5 (m_j - 1) on rows with
+//                         m_i = 1; rows with m_i = 0 are zeroed after the IPA (ipa_pytorch.py:531), SURVEY V2 )
+//   ipa_core_kernel  : logits = S + sqrt(1/3) (W_b z_ij + b_b);  a = softmax_j;  a -> S (fp32);
 //                      o_pair = down_z(sum_j a_ij z_ij)   (down_z is linear and sum_j a = 1, so it commutes)
 //                      Both z contractions run on tcgen05 (fp16 z tile images straight from HBM via bulk copies, fp32 accumulate in TMEM):
 //                        GEMM-b  D1[j, h]  = z_tile[j, c] . Wb[h, c]^T         (A K-major, N = 16: rows 0-7 fp16 hi, 8-15 fp16 lo of W_b)
 //                        GEMM-o  D2[c, h] += z_tile[j, c]^T . P[h, j]^T        (A = the same smem tile read MN-major, B rows = hi | lo of a)
-//                      z[b,i,:,:] is read from HBM once per (b,i): the tiles of a row stay resident in the smem ring for both GEMMs when
-//                      N <= 128*ring slots, otherwise the second pass re-reads them from L2.
+//                      z[b,i,:,:] is read from HBM once per (b,i); the second pass (GEMM-o) re-reads the row from L2.
 //   O'[b,i,h,0:292]  <- A_h [V_h | v_pts_h]   (batched split-TF32 GEMM with MN-major B, written straight into the concat buffer)
 //   ipa_opt_kernel   : o_pt -> local frame R_i^T (p - t_i) in place, norms
 //   out = linear_out(cat')  (GEMM; linear_out.weight columns permuted once to the cat' order)
@@ -37,7 +38,7 @@ static_assert(CATP_PAIR + NH * (C_Z / 4) == CAT, "concat width");
 // In-place frame application on the point slots of proj (planar x|y|z per head), ipa_pytorch.py:214-239, rigid_utils.py:82-106.
 __global__ void __launch_bounds__(256) ipa_prep_kernel(int M, float* __restrict__ proj, const float* __restrict__ quats,
                                                        const float* __restrict__ trans, const float* __restrict__ head_w,
-                                                       float* __restrict__ kn) {
+                                                       const float* __restrict__ mask, int N, float* __restrict__ kbias) {
   const int m = blockIdx.x, tid = threadIdx.x;
   __shared__ float R[9], t[3];
   if (tid == 0) {
@@ -77,7 +78,10 @@ __global__ void __launch_bounds__(256) ipa_prep_kernel(int M, float* __restrict_
     d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
     d2 += __shfl_xor_sync(0xffffffffu, d2, 2);
     d2 += __shfl_xor_sync(0xffffffffu, d2, 4);
-    if (p == 0) kn[(long long)m * NH + h] = -0.5f * gamma * d2;
+    if (p == 0) {  // kbias[b][h][j]
+      const int b = m / N, j = m - b * N;
+      kbias[((long long)b * NH + h) * N + j] = -0.5f * gamma * d2 + 1e5f * (mask[m] - 1.f);
+    }
   }
   slot[p] = gx;
   slot[np + p] = gy;
@@ -111,39 +115,47 @@ __global__ void __launch_bounds__(96) ipa_opt_kernel(int M, float* __restrict__ 
 
 struct IpaCoreArgs {
   int B, N, JB, ldS;
-  float* S;              // [B,H,N,ldS] in: s_qk q.k + gamma q_pts.k_pts ; out: attention probabilities
+  float* S;              // [B,H,N,ldS] in: s_qk q.k + gamma q_pts.k_pts + kbias ; out: attention probabilities
   const __half* z;       // fp16 tile images [B][N][JB][2 k-blocks][128 rows][128 B, 128B-swizzled] (et_fused.cuh)
-  const float* kn;       // [B*N, H]   -gamma_h/2 |k_pts|^2
-  const float* mask;     // [B*N]
   const __half* Wb_img;  // 4 KB operand image [2 kb][16 rows][128 B]: rows 0-7 fp16 hi, rows 8-15 fp16 lo of linear_b.weight
   const float* bb;       // [H]
   const float* Wd;       // [32,128] down_z.weight
   const float* bd;       // [32]
   float* cat;            // [B*N, CAT] (cat' order)
-  int rz, resident;      // ring slots; 1 = the JB tiles of a row stay in the ring for both GEMMs
+  int rz, tmem_cols;     // z ring slots; TMEM columns to allocate (two D1 buffers + D2)
   int rows;              // B*N
   int mn_swap;           // bring-up knob: swap LBO / SBO of the MN-major A descriptor
+  long long* dbg;        // optional clock64 timeline of CTA 0 ([row iteration][48] stamps), or nullptr
 };
+
+#define IPA_TS(id)                                                                  \
+  do {                                                                              \
+    if (a.dbg && blockIdx.x == 0 && (it) < 8) a.dbg[(it) * 48 + (id)] = clock64();  \
+  } while (0)
 
 constexpr int IPA_TILE_BYTES = 32768;
 constexpr int IPA_PIMG_TILE = 4096;   // [2 kb][16 rows][128 B]
 constexpr int IPA_OZ_LD = 132;
-constexpr int IPA_WDT_LD = 33;
 constexpr int IPA_MAX_RZ = 6, IPA_MAX_JB = 8;
 
 struct IpaSmemPlan {
-  int rz, resident, ctas_per_sm;
+  int rz, ctas_per_sm, tmem_cols;
   size_t bytes;
 };
-// Shared-memory plan.  The kernel is latency-bound per row (load -> GEMM-b -> logits -> softmax -> GEMM-o -> down_z), so two CTAs per
-// SM are preferred whenever they fit (2-slot ring, second pass re-reads the row from L2); otherwise one CTA with the deepest ring.
+__host__ __device__ inline size_t ipa_pimg_bytes(int JB) {  // probability images; the region doubles as ozs [H][132] fp32 once GEMM-o has read it
+  const size_t p = (size_t)JB * IPA_PIMG_TILE, o = (size_t)NH * IPA_OZ_LD * 4;
+  return ((p > o ? p : o) + 1023) / 1024 * 1024;
+}
+// Shared-memory / TMEM plan.  The kernel is latency-bound per row (load -> GEMM-b -> logits -> softmax -> GEMM-o -> down_z), so two
+// CTAs per SM are preferred whenever they fit (2-slot z ring, <= 256 TMEM columns each); otherwise one CTA with the deepest ring.
 inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
   const int JB = (N + 127) / 128;
-  const size_t lbytes = (size_t)NH * (JB * 128 > IPA_OZ_LD ? JB * 128 : IPA_OZ_LD) * 4;  // logits [H][ldL], re-used as ozs [H][132]
-  const size_t other = (size_t)JB * IPA_PIMG_TILE + 4096 + lbytes + C_Z * IPA_WDT_LD * 4 + 512 + 1024;
+  const size_t other = ipa_pimg_bytes(JB) + 4096 + (size_t)NH * JB * 128 * 4 + C_Z * (C_Z / 4) * 4 + 512 + 1024;
+  const int need_cols = 2 * JB * 16 + 16;  // two D1 buffers + D2
   IpaSmemPlan p;
+  p.tmem_cols = need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512);
   const size_t two = other + 2 * (size_t)IPA_TILE_BYTES;
-  if (2 * (two + 1024) <= (size_t)max_smem_per_sm) {
+  if (2 * (two + 1024) <= (size_t)max_smem_per_sm && p.tmem_cols <= 256) {
     p.rz = 2;
     p.ctas_per_sm = 2;
   } else {
@@ -151,11 +163,16 @@ inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
     p.rz = rz > IPA_MAX_RZ ? IPA_MAX_RZ : rz;
     p.ctas_per_sm = 1;
   }
-  p.resident = JB <= p.rz ? 1 : 0;
   p.bytes = other + (size_t)p.rz * IPA_TILE_BYTES;
   return p;
 }
 
+// One CTA streams rows (b, i).  Software pipeline across rows (it = row iteration of this CTA):
+//   loader / MMA warp order:  b(0), b(1), { o(it), b(it+2) }          b = GEMM-b into D1[it & 1],  o = GEMM-o (second pass over the
+//                                                                      row's z tiles, L2 hits) once the softmax of row it has stored P
+//   epilogue order:           logits(0), { softmax(it), logits(it+1), down_z(it) }
+// so the HBM loads and GEMM-b of the next rows run under the softmax of the current one, and the logits of the next row are computed
+// while the tensor core does GEMM-o.
 __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -163,76 +180,88 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
   const int N = a.N, JB = a.JB, ldL = JB * 128;
   uint8_t* ring = smem;                                      // rz x 32 KB z tiles
   uint8_t* Pimg = ring + (size_t)a.rz * IPA_TILE_BYTES;      // JB x 4 KB probability images (B operand of GEMM-o)
-  uint8_t* Wbs = Pimg + (size_t)JB * IPA_PIMG_TILE;          // 4 KB
+  float* ozs = reinterpret_cast<float*>(Pimg);               // [H][132], aliases Pimg (dead once GEMM-o has completed)
+  uint8_t* Wbs = Pimg + ipa_pimg_bytes(JB);                  // 4 KB
   float* L = reinterpret_cast<float*>(Wbs + 4096);           // [H][ldL] logits / exp
-  float* ozs = L;                                            // [H][IPA_OZ_LD], aliases L (dead once the probabilities are written)
-  float* WdT = L + NH * (ldL > IPA_OZ_LD ? ldL : IPA_OZ_LD);  // [128][33] down_z.weight^T
-  uint64_t* bars = reinterpret_cast<uint64_t*>(WdT + C_Z * IPA_WDT_LD);
-  uint64_t* zfull = bars;                    // [IPA_MAX_RZ]
-  uint64_t* zfree = zfull + IPA_MAX_RZ;      // [IPA_MAX_RZ]
-  uint64_t* d1_full = zfree + IPA_MAX_RZ;    // [IPA_MAX_JB]
-  uint64_t* p_full = d1_full + IPA_MAX_JB;   // [1]
-  uint64_t* d2_full = p_full + 1;            // [1]
-  uint64_t* wb_full = d2_full + 1;           // [1]
+  float* Wd4 = L + NH * ldL;                                 // [32 channel groups][32 d][4] down_z.weight
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Wd4 + C_Z * (C_Z / 4));
+  uint64_t* zfull = bars;                        // [IPA_MAX_RZ]
+  uint64_t* zfree = zfull + IPA_MAX_RZ;          // [IPA_MAX_RZ]
+  uint64_t* d1_full = zfree + IPA_MAX_RZ;        // [2][IPA_MAX_JB]
+  uint64_t* d1_free = d1_full + 2 * IPA_MAX_JB;  // [2]
+  uint64_t* p_full = d1_free + 2;                // [1]
+  uint64_t* d2_full = p_full + 1;                // [1]
+  uint64_t* wb_full = d2_full + 1;               // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wb_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int nrows = (a.rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // rows blockIdx.x, + gridDim.x, ...
 
   if (tid == 0) {
     for (int s = 0; s < IPA_MAX_RZ; ++s) {
       mbar_init(&zfull[s], 1);
       mbar_init(&zfree[s], 1);
     }
-    for (int t = 0; t < IPA_MAX_JB; ++t) mbar_init(&d1_full[t], 1);
+    for (int t = 0; t < 2 * IPA_MAX_JB; ++t) mbar_init(&d1_full[t], 1);
+    mbar_init(&d1_free[0], 128);
+    mbar_init(&d1_free[1], 128);
     mbar_init(p_full, 128);
     mbar_init(d2_full, 1);
     mbar_init(wb_full, 1);
     fence_barrier_init();
   }
-  // rows 8..15 of the probability images hold the fp16 lo parts; every byte is rewritten per row, nothing to clear
   for (int k = tid; k < C_Z * (C_Z / 4); k += blockDim.x) {
     const int d = k / C_Z, c = k % C_Z;
-    WdT[c * IPA_WDT_LD + d] = a.Wd[k];
+    Wd4[((c >> 2) * (C_Z / 4) + d) * 4 + (c & 3)] = a.Wd[k];
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t D1 = tmem_base, D2 = tmem_base + 128;
+  const uint32_t D1 = tmem_base, D2 = tmem_base + 2 * JB * 16;  // D1 buffer b at D1 + b*JB*16
 
   if (warp == 5) {
     // ============================ loader ============================
-    if (lane == 0) {
+    if (lane == 0 && nrows > 0) {
       mbar_arrive_expect_tx(wb_full, 4096);
       bulk_g2s(Wbs, a.Wb_img, 4096, wb_full);
       uint32_t cnt = 0;
-      const int passes = a.resident ? 1 : 2;
-      for (int row = blockIdx.x; row < a.rows; row += gridDim.x) {
+      auto load_row = [&](int it) {
+        const int row = (int)blockIdx.x + it * (int)gridDim.x;
         const uint8_t* zrow = reinterpret_cast<const uint8_t*>(a.z) + (size_t)row * JB * IPA_TILE_BYTES;
-        for (int pass = 0; pass < passes; ++pass)
-          for (int t = 0; t < JB; ++t) {
-            const uint32_t s = cnt % a.rz;
-            mbar_wait(&zfree[s], ((cnt / a.rz) & 1) ^ 1);
-            mbar_arrive_expect_tx(&zfull[s], IPA_TILE_BYTES);
-            bulk_g2s(ring + (size_t)s * IPA_TILE_BYTES, zrow + (size_t)t * IPA_TILE_BYTES, IPA_TILE_BYTES, &zfull[s]);
-            ++cnt;
-          }
+        for (int t = 0; t < JB; ++t) {
+          const uint32_t s = cnt % a.rz;
+          mbar_wait(&zfree[s], ((cnt / a.rz) & 1) ^ 1);
+          mbar_arrive_expect_tx(&zfull[s], IPA_TILE_BYTES);
+          bulk_g2s(ring + (size_t)s * IPA_TILE_BYTES, zrow + (size_t)t * IPA_TILE_BYTES, IPA_TILE_BYTES, &zfull[s]);
+          ++cnt;
+        }
+      };
+      load_row(0);
+      if (nrows > 1) load_row(1);
+      for (int it = 0; it < nrows; ++it) {
+        load_row(it);                        // second pass of row it (GEMM-o): L2 hits
+        if (it + 2 < nrows) load_row(it + 2);
       }
     }
   } else if (warp == 4) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    if (lane == 0 && nrows > 0) {
       mbar_wait(wb_full, 0);
       tc_fence_after();
       const uint32_t idesc_b = make_idesc_f16(128, 16);
       const uint32_t idesc_o = make_idesc_f16(128, 16) | (1u << 15);  // A operand MN-major
       const uint32_t wb = smem_u32(Wbs), pimg = smem_u32(Pimg), ring_u = smem_u32(ring);
       const uint32_t lbo = a.mn_swap ? 1024u : 16384u, sbo = a.mn_swap ? 16384u : 1024u;
-      uint32_t cnt = 0, it = 0;
-      for (int row = blockIdx.x; row < a.rows; row += gridDim.x, ++it) {
-        const uint32_t base_cnt = cnt;
-        // GEMM-b: D1[t] = z_tile . Wb^T
+      uint32_t cnt = 0;
+      // GEMM-b of row iteration `it`: D1[it & 1][t] = z_tile . Wb^T
+      auto issue_b = [&](int it) {
+        const int buf = it & 1;
+        if (it >= 2) {  // the logits of row it-2 have been read out of this D1 buffer
+          mbar_wait(&d1_free[buf], ((it - 2) >> 1) & 1);
+          tc_fence_after();
+        }
         for (int t = 0; t < JB; ++t) {
           const uint32_t s = cnt % a.rz;
           mbar_wait(&zfull[s], (cnt / a.rz) & 1);
@@ -242,33 +271,39 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
           for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(D1 + t * 16, make_sw128_desc(zt + kb * 16384 + k * 32), make_sw128_desc(wb + kb * 2048 + k * 32), idesc_b,
+              umma_f16(D1 + (buf * JB + t) * 16, make_sw128_desc(zt + kb * 16384 + k * 32), make_sw128_desc(wb + kb * 2048 + k * 32), idesc_b,
                        (kb | k) ? 1u : 0u);
-          umma_commit(&d1_full[t]);
-          if (!a.resident) umma_commit(&zfree[s]);
+          umma_commit(&d1_full[buf * IPA_MAX_JB + t]);
+          umma_commit(&zfree[s]);
           ++cnt;
+          if (t == 0) IPA_TS(1);
         }
-        // GEMM-o: D2 += z_tile^T . P^T  (after the softmax of this row has written the probability images)
+      };
+      // GEMM-o of row iteration `it`: D2 += z_tile^T . P^T  (after the softmax of this row has written the probability images)
+      auto issue_o = [&](int it) {
         mbar_wait(p_full, it & 1);
         tc_fence_after();
+        IPA_TS(9);
         for (int t = 0; t < JB; ++t) {
-          uint32_t s;
-          if (a.resident) {
-            s = (base_cnt + t) % a.rz;
-          } else {
-            s = cnt % a.rz;
-            mbar_wait(&zfull[s], (cnt / a.rz) & 1);
-            tc_fence_after();
-            ++cnt;
-          }
+          const uint32_t s = cnt % a.rz;
+          mbar_wait(&zfull[s], (cnt / a.rz) & 1);
+          tc_fence_after();
           const uint32_t zt = ring_u + s * IPA_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // 16 j-rows per step
             umma_f16(D2, make_sw128_desc_ls(zt + k * 2048, lbo, sbo),
                      make_sw128_desc(pimg + t * IPA_PIMG_TILE + (k >> 2) * 2048 + (k & 3) * 32), idesc_o, (t | k) ? 1u : 0u);
           umma_commit(&zfree[s]);
+          ++cnt;
         }
         umma_commit(d2_full);
+        IPA_TS(10);
+      };
+      issue_b(0);
+      if (nrows > 1) issue_b(1);
+      for (int it = 0; it < nrows; ++it) {
+        issue_o(it);
+        if (it + 2 < nrows) issue_b(it + 2);
       }
     }
   } else {
@@ -279,74 +314,108 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
     float bbv[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) bbv[h] = a.bb[h];
-    const int d0 = (2 * r) & 31, hh_out = r >> 4;
-    const float bd0 = a.bd[d0], bd1 = a.bd[d0 + 1];
-    uint32_t it = 0;
-    for (int row = blockIdx.x; row < a.rows; row += gridDim.x, ++it) {
+    const int hh_out = r >> 4, dq = r & 15;
+    const float bd0 = a.bd[dq], bd1 = a.bd[dq + 16];
+    const long long hs = (long long)N * a.ldS;
+    // S row of iteration `it` (8 heads x ldS floats) -> L, asynchronously (cp.async, 16 bytes per request)
+    auto prefetch_S = [&](int it) {
+      const int row = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = row / N, i = row - b * N;
-      const float mi = a.mask[row];
-      float* Srow0 = a.S + (((long long)b * NH) * N + i) * a.ldS;  // head h: + h * N * ldS
-      const long long hs = (long long)N * a.ldS;
+      const float* Srow0 = a.S + (((long long)b * NH) * N + i) * a.ldS;
+      const int cpr = a.ldS >> 2;  // 16-byte chunks per head
+      for (int k = tid; k < NH * cpr; k += 128) {
+        const int h = k / cpr, c = k - h * cpr;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(L + h * ldL + 4 * c)), "l"(Srow0 + h * hs + 4 * c) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // logits of row iteration `it`: L[h][j] = S'[h][j] + sqrt(1/3) (b_ij,h + b_b,h), -inf beyond N
+    auto logits = [&](int it) {
+      const int buf = it & 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // every thread's part of the S row has landed
       for (int t = 0; t < JB; ++t) {
         const int j = t * 128 + r;
-        const bool valid = j < N;
-        float sv[NH];
-        float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
-        float mj = 0.f;
-        if (valid) {
-#pragma unroll
-          for (int h = 0; h < NH; ++h) sv[h] = Srow0[h * hs + j];
-          const float4* kp = reinterpret_cast<const float4*>(a.kn + ((long long)b * N + j) * NH);
-          k0 = __ldg(kp);
-          k1 = __ldg(kp + 1);
-          mj = a.mask[(long long)b * N + j];
-        }
-        mbar_wait(&d1_full[t], it & 1);
+        mbar_wait(&d1_full[buf * IPA_MAX_JB + t], (it >> 1) & 1);
         tc_fence_after();
         float bv[16];
-        tmem_ld16(D1 + lane_base + t * 16, bv);
+        tmem_ld16(D1 + lane_base + (buf * JB + t) * 16, bv);
         tmem_ld_wait();
-        const float knv[NH] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-        const float mterm = 1e5f * (mi * mj - 1.f);
+        if (j < N) {
 #pragma unroll
-        for (int h = 0; h < NH; ++h)
-          L[h * ldL + j] = valid ? sv[h] + s_b * (bv[h] + bv[h + 8] + bbv[h]) + knv[h] + mterm : -INFINITY;
+          for (int h = 0; h < NH; ++h) L[h * ldL + j] += s_b * (bv[h] + bv[h + 8] + bbv[h]);
+        } else {
+#pragma unroll
+          for (int h = 0; h < NH; ++h) L[h * ldL + j] = -INFINITY;
+        }
       }
       tc_fence_before();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // ---- softmax over j: warp w owns heads 2w, 2w+1
+      mbar_arrive(&d1_free[buf]);
+    };
+    if (nrows > 0) prefetch_S(0);
+    if (nrows > 0) logits(0);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int it = 0; it < nrows; ++it) {
+      const int row = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = row / N, i = row - b * N;
+      float* Srow0 = a.S + (((long long)b * NH) * N + i) * a.ldS;
+      if (tid == 0) IPA_TS(20);
+      // ---- softmax over j: warp w owns heads 2w, 2w+1; a lane owns 4 consecutive j per 128-column tile
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int h = 2 * warp + hh;
-        float* Lh = L + h * ldL;
+        const float4* L4 = reinterpret_cast<const float4*>(L + h * ldL);
+        float4 v[IPA_MAX_JB];
         float mx = -INFINITY;
-        for (int j = lane; j < ldL; j += 32) mx = fmaxf(mx, Lh[j]);
+#pragma unroll
+        for (int q = 0; q < IPA_MAX_JB; ++q)
+          if (q < JB) {
+            v[q] = L4[lane + 32 * q];
+            mx = fmaxf(mx, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
+          }
         mx = warp_max(mx);
         float sum = 0.f;
-        for (int j = lane; j < ldL; j += 32) {
-          const float e = expf(Lh[j] - mx);
-          Lh[j] = e;
-          sum += e;
-        }
+        constexpr float LOG2E = 1.4426950408889634f;
+#pragma unroll
+        for (int q = 0; q < IPA_MAX_JB; ++q)
+          if (q < JB) {
+            v[q].x = exp2f((v[q].x - mx) * LOG2E);
+            v[q].y = exp2f((v[q].y - mx) * LOG2E);
+            v[q].z = exp2f((v[q].z - mx) * LOG2E);
+            v[q].w = exp2f((v[q].w - mx) * LOG2E);
+            sum += (v[q].x + v[q].y) + (v[q].z + v[q].w);
+          }
         sum = warp_sum(sum);
         const float inv = 1.f / sum;
         float* Sh = Srow0 + h * hs;
-        for (int j = lane; j < ldL; j += 32) {
-          const float p = Lh[j] * inv;
-          if (j < N) Sh[j] = p;
-          const __half ph = __float2half_rn(p);
-          const __half pl = __float2half_rn(p - __half2float(ph));
-          const int t = j >> 7, jj = j & 127;
-          uint8_t* dst = Pimg + t * IPA_PIMG_TILE + (jj >> 6) * 2048 + h * 128 + ((((jj & 63) >> 3) ^ (h & 7)) << 4) + (jj & 7) * 2;
-          *reinterpret_cast<__half*>(dst) = ph;
-          *reinterpret_cast<__half*>(dst + 1024) = pl;  // row h + 8 (same swizzle phase)
-        }
+#pragma unroll
+        for (int q = 0; q < IPA_MAX_JB; ++q)
+          if (q < JB) {
+            const float4 p = make_float4(v[q].x * inv, v[q].y * inv, v[q].z * inv, v[q].w * inv);
+            const int j = 4 * (lane + 32 * q);
+            if (j < a.ldS) *reinterpret_cast<float4*>(Sh + j) = p;  // columns in [N, ldS) are zero
+            const __half2 h01 = __floats2half2_rn(p.x, p.y), h23 = __floats2half2_rn(p.z, p.w);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(p.x - f01.x, p.y - f01.y), l23 = __floats2half2_rn(p.z - f23.x, p.w - f23.y);
+            const int jj = j & 127;
+            uint8_t* dst = Pimg + q * IPA_PIMG_TILE + (jj >> 6) * 2048 + h * 128 + ((((jj & 63) >> 3) ^ (h & 7)) << 4) + (jj & 7) * 2;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            *reinterpret_cast<uint2*>(dst + 1024) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+          }
       }
       fence_proxy_async();
       mbar_arrive(p_full);
+      if (tid == 0) IPA_TS(31);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // every warp is done with L
+      if (it + 1 < nrows) {                            // overlaps GEMM-o of this row
+        prefetch_S(it + 1);
+        logits(it + 1);
+      }
+      if (tid == 0) IPA_TS(30);
       // ---- o_pair: D2[c, h] (hi + lo columns) -> ozs[h][c] -> down_z
       mbar_wait(d2_full, it & 1);
       tc_fence_after();
+      if (tid == 0) IPA_TS(32);
       {
         float ov[16];
         tmem_ld16(D2 + lane_base, ov);
@@ -358,23 +427,26 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       {
         float acc0 = bd0, acc1 = bd1;
-        const float* o = ozs + hh_out * IPA_OZ_LD;
-        const float* w = WdT + d0;
+        const float4* o4 = reinterpret_cast<const float4*>(ozs + hh_out * IPA_OZ_LD);
+        const float4* w4 = reinterpret_cast<const float4*>(Wd4);
 #pragma unroll 8
-        for (int c = 0; c < C_Z; ++c) {
-          const float x = o[c];
-          acc0 = fmaf(w[c * IPA_WDT_LD], x, acc0);
-          acc1 = fmaf(w[c * IPA_WDT_LD + 1], x, acc1);
+        for (int cgp = 0; cgp < C_Z / 4; ++cgp) {
+          const float4 x = o4[cgp];
+          const float4 w0 = w4[cgp * (C_Z / 4) + dq], w1 = w4[cgp * (C_Z / 4) + dq + 16];
+          acc0 = fmaf(w0.x, x.x, fmaf(w0.y, x.y, fmaf(w0.z, x.z, fmaf(w0.w, x.w, acc0))));
+          acc1 = fmaf(w1.x, x.x, fmaf(w1.y, x.y, fmaf(w1.z, x.z, fmaf(w1.w, x.w, acc1))));
         }
-        float* dst = a.cat + (long long)row * CAT + CATP_PAIR + hh_out * (C_Z / 4) + d0;
-        *reinterpret_cast<float2*>(dst) = make_float2(acc0, acc1);
+        float* dst = a.cat + (long long)row * CAT + CATP_PAIR + hh_out * (C_Z / 4);
+        dst[dq] = acc0;
+        dst[dq + 16] = acc1;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // ozs aliases L: the next row's logits may not land before every thread is done
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // ozs aliases the probability images: the next softmax may not start earlier
+      if (tid == 0) IPA_TS(33);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 }  // namespace fdpt
