@@ -1165,7 +1165,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
   switch (option) {
     case FDPT_OPT_GEMM_TC: ctx->gemm_tc = value != 0; return FDPT_OK;
     case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
-    case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); return FDPT_OK;
+    case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {

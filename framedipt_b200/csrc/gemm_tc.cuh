@@ -317,6 +317,8 @@ inline bool aligned16(const void* p, long long ld, long long s1, long long s2) {
 
 // Same contract as launch_gemm (gemm_simt.cuh). Problems the tensor-core tile shape cannot serve well (N < 16, or the
 // pair-broadcast epilogue) stay on the SIMT kernel.
+static int g_force_bn = 0;  // bring-up knob (FDPT_OPT_DEBUG_FLAGS bit 3)
+
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, bool b_kmajor, int batch, cudaStream_t st, int num_sms) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
   if (g.N < 16 || g.U != nullptr || g.K <= 0) return launch_gemm(g, b_kmajor, batch, st);
@@ -325,7 +327,9 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, bool b_kmajor, int batch, c
   a.b_kmajor = b_kmajor ? 1 : 0;
   const long long tiles128 = (long long)((g.M + GT_BM - 1) / GT_BM) * ((g.N + 127) / 128) * batch;
   (void)tiles128; (void)num_sms;
-  a.bn = 64;  // 96 KB of shared memory per CTA -> two CTAs per SM
+  // 64 columns: 96 KB of shared memory per CTA -> two CTAs per SM (best for the latency-bound single GEMMs); the batched attention
+  // GEMMs (many tiles, L2-traffic bound) prefer 128 columns: each operand tile is loaded and split for half as many CTAs
+  a.bn = ((batch >= 8 || g_force_bn == 128) && g.N > 128) ? 128 : 64;
   a.a_vec = aligned16(g.A, g.lda, g.sA1, g.sA2);
   a.b_vec = aligned16(g.B, g.ldb, g.sB1, g.sB2);
   a.c_vec = aligned16(g.C, g.ldc, g.sC1, g.sC2) && (!g.residual || aligned16(g.residual, g.ldr, 0, 0));

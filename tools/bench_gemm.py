@@ -9,9 +9,9 @@ shapes = [("node 256x256", 1, 2800, 256, 256, True), ("tfmr in_proj", 1, 2800, 9
           ("ipa proj", 1, 2800, 6816, 256, True), ("ipa linear_out", 1, 2800, 256, 2688, True), ("ipa S", 64, 350, 350, 280, True),
           ("ipa AV", 64, 350, 292, 350, False), ("tfmr S", 32, 350, 350, 80, True), ("tfmr PV", 32, 350, 80, 350, False),
           ("edge chunk", 1, 1 << 20, 128, 128, True), ("cfg3 proj", 1, 16384, 6816, 256, True)]
-for use_tc in (1, 0):
-    ctx.set_option(0, use_tc)
-    print("== tcgen05 split-TF32" if use_tc else "== SIMT fp32")
+for use_tc in (1, 2):
+    ctx.set_option(3, 8 if use_tc == 2 else 0)
+    print("== gemm_tc bn=64 (2 CTAs/SM)" if use_tc == 1 else "== gemm_tc bn=128 where N > 128")
     for name, Bt, M, N, K, km in shapes:
         a = torch.randn(Bt, M, K, device="cuda")
         b = torch.randn(Bt, N, K, device="cuda") if km else torch.randn(Bt, K, N, device="cuda")
