@@ -370,9 +370,18 @@ struct Lin {
         a.x_vec = tc::aligned16(x, lda, 0, 0);
         a.y_vec = 0;
         dim3 grid(m_tiles, (pw.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta);
-        tc::lin_tc_kernel<<<grid, tc::LT_THREADS, tc::lin_tc_smem_bytes(pw.nkb, a.units, a.stg_cols), st>>>(a);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(tc::LT_THREADS);
+        cfg.dynamicSmemBytes = tc::lin_tc_smem_bytes(pw.nkb, a.units, a.stg_cols);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = tc::g_use_pdl;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel, a);
         ctx->launches++;
-        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "lin_tc launch: %s", cudaGetErrorString(e));
         return FDPT_OK;
       }
@@ -1165,7 +1174,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
   switch (option) {
     case FDPT_OPT_GEMM_TC: ctx->gemm_tc = value != 0; return FDPT_OK;
     case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
-    case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; return FDPT_OK;
+    case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; tc::g_use_pdl = (value & 16) ? 0 : 1; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {

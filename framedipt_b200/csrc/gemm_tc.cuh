@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(GemmTcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == GT_PRODUCERS / 32) {
     // ============================ MMA issuer ============================
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(GemmTcArgs a) {
     // one register tile per operand (<= 112 registers so that two CTAs share an SM: while one waits on its loads or runs its
     // epilogue, the other converts / multiplies)
     RegTile ta, tb;
+    pdl_wait();  // operands (and residual / C) belong to the predecessor kernel until it has completed
     for (int kb = 0; kb < nkb; ++kb) {
       load_tile(pa, kb, ta);
       load_tile(pb, kb, tb);
@@ -318,6 +320,7 @@ inline bool aligned16(const void* p, long long ld, long long s1, long long s2) {
 // Same contract as launch_gemm (gemm_simt.cuh). Problems the tensor-core tile shape cannot serve well (N < 16, or the
 // pair-broadcast epilogue) stay on the SIMT kernel.
 static int g_force_bn = 0;  // bring-up knob (FDPT_OPT_DEBUG_FLAGS bit 3)
+static int g_use_pdl = 1;   // programmatic dependent launch of the GEMM kernels (FDPT_OPT_DEBUG_FLAGS bit 4 turns it off)
 
 inline cudaError_t launch_gemm_tc(const GemmArgs& g, bool b_kmajor, int batch, cudaStream_t st, int num_sms) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
@@ -334,8 +337,17 @@ inline cudaError_t launch_gemm_tc(const GemmArgs& g, bool b_kmajor, int batch, c
   a.b_vec = aligned16(g.B, g.ldb, g.sB1, g.sB2);
   a.c_vec = aligned16(g.C, g.ldc, g.sC1, g.sC2) && (!g.residual || aligned16(g.residual, g.ldr, 0, 0));
   dim3 grid((g.M + GT_BM - 1) / GT_BM, (g.N + a.bn - 1) / a.bn, batch);
-  gemm_tc_kernel<<<grid, GT_THREADS, gemm_tc_smem_bytes(a.bn), st>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GT_THREADS);
+  cfg.dynamicSmemBytes = gemm_tc_smem_bytes(a.bn);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel, a);
 }
 
 }  // namespace tc

@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 9) {
-    // ============================ weight loader ============================
+    // ============================ weight loader (weights are static: no need to wait for the predecessor kernel) ============================
     if (lane == 0) {
       int it = 0;  // ring unit counter: 2 per k-block (hi, lo)
       for (int nt = nt_begin; nt < nt_end; ++nt)
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
     }
   } else {
     // ============================ workers: stage X once, then epilogues ============================
+    pdl_wait();  // X (and residual / Y) belong to the predecessor kernel until it has completed
     {
       ChunkPlan pa;
       const int r0 = tid >> 3, c = tid & 7;

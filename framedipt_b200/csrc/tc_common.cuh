@@ -19,6 +19,14 @@ namespace tc {
 
 FDPT_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is still
+// running (as soon as every predecessor CTA has called launch_dependents or exited); it must call pdl_wait() before it touches
+// anything the predecessor wrote.  Used by the node-side GEMM kernels to overlap their prologue (barrier init, TMEM allocation, weight
+// prefetch) with the tail of the previous kernel.
+FDPT_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+FDPT_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier ---------------------------------------------------------------------------------------
 FDPT_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
