@@ -264,3 +264,24 @@ def test_forward_vs_oracle_ring_streaming():
 
 def test_forward_vs_oracle_de_novo():
     _oracle_forward_case(("dn150", 2, (150,), (), 10), True, 13, 0.8)
+
+
+def test_long_trajectory_vs_oracle(model, state_dict):
+    """200 free-running steps (N=64, config-#1 geometry) against the CPU oracle with the same noise stream: the divergence must stay
+    inside the 1e-3 A budget over a long horizon too (the configs the metric is quoted on run 200-500 steps)."""
+    from framedipt_b200 import synthetic
+    from framedipt_b200.inference import inference_fn
+    from oracle import framedipt_oracle as orc
+
+    m, diffuser = model
+    wl = synthetic.Workload("long64", 1, (64,), ((20, 32),), 200)
+    np.random.seed(321)
+    feats = synthetic.make_features(wl, diffuser, seed=5)
+    noise = synthetic.draw_noise(wl.num_t, wl.batch, wl.n_res)
+    out = inference_fn(m, diffuser, {k: v.to("cuda") for k, v in feats.items()}, num_t=wl.num_t, min_t=0.01, aux_traj=True, noise_scale=0.1,
+                       inpainting=True, input_aatype=True, noise=noise)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = orc.inference_loop(state_dict, feats, num_t=wl.num_t, min_t=0.01, noise=noise, noise_scale=0.1)
+    r = bb_rmsd(out["prot_traj"][0][:, :, :5], ref["prot_traj"][0][:, :, :5])
+    print(f"200-step trajectory vs oracle: per-residue RMSD max {r.max():.3e} mean {r.mean():.3e}")
+    assert r.max() < 1e-3
