@@ -1154,6 +1154,62 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
   return FDPT_OK;
 }
 
+// ---- PDB text of one backbone model (host-side; "next" row (f)(2) of SURVEY §8) ------------------------------------------
+// Restates framedipt/protein/protein.py:165-279 (to_pdb) for the 5 backbone slots the sampler produces (atom37 slots 0..4 =
+// N, CA, C, CB, O), with the atom mask of framedipt/analysis/utils.py:128-129 (sum |xyz| > 1e-7).  Byte-for-byte the reference text.
+int64_t fdpt_to_pdb(const float* atom37_bb, const int32_t* aatype, const int32_t* residue_index, const int32_t* chain_index,
+                    const float* b_factors, int n_res, int model, int add_end, char* out, int64_t cap) {
+  static const char* kRes3[21] = {"ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE", "LEU",
+                                  "LYS", "MET", "PHE", "PRO", "SER", "THR", "TRP", "TYR", "VAL", "UNK"};
+  static const char* kAtom[5] = {"N", "CA", "C", "CB", "O"};
+  static const char kChains[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789";
+  if (!atom37_bb || !out || n_res <= 0 || cap <= 0) return FDPT_ERR_INVALID;
+  for (int i = 0; i < n_res; ++i) {
+    if (aatype && (aatype[i] < 0 || aatype[i] > 20)) return FDPT_ERR_INVALID;        // "Invalid aatypes." / res_index range
+    if (chain_index && (chain_index[i] < 0 || chain_index[i] >= 62)) return FDPT_ERR_INVALID;  // PDB_MAX_CHAINS
+  }
+  int64_t pos = 0;
+  char line[128];
+  auto emit = [&](int len) -> bool {  // line.ljust(80) + newline: pads short lines, never truncates (coordinates >= 1e4 widen a line)
+    if (len < 0 || len >= (int)sizeof(line)) return false;
+    const int w = len < 80 ? 80 : len;
+    if (pos + w + 1 > cap) return false;
+    memcpy(out + pos, line, len);
+    if (len < 80) memset(out + pos + len, ' ', 80 - len);
+    out[pos + w] = '\n';
+    pos += w + 1;
+    return true;
+  };
+  auto aa = [&](int i) { return aatype ? aatype[i] : 0; };
+  auto ch = [&](int i) { return chain_index ? chain_index[i] : 0; };
+  auto ri = [&](int i) { return residue_index ? residue_index[i] : i; };
+  if (!emit(snprintf(line, sizeof(line), "MODEL     %d", model))) return FDPT_ERR_INVALID;
+  int atom_index = 1, last_chain = ch(0);
+  for (int i = 0; i < n_res; ++i) {
+    if (last_chain != ch(i)) {
+      if (!emit(snprintf(line, sizeof(line), "%-6s%5d      %3s %c%4d", "TER", atom_index, kRes3[aa(i - 1)], kChains[ch(i - 1)], ri(i - 1))))
+        return FDPT_ERR_INVALID;
+      last_chain = ch(i);
+      ++atom_index;
+    }
+    for (int k = 0; k < 5; ++k) {
+      const float* p = atom37_bb + ((long long)i * 5 + k) * 3;
+      if (!(fabsf(p[0]) + fabsf(p[1]) + fabsf(p[2]) > 1e-7f)) continue;
+      const double bf = b_factors ? (double)b_factors[(long long)i * 5 + k] : 0.0;
+      const int len = snprintf(line, sizeof(line), "%-6s%5d  %-3s%1s%3s %c%4d%1s   %8.3f%8.3f%8.3f%6.2f%6.2f          %2c%2s", "ATOM", atom_index,
+                               kAtom[k], "", kRes3[aa(i)], kChains[ch(i)], ri(i), "", (double)p[0], (double)p[1], (double)p[2], 1.0, bf,
+                               kAtom[k][0], "");
+      if (!emit(len)) return FDPT_ERR_INVALID;
+      ++atom_index;
+    }
+  }
+  if (!emit(snprintf(line, sizeof(line), "%-6s%5d      %3s %c%4d", "TER", atom_index, kRes3[aa(n_res - 1)], kChains[ch(n_res - 1)], ri(n_res - 1))))
+    return FDPT_ERR_INVALID;
+  if (!emit(snprintf(line, sizeof(line), "ENDMDL"))) return FDPT_ERR_INVALID;
+  if (add_end && !emit(snprintf(line, sizeof(line), "END"))) return FDPT_ERR_INVALID;
+  return pos;
+}
+
 // ---- unit entry points ------------------------------------------------------------------------------------
 int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act, float* y, void* stream) {
   if (!ctx || !x || !w || !y) return FDPT_ERR_INVALID;

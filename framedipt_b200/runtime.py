@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
         L.fdpt_matmul.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_int,
                                   C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]
         L.fdpt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.fdpt_to_pdb.restype = C.c_int64
+        L.fdpt_to_pdb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int64]
         L.fdpt_bench_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.POINTER(C.c_float)]
         L.fdpt_debug_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]

@@ -148,6 +148,13 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
                 const float* t_emb_tab, const double* noise, int self_condition, int center,
                 int diffuse_rot, int diffuse_trans, const fdpt_traj* out, void* stream);
 
+/* replaces: framedipt.protein.protein.to_pdb (protein.py:165-279) as called by analysis.utils.write_prot_to_pdb (utils.py:78-156)
+ * for one model of backbone atoms.  HOST function (no GPU work): atom37_bb [n_res,5,3] host floats (atom37 slots 0..4 = N,CA,C,CB,O;
+ * all-zero atoms are masked out like the reference's atom37_mask), aatype / residue_index / chain_index [n_res] (NULL: ALA / 0..n-1 /
+ * chain 0), b_factors [n_res,5] or NULL.  Writes the PDB text (80-column lines) into out[cap]; returns the byte count or < 0. */
+int64_t fdpt_to_pdb(const float* atom37_bb, const int32_t* aatype, const int32_t* residue_index, const int32_t* chain_index,
+                    const float* b_factors, int n_res, int model, int add_end, char* out, int64_t cap);
+
 /* number of kernel launches enqueued by this context since creation (bench.py's gpu_launches) */
 int64_t fdpt_launch_count(const fdpt_ctx* ctx);
 
