@@ -545,22 +545,22 @@ int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaSt
     const auto& L = p.tf[l];
     RET(lin(w.tf_x, TF_D, L.Win, TF_D, L.bin, w.qkv, 3 * TF_D, M, 3 * TF_D, TF_D));
     {
-      GemmArgs g;  // S[b,h] = Q K^T
+      GemmArgs g;  // S[b,h] = Q K^T  (rows padded to ldS floats: 16-byte aligned rows for the softmax and the P V operand loads)
       g.A = w.qkv; g.lda = 3 * TF_D; g.sA1 = (long long)N * 3 * TF_D; g.sA2 = TF_DH;
       g.B = w.qkv + TF_D; g.ldb = 3 * TF_D; g.sB1 = (long long)N * 3 * TF_D; g.sB2 = TF_DH;
-      g.C = w.S; g.ldc = N; g.sC1 = (long long)TF_H * N * N; g.sC2 = (long long)N * N;
+      g.C = w.S; g.ldc = w.ldS; g.sC1 = (long long)TF_H * N * w.ldS; g.sC2 = (long long)N * w.ldS;
       g.M = N; g.N = N; g.K = TF_DH; g.batch2 = TF_H;
       CK(gemm_dispatch(ctx, g, true, B * TF_H, st));
       ctx->launches++;
     }
     {
       const long long rows = (long long)B * TF_H * N;
-      softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.S, rows, N, TF_H * N, 1.0f / sqrtf((float)TF_DH), mask);
+      softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.S, rows, N, w.ldS, TF_H * N, 1.0f / sqrtf((float)TF_DH), mask);
       LAUNCH_CHECK();
     }
     {
       GemmArgs g;  // O = P V
-      g.A = w.S; g.lda = N; g.sA1 = (long long)TF_H * N * N; g.sA2 = (long long)N * N;
+      g.A = w.S; g.lda = w.ldS; g.sA1 = (long long)TF_H * N * w.ldS; g.sA2 = (long long)N * w.ldS;
       g.B = w.qkv + 2 * TF_D; g.ldb = 3 * TF_D; g.sB1 = (long long)N * 3 * TF_D; g.sB2 = TF_DH;
       g.C = w.att_o; g.ldc = TF_D; g.sC1 = (long long)N * TF_D; g.sC2 = TF_DH;
       g.M = N; g.N = TF_DH; g.K = N; g.batch2 = TF_H;

@@ -259,27 +259,50 @@ __global__ void compose_update_kernel(int M, const float* __restrict__ upd, cons
 // Row softmax with scale and key mask (sequence transformer; boolean key-padding semantics).
 // S[rows, N]: row = ((b*H + h)*N + i).  One warp per row, in place.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long rows, int N, int rows_per_batch,
+// Rows have stride ld (multiple of 4, >= N, <= 1024); the row lives in registers between the single read and the single write.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long rows, int N, int ld, int rows_per_batch,
                                                            float scale, const float* __restrict__ keymask) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const long long b = row / rows_per_batch;
-  float* s = S + row * N;
+  float4* s4 = reinterpret_cast<float4*>(S + row * ld);
   const float* km = keymask + b * N;
+  const int nch = ld >> 2;  // 16-byte chunks per row
+  float4 v[8];
   float mx = -INFINITY;
-  for (int j = lane; j < N; j += 32)
-    if (km[j] != 0.f) mx = fmaxf(mx, s[j] * scale);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = lane + 32 * q;
+    v[q] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (c < nch) {
+      const float4 x = s4[c];
+      const int j = 4 * c;
+      v[q].x = (j < N && km[j] != 0.f) ? x.x * scale : -INFINITY;
+      v[q].y = (j + 1 < N && km[j + 1] != 0.f) ? x.y * scale : -INFINITY;
+      v[q].z = (j + 2 < N && km[j + 2] != 0.f) ? x.z * scale : -INFINITY;
+      v[q].w = (j + 3 < N && km[j + 3] != 0.f) ? x.w * scale : -INFINITY;
+      mx = fmaxf(mx, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
+    }
+  }
   mx = warp_max(mx);
+  if (mx == -INFINITY) mx = 0.f;  // fully masked row: all probabilities 0
   float sum = 0.f;
-  for (int j = lane; j < N; j += 32) {
-    const float e = (km[j] != 0.f) ? expf(s[j] * scale - mx) : 0.f;
-    s[j] = e;
-    sum += e;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    v[q].x = expf(v[q].x - mx);
+    v[q].y = expf(v[q].y - mx);
+    v[q].z = expf(v[q].z - mx);
+    v[q].w = expf(v[q].w - mx);
+    sum += (v[q].x + v[q].y) + (v[q].z + v[q].w);
   }
   sum = warp_sum(sum);
   const float inv = sum > 0.f ? 1.f / sum : 0.f;
-  for (int j = lane; j < N; j += 32) s[j] *= inv;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = lane + 32 * q;
+    if (c < nch) s4[c] = make_float4(v[q].x * inv, v[q].y * inv, v[q].z * inv, v[q].w * inv);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
