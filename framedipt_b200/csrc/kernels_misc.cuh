@@ -55,45 +55,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, float* y
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pair LayerNorm (C = 128) writing the fp16 tile-image layout of z used by the tcgen05 pair kernels (et_fused.cuh):
-//   image[(b*N+i)][jb][k-block][row j%128][128 B swizzled];  y = LN(x) * gamma + beta, times m[b,i] m[b,j].
-// One warp per pair row; lane covers channels 4*lane .. 4*lane+3.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pair_ln_image_kernel(const float* __restrict__ x, __half* __restrict__ img,
-                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            long long rows, const float* __restrict__ mask, int nres, int JB,
-                                                            long long row0) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float4 v4 = *reinterpret_cast<const float4*>(x + row * C_Z + lane * 4);
-  float v[4] = {v4.x, v4.y, v4.z, v4.w};
-  const float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.f / C_Z);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float d = v[i] - mean;
-    q += d * d;
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / C_Z) + 1e-5f);
-  const long long p = row0 + row;
-  const long long nn = (long long)nres * nres;
-  const long long b = p / nn;
-  const int rem = (int)(p - b * nn);
-  const int i = rem / nres, j = rem - i * nres;
-  const float m = mask[b * nres + i] * mask[b * nres + j];
-  const float4 g4 = *reinterpret_cast<const float4*>(gamma + lane * 4);
-  const float4 b4 = *reinterpret_cast<const float4*>(beta + lane * 4);
-  const float o0 = ((v[0] - mean) * rstd * g4.x + b4.x) * m, o1 = ((v[1] - mean) * rstd * g4.y + b4.y) * m;
-  const float o2 = ((v[2] - mean) * rstd * g4.z + b4.z) * m, o3 = ((v[3] - mean) * rstd * g4.w + b4.w) * m;
-  const __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
-  const int c = lane * 4, r = j & 127;
-  uint8_t* dst = reinterpret_cast<uint8_t*>(img) + ((b * nres + i) * (long long)JB + (j >> 7)) * 32768 + (c >> 6) * 16384 + r * 128 +
-                 ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2;
-  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-}
-
-// ------------------------------------------------------------------------------------------------
 // Node features (Embedder.forward, score_network.py:153-182):
 //   feat1d[m, :F1] = [onehot21(aatype) | t_emb (eps row on fixed residues) | fixed_mask]      (F1 = 54, or 33 without aatype)
 //   node_feat[m, :F1+32] = [feat1d | idx_emb]
@@ -132,54 +93,6 @@ __global__ void node_feats_kernel(int M, int N, int with_aatype, const int32_t* 
     node_feat[(long long)m * FN + c] = v;
     if (c < F1) feat1d[(long long)m * F1 + c] = v;
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Edge-embedder layer 1, factorised:
-//   h1[p, c] = relu( PA[b,i,c] + PB[b,j,c] + RelProj[seq_i - seq_j - rel_min, c] + W0[c, dcol0 + bin(d_ij)] )
-// PA already holds the layer bias.  bin: (d > lower[k]) & (d < upper[k]), upper[21] = 1e8
-// (framedipt/data/utils.py:541-550); d = ||sc_ca_i - sc_ca_j|| in fp32.
-// One warp per pair, lane covers 4 channels.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) edge_l1_kernel(long long row0, long long rows, int N, const float* __restrict__ PA,
-                                                      const float* __restrict__ PB, const float* __restrict__ RelProj,
-                                                      const int32_t* __restrict__ seq_idx, int rel_min, int rel_count,
-                                                      const float* __restrict__ sc_ca, const float* __restrict__ bin_lower,
-                                                      const float* __restrict__ W0, int ldw, int dcol0,
-                                                      float* __restrict__ h1) {
-  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const long long p = row0 + r;
-  const long long nn = (long long)N * N;
-  const long long b = p / nn;
-  const int rem = (int)(p - b * nn);
-  const int i = rem / N, j = rem - i * N;
-  const long long mi = b * N + i, mj = b * N + j;
-  const float dx = sc_ca[mi * 3 + 0] - sc_ca[mj * 3 + 0];
-  const float dy = sc_ca[mi * 3 + 1] - sc_ca[mj * 3 + 1];
-  const float dz = sc_ca[mi * 3 + 2] - sc_ca[mj * 3 + 2];
-  const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-  int bin = -1;
-#pragma unroll 1
-  for (int k = 0; k < NBINS; ++k) {
-    const float lo = bin_lower[k];
-    const float hi = (k + 1 < NBINS) ? bin_lower[k + 1] : 1e8f;
-    if (d > lo && d < hi) bin = k;
-  }
-  int rel = seq_idx[mi] - seq_idx[mj] - rel_min;
-  rel = min(max(rel, 0), rel_count - 1);
-  const int c = lane * 4;
-  const float4 a = *reinterpret_cast<const float4*>(PA + mi * C_Z + c);
-  const float4 bb = *reinterpret_cast<const float4*>(PB + mj * C_Z + c);
-  const float4 rr = *reinterpret_cast<const float4*>(RelProj + (long long)rel * C_Z + c);
-  float v[4] = {a.x + bb.x + rr.x, a.y + bb.y + rr.y, a.z + bb.z + rr.z, a.w + bb.w + rr.w};
-  if (bin >= 0) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] += W0[(long long)(c + k) * ldw + dcol0 + bin];
-  }
-  float4 o = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-  *reinterpret_cast<float4*>(h1 + r * C_Z + c) = o;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -285,3 +285,34 @@ def test_long_trajectory_vs_oracle(model, state_dict):
     r = bb_rmsd(out["prot_traj"][0][:, :, :5], ref["prot_traj"][0][:, :, :5])
     print(f"200-step trajectory vs oracle: per-residue RMSD max {r.max():.3e} mean {r.mean():.3e}")
     assert r.max() < 1e-3
+
+
+def test_linear_shapes_cover_the_packed_kernel(ctx):
+    """fdpt_linear runs the A-stationary lin_tc kernel (weights split on the fly for this unit entry): ragged M, tiny and wide N,
+    K not a multiple of 64 / 8, every k-block count up to 5."""
+    g = torch.Generator().manual_seed(5)
+    for (M, N, K, act) in [(1, 6, 256, 0), (129, 2, 256, 0), (300, 128, 54, 0), (2800, 960, 320, 1), (77, 6816, 256, 0), (500, 64, 65, 1),
+                           (128, 384, 128, 0), (1000, 320, 192, 1)]:
+        x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+        y = ctx.linear(x.cuda(), w.cuda(), b.cuda(), act).cpu()
+        ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        if act:
+            ref = ref.relu()
+        err = (y - ref.float()).abs().max().item()
+        assert err < 1e-5 * max(1.0, ref.abs().max().item()), (M, N, K, err)
+
+
+def test_tiny_and_oversized_inputs(model):
+    """N = 5 (far below one tile) runs and matches the oracle; N > 1024 is rejected loudly (no fallback)."""
+    from framedipt_b200 import runtime
+
+    _oracle_forward_case(("tiny5", 1, (5,), ((1, 3),), 4), False, 21, 0.5)
+    m, diffuser = model
+    from framedipt_b200 import synthetic
+
+    wl = synthetic.Workload("big", 1, (1100,), ((10, 20),), 4)
+    np.random.seed(1)
+    feats = synthetic.make_features(wl, diffuser, seed=1)
+    feats["t"] = torch.ones(1)
+    with pytest.raises(runtime.FdptError):
+        m({k: v.to("cuda") for k, v in feats.items()})
