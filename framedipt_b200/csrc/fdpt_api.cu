@@ -18,6 +18,7 @@
 #include "kernels_ipa.cuh"
 #include "kernels_misc.cuh"
 #include "et_fused.cuh"
+#include "et_fused2.cuh"
 #include "edge_embed_fused.cuh"
 #include "tc_linear.cuh"
 #include "gemm_tc.cuh"
@@ -111,6 +112,7 @@ struct fdpt_ctx {
     int64_t launches = 0;
   } step_graph;
   int use_graph = 1;
+  int et_pair = 0;  // 1: EdgeTransition on CTA pairs (et_fused2.cuh, experimental: slower); 0: single-CTA kernel (et_fused.cuh)
   cudaStream_t own_stream = nullptr;   // the legacy default stream cannot be captured: fdpt_sample then runs on this stream,
   cudaEvent_t fence_in = nullptr, fence_out = nullptr;  // fenced against the caller's stream with these events
   long long* et_dbg = nullptr;  // optional clock64 timeline buffer of the EdgeTransition kernel (FDPT_OPT_ET_TIMELINE)
@@ -524,8 +526,23 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   a.ln_g = p.eln_g; a.ln_b = p.eln_b; a.mask = mask; a.W1cat = p.imgW1cat; a.W2 = p.imgW2; a.W3cat = p.imgW3cat;
   a.tiles = M * w.JB;
   a.dbg = (ctx->dbg_flags & 4) ? nullptr : ctx->et_dbg;
-  const int grid = (int)std::min<long long>(ctx->num_sms, a.tiles);
-  tc::et_fused_kernel<<<grid, tc::ET_THREADS, tc::et_smem_bytes(), st>>>(a);
+  a.flags = (ctx->dbg_flags >> 5) & 7;  // debug flag bits 32 / 64 / 128 -> EtArgs.flags 1 / 2 / 4
+  if (ctx->et_pair && a.tiles >= 2) {
+    const long long pairs = (a.tiles + 1) / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(ctx->num_sms / 2, pairs));
+    cfg.blockDim = dim3(tc::ET_THREADS);
+    cfg.dynamicSmemBytes = tc::et2_smem_bytes();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, tc::et_fused2_kernel, a));
+  } else {
+    const int grid = (int)std::min<long long>(ctx->num_sms, a.tiles);
+    tc::et_fused_kernel<<<grid, tc::ET_THREADS, tc::et_smem_bytes(), st>>>(a);
+  }
   LAUNCH_CHECK();
   return FDPT_OK;
 }
@@ -709,6 +726,7 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaDeviceGetAttribute(&ctx->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
   cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::et_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et_smem_bytes());
+  cudaFuncSetAttribute(tc::et_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et2_smem_bytes());
   cudaFuncSetAttribute(tc::ee_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ee_smem_bytes());
   cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::tc_linear_smem_bytes(512));
   cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_tc_smem_bytes(128));
@@ -755,7 +773,7 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaEventDestroy(ctx->fence_in);
     cudaEventDestroy(ctx->fence_out);
   }
-  cudaFree(ctx->et_dbg);
+  cudaFreeHost(ctx->et_dbg);
   for (auto& kv : ctx->packed) cudaFree(kv.second.img);
   cudaFree(ctx->top.imgE0);
   cudaFree(ctx->top.imgE2);
@@ -1232,10 +1250,14 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
     case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
     case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; tc::g_use_pdl = (value & 16) ? 0 : 1; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
+    case FDPT_OPT_ET_PAIR: ctx->et_pair = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {
-        CK(cudaMalloc(&ctx->et_dbg, 8 * 48 * sizeof(long long)));
-        CK(cudaMemset(ctx->et_dbg, 0, 8 * 48 * sizeof(long long)));
+        // host-mapped so that the stamps (and the barrier-timeout records of tc::mbar_wait) survive a device-side trap
+        CK(cudaHostAlloc(&ctx->et_dbg, (8 * 48 + 32) * sizeof(long long), cudaHostAllocMapped));
+        memset(ctx->et_dbg, 0, (8 * 48 + 32) * sizeof(long long));
+        unsigned long long* fail_buf = reinterpret_cast<unsigned long long*>(ctx->et_dbg) + 8 * 48;
+        CK(cudaMemcpyToSymbol(tc::g_mbar_fail_buf, &fail_buf, sizeof(fail_buf)));
       }
       return FDPT_OK;
     default: return fail(ctx, FDPT_ERR_INVALID, "unknown option %d", option);
@@ -1243,9 +1265,9 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
 }
 
 int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n) {
-  if (!ctx || !out || !ctx->et_dbg || n > 8 * 48) return FDPT_ERR_INVALID;
-  CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, ctx->et_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (!ctx || !out || !ctx->et_dbg || n > 8 * 48 + 32) return FDPT_ERR_INVALID;
+  cudaDeviceSynchronize();  // may report a sticky error after a trap: the host-mapped buffer is still readable
+  memcpy(out, ctx->et_dbg, n * sizeof(long long));
   return FDPT_OK;
 }
 

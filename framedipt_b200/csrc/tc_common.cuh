@@ -50,12 +50,27 @@ FDPT_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (reported as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug must trap (reported as a CUDA error) instead of hanging the GPU.  When a host-mapped record buffer
+// is installed (FDPT_OPT_ET_TIMELINE) the first 31 waits that time out leave {block, thread, barrier offset, parity} behind.
+__device__ unsigned long long* g_mbar_fail_buf = nullptr;
+__device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+  unsigned long long* fb = g_mbar_fail_buf;
+  if (fb) {
+    const unsigned long long slot = atomicAdd(fb, 1ull);
+    if (slot < 31)
+      fb[1 + slot] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)threadIdx.x << 32) | ((unsigned long long)(bar_addr & 0xFFFFFF) << 1) | parity;
+    __threadfence_system();
+    const long long t1 = clock64();
+    while (clock64() - t1 < 400000000LL) {
+    }
+  }
+  __trap();
+}
 FDPT_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(smem_u32(bar), parity);
   }
 }
 

@@ -310,7 +310,7 @@ class Context:
 
     def debug_read(self, n: int = 8 * 48) -> np.ndarray:
         buf = (C.c_int64 * n)()
-        self._ck(lib().fdpt_debug_read(self._h, buf, n))
+        lib().fdpt_debug_read(self._h, buf, n)
         return np.array(buf[:], np.int64)
 
     def matmul(self, a, b, b_kmajor=True, alpha=1.0):

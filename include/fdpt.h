@@ -186,7 +186,8 @@ int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, i
 int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, float* y, int reps,
                       float* ms_per_call);
 /* bring-up / A-B switches (not needed by integrators) */
-enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */ };
+enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
+       FDPT_OPT_ET_PAIR = 5 /* 1: EdgeTransition kernel on CTA pairs (cta_group::2; experimental, slower); 0 (default): single-CTA kernel */ };
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
 /* clock64 timeline of CTA 0 of the last EdgeTransition kernel ([tile][48] stamps; profiling aid, needs FDPT_OPT_ET_TIMELINE) */
 int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n);

@@ -7,6 +7,8 @@ from framedipt_b200.params import synthetic_state_dict
 ctx = runtime.Context()
 ctx.load_state_dict(synthetic_state_dict(0))
 ctx.set_option(2, 1)
+ctx.set_option(5, int(os.environ.get("ET_PAIR", "1")))
+ctx.set_option(3, int(os.environ.get("DBG_FLAGS", "0")))
 B, N = 8, 350
 node = torch.randn(B, N, 256, device="cuda"); z = torch.randn(B, N, N, 128, device="cuda"); mask = torch.ones(B, N, device="cuda")
 for _ in range(2):
@@ -25,4 +27,5 @@ for tile in (1, 2):
     for t, n in ev:
         print(f"{t:8d} (+{0 if prev is None else t - prev:5d})  {n}")
         prev = t
+print("weight-stage wait cycles (cumulative) local/peer:", [(int(ts[i][40]), int(ts[i][41])) for i in range(0, 6)])
 print("tile period (cycles):", [int(ts[i + 1][0] - ts[i][0]) for i in range(1, 6)])
