@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
   uint64_t* vec_full = d2_empty + 1;          // [2]
   uint64_t* vec_free = vec_full + 2;          // [2]
   uint64_t* stg_full = vec_free + 2;          // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_full + 1);
+  uint64_t* d3_full = stg_full + 1;           // [1] D3 (in D2 columns [0,128)) complete
+  uint64_t* d2c0_empty = d3_full + 1;         // [1] (leader) 16 warp arrivals: E2 has drained D2 columns [0,128)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2c0_empty + 1);
   float* Ui_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][384]
   float* Pf_s = Ui_s + 2 * 384;                            // [2][128]
   float* b2_s = Pf_s + 2 * 128;                            // [384]
@@ -153,6 +155,8 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, 16);
     mbar_init(stg_full, ET_WORKERS);
+    mbar_init(d3_full, 1);
+    mbar_init(d2c0_empty, 16);
     fence_barrier_init();
   }
   for (int k = threadIdx.x; k < 384; k += blockDim.x) b2_s[k] = a.b2[k];
@@ -214,7 +218,11 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       load_z(p_begin);
       load_n(p_begin);
       for (long long p = p_begin; p < p_end; ++p) {
-        for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 0, kb);                                   // G1(0)
+        const uint32_t it = (uint32_t)(p - p_begin);
+        for (int kb = 0; kb < 4; ++kb) {
+          stage(a.W1cat, 384, 0, kb);                                                                // G1(0)
+          ET2_TS(33 + kb);
+        }
         for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 128, kb);                                 // G1(1)
         if (p + 1 < p_end) load_z(p + 1);
         for (int n = 0; n < 3; ++n) for (int kb = 0; kb < 2; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(0)
@@ -267,27 +275,40 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       // ============================ leader: MMA issuer for the pair ============================
       const uint32_t idesc = make_idesc_f16(256, 128);
       uint32_t wit = 0, ds_e = 0, bf[2] = {0, 0}, d2_e = 0, an_f = 0, an_pf = 0;
+      int ts_slot = -1;
+      uint32_t ts_it = 0;
+      const bool prof = a.dbg != nullptr && blockIdx.x == 0;  // timeline / wait accounting of cluster 0 only
+      long long ti = 0, tcm = 0;  // cycles spent issuing MMAs / commits
       long long wl = 0, wp = 0;  // cycles spent waiting for the local / the peer's half of the weight stages
       auto gemm_kb = [&](uint32_t a_addr, uint32_t d_col, bool first_acc) {
         const int s = wit % ET2_WSTAGES;
         const uint32_t ph = (wit / ET2_WSTAGES) & 1;
         if (!(a.flags & 1)) {
-          const long long c0 = clock64();
+          const long long c0 = prof ? clock64() : 0;
           mbar_wait(&w_full[s], ph);
-          const long long c1 = clock64();
+          const long long c1 = prof ? clock64() : 0;
           mbar_wait_cluster(&w_peer[s], ph);
+          const long long c2 = prof ? clock64() : 0;
           wl += c1 - c0;
-          wp += clock64() - c1;
+          wp += c2 - c1;
+          if (ts_slot >= 0 && a.dbg && blockIdx.x == 0 && ts_it < 8) {
+            a.dbg[ts_it * 48 + ts_slot] = c1;
+            a.dbg[ts_it * 48 + ts_slot + 1] = c2;
+          }
         }
         tc_fence_after();
         const uint32_t b_addr = smem_u32(WST + s * ET2_HALF_BYTES);
+        const long long i0 = prof ? clock64() : 0;
         const int reps = (a.flags & 2) ? 0 : (a.flags & 4) ? 2 : 1;  // profiling experiments: no MMAs / every MMA twice
         for (int r = 0; r < reps; ++r) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16_pair(d_col, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc, (first_acc && k == 0 && r == 0) ? 0u : 1u);
         }
+        const long long i1 = prof ? clock64() : 0;
         umma_commit_pair(&w_empty[s]);
+        tcm += (prof ? clock64() : 0) - i1;
+        ti += i1 - i0;
         ++wit;
       };
       for (long long p = p_begin; p < p_end; ++p) {
@@ -309,11 +330,19 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         const uint32_t az = smem_u32(A0z + zs * ET_TILE_BYTES), an = smem_u32(A0n);
         const uint32_t bufa[2] = {smem_u32(BUF), smem_u32(BUF + ET_TILE_BYTES)};
         auto a0_kb = [&](int kb) { return kb < 2 ? az + kb * 16384 : an + (kb - 2) * 16384; };
-        auto G1 = [&]() {
+        auto G1 = [&](int c) {
           mbar_wait_cluster(ds_empty, (ds_e & 1) ^ 1);
           ++ds_e;
           tc_fence_after();
-          for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
+          if (c == 0) ET2_TS(14);
+          for (int kb = 0; kb < 4; ++kb) {
+            ts_it = it;
+            ts_slot = (c == 0 && kb < 3) ? 42 + 2 * kb : -1;
+            gemm_kb(a0_kb(kb), DS, kb == 0);
+            ts_slot = -1;
+            if (c == 0 && kb == 0) ET2_TS(15);
+            if (c == 0 && kb > 0) ET2_TS(36 + kb);
+          }
           umma_commit_pair(ds_full);
         };
         auto G2 = [&](int c) {
@@ -330,22 +359,23 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
           umma_commit_pair(&buf_free[b]);
           if (c == 2) umma_commit_pair(d2_full);
         };
-        G1();
+        G1(0);
         ET2_TS(1);
-        G1();
+        G1(1);
         ET2_TS(2);
         G2(0);
         ET2_TS(3);
-        G1();
+        G1(2);
         ET2_TS(4);
         G2(1);
         ET2_TS(5);
         G2(2);
         ET2_TS(6);
-        mbar_wait_cluster(ds_empty, (ds_e & 1) ^ 1);
-        ++ds_e;
+        // G3 static part -> D3 = D2 columns [0,128) once E2(0) has drained them; DS stays free, so the next tile's G1(0) is issued
+        // right behind this tile's G3 and runs while the workers are in E3
+        mbar_wait_cluster(d2c0_empty, it & 1);
         tc_fence_after();
-        for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
+        for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), D2, kb == 0);
         umma_commit_pair(&az_empty[zs]);
         ET2_TS(7);
         for (int c = 0; c < 3; ++c) {
@@ -353,15 +383,17 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
           mbar_wait_cluster(&buf_full[b], bf[b] & 1);
           ++bf[b];
           tc_fence_after();
-          ET2_TS(11 + c);
-          for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, DS, false);
+          if (c < 1) ET2_TS(11 + c);
+          for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, D2, false);
           if (c != 1) umma_commit_pair(&buf_free[b]);  // BUF[1] becomes the output staging buffer: released by worker thread 0
           ET2_TS(8 + c);
         }
-        umma_commit_pair(ds_full);
+        umma_commit_pair(d3_full);
         if (a.dbg && blockIdx.x == 0 && it < 8) {
           a.dbg[it * 48 + 40] = wl;
           a.dbg[it * 48 + 41] = wp;
+          a.dbg[it * 48 + 13] = ti;
+          a.dbg[it * 48 + 12] = tcm;
         }
       }
     }
@@ -372,7 +404,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
     const int cg = wg * 64;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t l_ds_empty = mapa_u32(smem_u32(ds_empty), 0), l_buf_full = mapa_u32(smem_u32(buf_full), 0),
-                   l_d2_empty = mapa_u32(smem_u32(d2_empty), 0);
+                   l_d2_empty = mapa_u32(smem_u32(d2_empty), 0), l_d2c0_empty = mapa_u32(smem_u32(d2c0_empty), 0);
     uint32_t ds_f = 0, fr[2] = {0, 0}, d2_f = 0;
     auto warp_arrive = [&](uint32_t leader_bar) {  // one arrival per warp on a leader barrier
       __syncwarp();
@@ -438,9 +470,9 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       if (threadIdx.x == 0) ET2_TS(26);
       for (int c = 0; c < 3; ++c) {
         load_half(D2 + c * 128, v);
-        if (c == 2) {
+        if (c == 0) {
           tc_fence_before();
-          warp_arrive(l_d2_empty);
+          warp_arrive(l_d2c0_empty);
         }
 #pragma unroll
         for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + b2_s[c * 128 + cg + n], 0.f);
@@ -451,11 +483,10 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         if (threadIdx.x == 0) ET2_TS(27 + c);
       }
       // ---- E3: LayerNorm + mask -> fp16 tile image staged in BUF[1] -> bulk store (see et_fused.cuh)
-      mbar_wait(ds_full, ds_f & 1);
-      ++ds_f;
+      mbar_wait(d3_full, it & 1);
       tc_fence_after();
       if (threadIdx.x == 0) ET2_TS(30);
-      load_half(DS, v);
+      load_half(D2, v);
       float s0 = 0.f;
 #pragma unroll
       for (int n = 0; n < 64; ++n) {
@@ -475,7 +506,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         float w[32];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          tmem_ld32(DS + lane_base + og + 32 * h, w);
+          tmem_ld32(D2 + lane_base + og + 32 * h, w);
           tmem_ld_wait();
 #pragma unroll
           for (int n = 0; n < 32; ++n) {
@@ -486,7 +517,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         }
       }
       tc_fence_before();
-      warp_arrive(l_ds_empty);
+      warp_arrive(l_d2_empty);  // all of D2 (E2 drained [128,384) earlier) may be overwritten by the next tile's G2(0)
       const float dm = sd * (1.f / 128.f);
       const float mean = shift + dm;
       const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - dm * dm, 0.f) + 1e-5f);

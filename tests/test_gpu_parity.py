@@ -316,3 +316,22 @@ def test_tiny_and_oversized_inputs(model):
     feats["t"] = torch.ones(1)
     with pytest.raises(runtime.FdptError):
         m({k: v.to("cuda") for k, v in feats.items()})
+
+
+def test_edge_transition_cta_pair_variant_is_bit_identical(ctx):
+    """The experimental cta_group::2 EdgeTransition kernel (et_fused2.cuh, FDPT_OPT_ET_PAIR) runs the same MMAs in the same order on
+    CTA pairs: its output must equal the default kernel's bit for bit, including odd tile counts (the peer CTA repeats the last tile)
+    and pairs that straddle a (sample, j-block) boundary."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    try:
+        for (B, N) in [(1, 37), (1, 131), (2, 129), (3, 200)]:
+            node = torch.randn(B, N, 256, device="cuda", generator=g)
+            z = torch.randn(B, N, N, 128, device="cuda", generator=g)
+            mask = (torch.rand(B, N, device="cuda", generator=g) > 0.1).float()
+            ctx.set_option(5, 0)
+            ref = ctx.edge_transition(0, node, z, mask)
+            ctx.set_option(5, 1)
+            out = ctx.edge_transition(0, node, z, mask)
+            assert torch.equal(ref, out), (B, N, (ref - out).abs().max().item())
+    finally:
+        ctx.set_option(5, 0)

@@ -7,7 +7,8 @@ from framedipt_b200.params import synthetic_state_dict
 ctx = runtime.Context()
 ctx.load_state_dict(synthetic_state_dict(0))
 OPT_ET_PAIR = 5
-ctx.set_option(2, 1)  # host-mapped timeline + barrier-timeout records
+if not os.environ.get("NO_TIMELINE"):
+    ctx.set_option(2, 1)  # host-mapped timeline + barrier-timeout records
 BAR_NAMES = ["w_full"] * 7 + ["w_peer"] * 7 + ["w_empty"] * 7 + ["az_full"] * 2 + ["az_peer"] * 2 + ["az_empty"] * 2 + ["an_full", "an_peer", "ds_full", "ds_empty"] + \
     ["buf_full"] * 2 + ["buf_free"] * 2 + ["d2_full", "d2_empty"] + ["vec_full"] * 2 + ["vec_free"] * 2 + ["stg_full"]
 
