@@ -80,3 +80,56 @@ def inference_fn(model: ScoreNetwork, diffuser, data_init: dict, num_t: int, min
         ret["psi_pred"] = out["psi_pred"].cpu().numpy()[None]
         ret["rigid_0_traj"] = _expand37(out["rigid_0_traj"].cpu().numpy())
     return ret
+
+
+# ---- EigenFold confidence score (experiments/utils.py:251-289, 752-869) -------------------------------------------------------
+def one_step_inference_score(model: ScoreNetwork, diffuser, sample_feats: dict, t: float, t_placeholder: torch.Tensor,
+                             self_condition: bool = True):
+    """Translation and rotation scores of one network evaluation at time t (with the self-conditioning pre-pass)."""
+    sample_feats["t"] = t * t_placeholder
+    rot_scaling, trans_scaling = diffuser.score_scaling(t)
+    sample_feats["rot_score_scaling"] = rot_scaling * t_placeholder
+    sample_feats["trans_score_scaling"] = trans_scaling * t_placeholder
+    if self_condition:
+        sample_feats["sc_ca_t"] = model(sample_feats)["rigids"][..., 4:]
+    out = model(sample_feats)
+    return out["trans_score"], out["rot_score"]
+
+
+def logp_confidence_score(model: ScoreNetwork, diffuser, rigids_t, sample_feats: dict, diffuse_mask: np.ndarray, num_t: int,
+                          min_t: float, device, self_condition: bool):
+    """log p(sample) estimated along one forward-noising path: sum over steps of log p(x(t-1)|x(t)) - log q(x(t)|x(t-1)), plus the
+    prior log-density at t=1.  Same signature, RNG consumption (legacy global numpy stream: translation then rotation noise per
+    step) and in-place updates of `sample_feats` as the reference; the two network evaluations per step run on the GPU through
+    `ScoreNetwork`, the [N, 3]-sized transition densities are host numpy exactly as in the reference.
+    Returns (log_prob, running log_prob after every step)."""
+    from .se3_diffuser import _rotvec_of, gaussian_log_prob
+
+    if not isinstance(model, ScoreNetwork):
+        raise TypeError("framedipt_b200.logp_confidence_score drives framedipt_b200.ScoreNetwork (there is no eager fallback)")
+    diffuse_mask = np.asarray(diffuse_mask)
+    forward_steps = np.linspace(min_t, 1.0, num_t)[:-1]
+    t_placeholder = torch.ones((1,)).to(device)
+    dt = 1 / num_t
+    log_probs, log_prob = [], 0.0
+    for i, t_1 in enumerate(forward_steps):
+        prev = rigids_t
+        rigids_t = diffuser.forward(rigids_t_1=prev, t_1=t_1, diffuse_mask=diffuse_mask, dt=dt)
+        sample_feats["rigids_t"] = rigids_t.to_tensor_7().to(device)
+        if sample_feats["rigids_t"].ndim == 2 and sample_feats["res_mask"].ndim == 2:
+            sample_feats["rigids_t"] = sample_feats["rigids_t"][None]
+        t = 1.0 if i == len(forward_steps) - 1 else forward_steps[i + 1]
+        trans_score, rot_score = one_step_inference_score(model, diffuser, sample_feats, t, t_placeholder, self_condition)
+        trans_score = trans_score.squeeze().cpu().numpy()
+        rot_score = rot_score.squeeze().cpu().numpy()
+        log_prob += diffuser.log_prob_backward(rigids_t=rigids_t, rigids_t_1=prev, trans_score_t=trans_score, rot_score_t=rot_score,
+                                               dt=dt, t=t, diffuse_mask=diffuse_mask)
+        log_prob -= diffuser.log_prob_forward(rigids_t=rigids_t, rigids_t_1=prev, dt=dt, t_1=t_1, diffuse_mask=diffuse_mask)
+        log_probs.append(log_prob)
+    # prior at t = 1: standard normal on the scaled translations, uniform rotations
+    trans, _ = _rotvec_of(rigids_t)
+    trans = diffuser._r3_diffuser._scale(trans)
+    log_prob += gaussian_log_prob(np.zeros_like(trans), np.ones_like(trans), trans, diffuse_mask)
+    log_prob += np.log(1 / np.pi ** 2) * diffuse_mask.sum().item()
+    log_probs.append(log_prob)
+    return log_prob, log_probs

@@ -17,7 +17,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .rigid import Rigid, Rotation
+from .rigid import Rigid, Rotation, rotmats_to_rigid
 
 
 def _get(conf, name, default=None):
@@ -99,6 +99,84 @@ class SO3Schedule:
         return x * ang[:, None]
 
 
+    # ---- one-step forward noising and the two transition log-densities (EigenFold confidence score, so3_diffuser.py:408-567)
+    def forward(self, x_t_1, t_1: float, dt: float, diffuse_mask=None, chain_indices=None, noise_scale: float = 1.0):
+        z = noise_scale * np.random.normal(size=x_t_1.shape)
+        step = self.diffusion_coef(t_1) * np.sqrt(dt) * z
+        if diffuse_mask is not None:
+            step = step * diffuse_mask[..., None]
+        return _compose_rotvec(x_t_1.reshape(-1, 3), step.reshape(-1, 3)).reshape(x_t_1.shape)
+
+    def distribution(self, rot_t, score_t, t: float, dt: float, diffuse_mask=None, chain_indices=None):
+        g = self.diffusion_coef(t)
+        drift = (g ** 2) * score_t * dt
+        if diffuse_mask is not None:
+            drift = drift * diffuse_mask[..., None]
+        mu = _compose_rotvec(rot_t.reshape(-1, 3), drift.reshape(-1, 3)).reshape(rot_t.shape)
+        return mu, g * np.sqrt(dt)
+
+    def log_prob_forward(self, rot_t, rot_t_1, t_1: float, dt: float, diffuse_mask=None, chain_indices=None) -> float:
+        std = self.diffusion_coef(t_1) * np.sqrt(dt)
+        return gaussian_log_prob(rot_t_1, std, align_rotation_vectors(rot_t, rot_t_1), diffuse_mask)
+
+    def log_prob_backward(self, rot_t, rot_t_1, score_t, t: float, dt: float, diffuse_mask=None, chain_indices=None) -> float:
+        mu, std = self.distribution(rot_t, score_t, t, dt, diffuse_mask)
+        return gaussian_log_prob(mu, std, align_rotation_vectors(rot_t_1, mu), diffuse_mask)
+
+
+def _rotvec_of(rigid: Rigid):
+    """(trans [.., 3] fp32, rotation vectors [.., 3] fp64) of a Rigid, the representation every diffuser step works in
+    (se3_diffuser.py:16-23: fp32 rotation matrices -> scipy rotvec)."""
+    from scipy.spatial.transform import Rotation as SR
+
+    R = rigid.get_rots().get_rot_mats().cpu().numpy()
+    rv = SR.from_matrix(R.reshape(-1, 3, 3)).as_rotvec().reshape(R.shape[:-2] + (3,))
+    return rigid.get_trans().cpu().numpy(), rv
+
+
+def _rigid_of(rotvec: np.ndarray, trans: np.ndarray) -> Rigid:
+    """Inverse of _rotvec_of; rotation matrices and translations are stored in fp32 (se3_diffuser.py:26-36)."""
+    from scipy.spatial.transform import Rotation as SR
+
+    mats = SR.from_rotvec(rotvec.reshape(-1, 3)).as_matrix().reshape(rotvec.shape[:-1] + (3, 3))
+    return rotmats_to_rigid(mats, trans)
+
+
+def _compose_rotvec(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """rotvec(R(a) R(b)) (right multiplication, data/transforms.py:33-38)."""
+    from scipy.spatial.transform import Rotation as SR
+
+    Ra, Rb = SR.from_rotvec(a.reshape(-1, 3)).as_matrix(), SR.from_rotvec(b.reshape(-1, 3)).as_matrix()
+    return SR.from_matrix(np.einsum("nij,njk->nik", Ra, Rb)).as_rotvec().reshape(a.shape)
+
+
+def align_rotation_vectors(inputs: np.ndarray, targets: np.ndarray) -> np.ndarray:
+    """The representative of `inputs` (angle theta or 2 pi - theta about the flipped axis) whose axis points into the half space
+    of `targets` (so3_diffuser.py:99-119)."""
+    ang = np.linalg.norm(inputs, axis=-1, keepdims=True)
+    axis = inputs / ang
+    t_axis = targets / np.linalg.norm(targets, axis=-1, keepdims=True)
+    sgn = np.sign(np.einsum("...i,...i->...", t_axis, axis))[..., None]
+    return (axis * sgn) * np.where(sgn > 0, ang, 2 * np.pi - ang)
+
+
+def gaussian_log_prob(mu, std, x, diffuse_mask=None) -> float:
+    """Sum over the masked residues of log N(x; mu, std^2) (r3_utils.py:10-42).  Evaluated with torch tensors so that the arithmetic
+    type follows the reference's: fp32 when both x and mu are fp32 positions (translation forward kernel; the scalar std adopts the
+    tensor dtype as in torch.distributions.Normal), fp64 as soon as a score or rotation vector is involved; the masked values are
+    summed by numpy (pairwise) in that dtype."""
+    import math
+
+    mu_t = torch.from_numpy(mu) if isinstance(mu, np.ndarray) else torch.as_tensor(mu)
+    x_t = torch.from_numpy(x) if isinstance(x, np.ndarray) else torch.as_tensor(x)
+    scale = torch.from_numpy(std) if isinstance(std, np.ndarray) else torch.as_tensor(float(std), dtype=mu_t.dtype)
+    lp = -((x_t - mu_t) ** 2) / (2 * scale ** 2) - scale.log() - math.log(math.sqrt(2 * math.pi))
+    if diffuse_mask is not None:
+        sel = torch.as_tensor(np.asarray(diffuse_mask)).bool()[..., None]
+        lp = torch.masked_select(lp, sel)
+    return lp.cpu().numpy().sum()
+
+
 class R3Schedule:
     """VP-SDE schedule on translations (r3_diffuser.py:12-96, 387-408)."""
 
@@ -108,10 +186,63 @@ class R3Schedule:
         self.coordinate_scaling = float(_get(r3_conf, "coordinate_scaling", 0.1))
 
     def b_t(self, t):
-        t = np.asarray(t)
-        if np.any(t < 0) or np.any(t > 1):
+        if np.any(np.asarray(t) < 0) or np.any(np.asarray(t) > 1):
             raise ValueError(f"Invalid t={t}")
-        return self.min_b + t * (self.max_b - self.min_b)
+        return self.min_b + t * (self.max_b - self.min_b)  # keeps t's type (python float stays "weak" in numpy promotion)
+
+    def diffusion_coef(self, t):
+        return np.sqrt(self.b_t(t))
+
+    def drift_coef(self, x, t):
+        return -1 / 2 * self.b_t(t) * x
+
+    def _scale(self, x):
+        return x * self.coordinate_scaling
+
+    def _unscale(self, x):
+        return x / self.coordinate_scaling
+
+    # ---- one-step forward noising and the two transition log-densities (EigenFold confidence score, r3_diffuser.py:122-260);
+    #      expressions keep the reference's operand order so that numpy's type promotion (fp32 positions, fp64 noise) is the same
+    def forward(self, x_t_1, t_1: float, dt: float, diffuse_mask=None, chain_indices=None, center: bool = True,
+                noise_scale: float = 1.0):
+        x_t_1 = self._scale(x_t_1)
+        g_t = self.diffusion_coef(t_1)
+        f_t = self.drift_coef(x_t_1, t_1)
+        z = noise_scale * np.random.normal(size=x_t_1.shape)
+        step = f_t * dt + g_t * np.sqrt(dt) * z
+        if diffuse_mask is not None:
+            step *= diffuse_mask[..., None]
+        else:
+            diffuse_mask = np.ones(x_t_1.shape[:-1])
+        x_t = x_t_1 + step
+        if center:
+            com = np.sum(x_t, axis=-2) / np.sum(diffuse_mask, axis=-1)[..., None]
+            x_t -= com[..., None, :]
+        return self._unscale(x_t)
+
+    def distribution(self, x_t, score_t, t: float, dt: float, diffuse_mask=None, chain_indices=None):
+        x_t = self._scale(x_t)
+        g_t = self.diffusion_coef(t)
+        f_t = self.drift_coef(x_t, t)
+        mu = x_t - (f_t - g_t ** 2 * score_t) * dt
+        if diffuse_mask is not None:
+            mu *= diffuse_mask[..., None]
+        return mu, g_t * np.sqrt(dt)
+
+    def log_prob_forward(self, x_t, x_t_1, t_1: float, dt: float, diffuse_mask, chain_indices=None) -> float:
+        x_t_1 = self._scale(x_t_1)
+        std = self.diffusion_coef(t_1) * np.sqrt(dt)
+        mu = x_t_1 + self.drift_coef(x_t_1, t_1) * dt
+        if diffuse_mask is not None:
+            mu *= diffuse_mask[..., None]
+        return gaussian_log_prob(mu, std, self._scale(x_t), diffuse_mask)
+
+    def log_prob_backward(self, x_t, x_t_1, score_t, t: float, dt: float, diffuse_mask, chain_indices=None) -> float:
+        if diffuse_mask is not None:
+            diffuse_mask = diffuse_mask.astype(bool)
+        mu, std = self.distribution(x_t, score_t, t, dt, diffuse_mask)
+        return gaussian_log_prob(mu, std, self._scale(x_t_1), diffuse_mask)
 
     def marginal_b_t(self, t):
         return t * self.min_b + 0.5 * (t ** 2) * (self.max_b - self.min_b)
@@ -197,6 +328,34 @@ class SE3Diffuser:
         if as_tensor_7:
             rigids_t = rigids_t.to_tensor_7()
         return {"rigids_t": rigids_t}
+
+    # ---- EigenFold confidence score pieces (se3_diffuser.py:50-196): host numpy on [N, 3] arrays, as in the reference --------
+    def forward(self, rigids_t_1: Rigid, t_1: float, dt: float, diffuse_mask=None, chain_indices=None) -> Rigid:
+        """One forward-noising step x(t-1) -> x(t); draws the translation noise first, then the rotation noise, from the legacy
+        global numpy RNG like the reference."""
+        trans_0, rot_0 = _rotvec_of(rigids_t_1)
+        trans_1 = self._r3_diffuser.forward(trans_0, t_1, dt, diffuse_mask, chain_indices, center=False)
+        rot_1 = self._so3_diffuser.forward(rot_0, t_1, dt, diffuse_mask, chain_indices)
+        if diffuse_mask is not None:
+            dm = diffuse_mask[..., None]
+            rot_1 = dm * rot_1 + (1 - dm) * rot_0
+            trans_1 = dm * trans_1 + (1 - dm) * trans_0
+        return _rigid_of(rot_1, trans_1)
+
+    def log_prob_forward(self, rigids_t: Rigid, rigids_t_1: Rigid, t_1: float, dt: float, diffuse_mask=None, chain_indices=None) -> float:
+        """log q(x(t) | x(t-1)) summed over the diffused residues."""
+        trans_t, rot_t = _rotvec_of(rigids_t)
+        trans_p, rot_p = _rotvec_of(rigids_t_1)
+        return (self._r3_diffuser.log_prob_forward(trans_t, trans_p, t_1, dt, diffuse_mask)
+                + self._so3_diffuser.log_prob_forward(rot_t, rot_p, t_1, dt, diffuse_mask))
+
+    def log_prob_backward(self, rigids_t: Rigid, rigids_t_1: Rigid, trans_score_t, rot_score_t, t: float, dt: float, diffuse_mask,
+                          chain_indices=None) -> float:
+        """log p(x(t-1) | x(t)) of the learned reverse kernel, summed over the diffused residues."""
+        trans_t, rot_t = _rotvec_of(rigids_t)
+        trans_p, rot_p = _rotvec_of(rigids_t_1)
+        return (self._r3_diffuser.log_prob_backward(trans_t, trans_p, trans_score_t, t, dt, diffuse_mask)
+                + self._so3_diffuser.log_prob_backward(rot_t, rot_p, rot_score_t, t, dt, diffuse_mask))
 
     # ---- device-executed pieces (bound lazily to avoid importing the CUDA library for host-only use) ----
     def reverse(self, rigid_t: Rigid, rot_score, trans_score, t: float, dt: float, diffuse_mask=None,
