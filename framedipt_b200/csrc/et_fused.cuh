@@ -47,7 +47,6 @@ struct EtArgs {
   const __half* W3cat;          // image [10 kb][128][128 B]
   long long tiles;              // B*N*JB
   long long* dbg;               // optional clock64 timeline of CTA 0 (bring-up / profiling aid): [tile][48] stamps, or nullptr
-  int flags = 0;                // profiling experiments: 1 = the MMA issuer does not wait for weight stages (results are garbage)
 };
 
 #define ET_TS(id)                                                                                  \

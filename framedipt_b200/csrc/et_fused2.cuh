@@ -88,7 +88,7 @@ FDPT_DEVINL void umma_commit_pair(uint64_t* bar) {
     if (a.dbg && blockIdx.x == 0 && it < 8) a.dbg[it * 48 + (id)] = clock64();          \
   } while (0)
 
-__global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
+__global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a, int flags) {  // flags: profiling experiments (1: no weight waits, 2: no MMAs, 4: every MMA twice)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* A0z = smem;                                 // 2 x 32 KB
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       auto load_z = [&](long long p) {
         const uint32_t n = (uint32_t)(p - p_begin);
         const int s = (int)(n & 1);
-        mbar_wait(&az_empty[s], ((n >> 1) & 1) ^ 1);
+        mbar_wait_diag(&az_empty[s], ((n >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&az_full[s], ET_TILE_BYTES);
         int jb;
         const long long m = tile_m(tile_of(p, rank), jb);
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       };
       auto stage = [&](const __half* img, int rows_total, int row0, int kb) {
         const int s = wit % ET2_WSTAGES;
-        mbar_wait(&w_empty[s], ((wit / ET2_WSTAGES) & 1) ^ 1);
+        mbar_wait_diag(&w_empty[s], ((wit / ET2_WSTAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&w_full[s], ET2_HALF_BYTES);
         bulk_g2s(WST + s * ET2_HALF_BYTES, reinterpret_cast<const uint8_t*>(img) + ((size_t)kb * rows_total + row0 + 64 * rank) * 128,
                  ET2_HALF_BYTES, &w_full[s]);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         if (p + 1 < p_end && n_changes(p + 1, rank)) {
           // the n_j image changes: wait until this pair's last reader (G3 static) has completed
           const uint32_t n = (uint32_t)(p - p_begin);
-          mbar_wait(&az_empty[n & 1], (n >> 1) & 1);
+          mbar_wait_diag(&az_empty[n & 1], (n >> 1) & 1);
           load_n(p + 1);
         }
       }
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
     // ============================ epilogue-vector prefetcher ============================
     for (long long p = p_begin; p < p_end; ++p) {
       const uint32_t n = (uint32_t)(p - p_begin), buf = n & 1;
-      mbar_wait(&vec_free[buf], ((n >> 1) & 1) ^ 1);
+      mbar_wait_diag(&vec_free[buf], ((n >> 1) & 1) ^ 1);
       int jb;
       const long long m = tile_m(tile_of(p, rank), jb);
       for (int k = lane; k < 384; k += 32) Ui_s[buf * 384 + k] = a.Ui[m * 384 + k];
@@ -257,16 +257,16 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       const uint32_t r_w = mapa_u32(smem_u32(w_peer), 0), r_az = mapa_u32(smem_u32(az_peer), 0), r_an = mapa_u32(smem_u32(an_peer), 0);
       for (long long p = p_begin; p < p_end; ++p) {
         const uint32_t n = (uint32_t)(p - p_begin);
-        mbar_wait(&az_full[n & 1], (n >> 1) & 1);
+        mbar_wait_diag(&az_full[n & 1], (n >> 1) & 1);
         mbar_arrive_cluster(r_az + (n & 1) * 8);
         if (n_changes(p, 1)) {
-          mbar_wait(an_full, an_f & 1);
+          mbar_wait_diag(an_full, an_f & 1);
           ++an_f;
           mbar_arrive_cluster(r_an);
         }
         for (int k = 0; k < 40; ++k) {  // 40 weight stages per tile (3 x 4 + 3 x 6 + 4 + 6)
           const int s = wit % ET2_WSTAGES;
-          mbar_wait(&w_full[s], (wit / ET2_WSTAGES) & 1);
+          mbar_wait_diag(&w_full[s], (wit / ET2_WSTAGES) & 1);
           mbar_arrive_cluster(r_w + s * 8);
           ++wit;
         }
@@ -283,9 +283,9 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       auto gemm_kb = [&](uint32_t a_addr, uint32_t d_col, bool first_acc) {
         const int s = wit % ET2_WSTAGES;
         const uint32_t ph = (wit / ET2_WSTAGES) & 1;
-        if (!(a.flags & 1)) {
+        if (!(flags & 1)) {
           const long long c0 = prof ? clock64() : 0;
-          mbar_wait(&w_full[s], ph);
+          mbar_wait_diag(&w_full[s], ph);
           const long long c1 = prof ? clock64() : 0;
           mbar_wait_cluster(&w_peer[s], ph);
           const long long c2 = prof ? clock64() : 0;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         tc_fence_after();
         const uint32_t b_addr = smem_u32(WST + s * ET2_HALF_BYTES);
         const long long i0 = prof ? clock64() : 0;
-        const int reps = (a.flags & 2) ? 0 : (a.flags & 4) ? 2 : 1;  // profiling experiments: no MMAs / every MMA twice
+        const int reps = (flags & 2) ? 0 : (flags & 4) ? 2 : 1;  // profiling experiments: no MMAs / every MMA twice
         for (int r = 0; r < reps; ++r) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -315,10 +315,10 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         const uint32_t it = (uint32_t)(p - p_begin);
         const int zs = (int)(it & 1);
         const uint32_t zuse = it >> 1;
-        mbar_wait(&az_full[zs], zuse & 1);
+        mbar_wait_diag(&az_full[zs], zuse & 1);
         mbar_wait_cluster(&az_peer[zs], zuse & 1);
         if (n_changes(p, 0)) {
-          mbar_wait(an_full, an_f & 1);
+          mbar_wait_diag(an_full, an_f & 1);
           ++an_f;
         }
         if (n_changes(p, 1)) {
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       if (lane == 0) mbar_arrive_cluster(leader_bar);
     };
     auto wait_free = [&](int b) {
-      mbar_wait(&buf_free[b], (fr[b] & 1) ^ 1);
+      mbar_wait_diag(&buf_free[b], (fr[b] & 1) ^ 1);
       ++fr[b];
     };
     auto store_half = [&](uint8_t* buf, const float* v /*[64]*/) {
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       const float* Pf_t = Pf_s + vbuf * 128;
       float mk = 0.f;
       if (j < a.N) mk = a.mask[m] * a.mask[(long long)bsamp * a.N + j];
-      mbar_wait(&vec_full[vbuf], (it >> 1) & 1);
+      mbar_wait_diag(&vec_full[vbuf], (it >> 1) & 1);
       float v[64];
       if (threadIdx.x == 0) ET2_TS(16);
       // ---- E1: three chunks of h1
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive(&buf_free[1]);
         }
-        mbar_wait(ds_full, ds_f & 1);
+        mbar_wait_diag(ds_full, ds_f & 1);
         ++ds_f;
         tc_fence_after();
         if (threadIdx.x == 0) ET2_TS(17 + 3 * c);
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         if (threadIdx.x == 0) ET2_TS(19 + 3 * c);
       }
       // ---- E2: three chunks of r2
-      mbar_wait(d2_full, d2_f & 1);
+      mbar_wait_diag(d2_full, d2_f & 1);
       ++d2_f;
       tc_fence_after();
       if (threadIdx.x == 0) ET2_TS(26);
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
         if (threadIdx.x == 0) ET2_TS(27 + c);
       }
       // ---- E3: LayerNorm + mask -> fp16 tile image staged in BUF[1] -> bulk store (see et_fused.cuh)
-      mbar_wait(d3_full, it & 1);
+      mbar_wait_diag(d3_full, it & 1);
       tc_fence_after();
       if (threadIdx.x == 0) ET2_TS(30);
       load_half(D2, v);
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused2_kernel(EtArgs a) {
       fence_proxy_async();
       mbar_arrive(stg_full);
       if (threadIdx.x == 0) {
-        mbar_wait(stg_full, it & 1);
+        mbar_wait_diag(stg_full, it & 1);
         if (valid) {
           uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * (long long)ET_TILE_BYTES);
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(BUF + ET_TILE_BYTES)),

@@ -457,7 +457,8 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
 
 // ---- IPA (kernels_ipa.cuh) ------------------------------------------------------------------------------------
 int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* z, const float* quats, const float* trans,
-            const float* mask, float* out, int ldo, const float* residual, const float* outmask, cudaStream_t st) {
+            const float* mask, float* out, int ldo, const float* residual, const float* outmask, cudaStream_t st,
+            const float* ln_g = nullptr, const float* ln_b = nullptr, float* ln_out = nullptr) {
   ProfScope ps(ctx, FDPT_PROF_IPA_TOTAL, st);
   Workspace& w = ctx->ws;
   const BlockParams& p = ctx->blk[blk];
@@ -499,8 +500,21 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
   }
   ipa_opt_kernel<<<(unsigned)M, NH * PV, 0, st>>>((int)M, w.cat, quats, trans);
   LAUNCH_CHECK();
+  if (ln_out && ctx->gemm_tc && !(ctx->dbg_flags & 256) && (CAT / 64) % 2 == 0) {
+    // linear_out as a 2-way split-K GEMM (K = 2432 is one long serial k-loop per CTA otherwise: 88 CTAs x 38 k-blocks); the two
+    // partial products are summed, biased, masked and added to the residual inside the LayerNorm kernel that follows
+    GemmArgs g;
+    g.A = w.cat; g.lda = CAT; g.sA1 = CAT / 2; g.B = p.Wout_perm; g.ldb = CAT; g.sB1 = CAT / 2;
+    g.C = w.tmpB; g.ldc = C_S; g.sC1 = w.tmpC - w.tmpB; g.M = (int)M; g.N = C_S; g.K = CAT / 2;
+    CK(gemm_dispatch(ctx, g, true, 2, st));
+    ctx->launches++;
+    sum2_layernorm_kernel<C_S><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(w.tmpB, w.tmpC, p.bout, residual, outmask, ln_out, ln_g, ln_b, M);
+    LAUNCH_CHECK();
+    return FDPT_OK;
+  }
   // linear_out (+ mask, + residual)
   RET(lin(w.cat, CAT, p.Wout_perm, CAT, p.bout, out, ldo, M, C_S, CAT, 0, residual, C_S, outmask));
+  if (ln_out) RET(layernorm<C_S>(ctx, st, out, ln_out, ln_g, ln_b, M, nullptr));
   return FDPT_OK;
 }
 
@@ -526,7 +540,6 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   a.ln_g = p.eln_g; a.ln_b = p.eln_b; a.mask = mask; a.W1cat = p.imgW1cat; a.W2 = p.imgW2; a.W3cat = p.imgW3cat;
   a.tiles = M * w.JB;
   a.dbg = (ctx->dbg_flags & 4) ? nullptr : ctx->et_dbg;
-  a.flags = (ctx->dbg_flags >> 5) & 7;  // debug flag bits 32 / 64 / 128 -> EtArgs.flags 1 / 2 / 4
   if (ctx->et_pair && a.tiles >= 2) {
     const long long pairs = (a.tiles + 1) / 2;
     cudaLaunchConfig_t cfg{};
@@ -538,7 +551,8 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, tc::et_fused2_kernel, a));
+    const int et_flags = (ctx->dbg_flags >> 5) & 7;  // debug flag bits 32 / 64 / 128: profiling experiments of the pair kernel
+    CK(cudaLaunchKernelEx(&cfg, tc::et_fused2_kernel, a, et_flags));
   } else {
     const int grid = (int)std::min<long long>(ctx->num_sms, a.tiles);
     tc::et_fused_kernel<<<grid, tc::ET_THREADS, tc::et_smem_bytes(), st>>>(a);
@@ -613,8 +627,7 @@ int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_o
   for (int b = 0; b < NBLK; ++b) {
     const BlockParams& p = ctx->blk[b];
     // node = LN(node + ipa(node) * mask)
-    RET(run_ipa(ctx, b, B, N, w.node, w.z, w.quats, w.trans, in->res_mask, w.tmpC, C_S, w.node, in->res_mask, st));
-    RET(layernorm<C_S>(ctx, st, w.tmpC, w.node, p.ln_g, p.ln_b, M, nullptr));
+    RET(run_ipa(ctx, b, B, N, w.node, w.z, w.quats, w.trans, in->res_mask, w.tmpC, C_S, w.node, in->res_mask, st, p.ln_g, p.ln_b, w.node));
     RET(run_seq_tfmr(ctx, b, B, N, in->res_mask, st));
     // node transition
     RET(lin(w.node, C_S, p.Wt1, C_S, p.bt1, w.tmpA, C_S, M, C_S, C_S, 1));

@@ -11,6 +11,43 @@ namespace fdpt {
 //   y = LN(x) * gamma + beta ; optionally y *= rowmask[row] (node mask) or pair mask m[b,i]*m[b,j].
 // x and y may alias.
 // ------------------------------------------------------------------------------------------------
+// y = LN(residual + inmask * (p0 + p1 + bias)): the reduce step of a 2-way split-K GEMM fused into the LayerNorm that follows it
+// (IPA linear_out, K = 2432: two K halves run as two batches of the GEMM kernel and halve its per-CTA latency).
+template <int C>
+__global__ void __launch_bounds__(256) sum2_layernorm_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                             const float* __restrict__ bias, const float* __restrict__ residual,
+                                                             const float* __restrict__ inmask, float* __restrict__ y,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, long long rows) {
+  constexpr int PER = C / 32;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float im = inmask ? inmask[row] : 1.f;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    float x = (p0[row * C + c] + p1[row * C + c] + bias[c]) * im;
+    if (residual) x += residual[row * C + c];
+    v[i] = x;
+    s += x;
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    y[row * C + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, float* y, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, long long rows,

@@ -50,10 +50,10 @@ FDPT_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (reported as a CUDA error) instead of hanging the GPU.  When a host-mapped record buffer
-// is installed (FDPT_OPT_ET_TIMELINE) the first 31 waits that time out leave {block, thread, barrier offset, parity} behind.
+// Bounded wait: a protocol bug must trap (reported as a CUDA error) instead of hanging the GPU.  mbar_wait_diag additionally records
+// {block, thread, barrier offset, parity} of the first 31 waits that time out in a host-mapped buffer (FDPT_OPT_ET_TIMELINE).
 __device__ unsigned long long* g_mbar_fail_buf = nullptr;
-__device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+FDPT_DEVINL void mbar_timeout(uint32_t bar_addr, uint32_t parity) {  // inlined: a call here costs the hot kernels a stack frame
   unsigned long long* fb = g_mbar_fail_buf;
   if (fb) {
     const unsigned long long slot = atomicAdd(fb, 1ull);
@@ -67,6 +67,14 @@ __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
   __trap();
 }
 FDPT_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// same, leaving a record behind before the trap (bring-up of new protocols; costs the caller a few registers)
+FDPT_DEVINL void mbar_wait_diag(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
