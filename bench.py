@@ -54,7 +54,8 @@ class ClockSampler:
     def __init__(self, gpu: int, period_s: float = 0.02):
         import threading
 
-        self.sm, self.reasons, self.sm_max = [], set(), None
+        self.sm, self.mem, self.reasons, self.sm_max = [], [], set(), None
+        self._armed = False
         self._stop = threading.Event()
         self.p = self.f = self.th = None
         try:
@@ -70,8 +71,12 @@ class ClockSampler:
 
             def loop():
                 while not self._stop.is_set():
+                    if os.environ.get("FDPT_BENCH_NO_POLL") and self._armed:
+                        self._stop.wait(period_s)
+                        continue
                     try:
                         self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mem.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_MEM)))
                         r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                         for k, bit in names.items():
                             if r & bit:
@@ -82,6 +87,7 @@ class ClockSampler:
 
             self.th = threading.Thread(target=loop, daemon=True)
             self.th.start()
+            self._nvml_ok = True
         except Exception:
             self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             try:
@@ -90,6 +96,14 @@ class ClockSampler:
             except Exception:
                 self.p = None
 
+    def begin(self):
+        """Forget what was sampled so far: called right before the timed region (the sampler itself is created -- NVML initialised --
+        before the warm-up, so that no idle gap separates warm-up and timed region)."""
+        self.sm.clear()
+        self.mem.clear()
+        self.reasons.clear()
+        self._armed = True
+
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": []}
         if self.th is not None:
@@ -97,6 +111,9 @@ class ClockSampler:
             self.th.join(timeout=2)
             if self.sm:
                 out["sm_mhz"] = float(np.median(self.sm))
+                out["sm_min_mhz"] = float(np.min(self.sm))
+                if self.mem:
+                    out["mem_min_mhz"] = float(np.min(self.mem))
                 out["samples"] = len(self.sm)
             out["reasons"] = sorted(self.reasons)
             out["source"] = "nvml"
@@ -260,15 +277,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- clock spin-up (untimed, not workload steps): a fresh box idles at low clocks and the first tens of
-    # milliseconds of work otherwise run while the GPU is still ramping (seen as occasional 30 % slow first passes) ----------------
-    xs = torch.randn(4, 2048, 512, device=dev)
+    clocks = ClockSampler(local_rank) if rank == 0 else None  # NVML initialisation happens here, before any GPU work is timed
+    # ---------------- clock spin-up (untimed, not counted as warm-up steps): a fresh box idles in a low power state and both the SM
+    # and the HBM clocks ramp over the first hundreds of milliseconds of load; without this the timed pass was occasionally 30-100 %
+    # slow while the later e2e pass never was.  The load is the workload itself (memory- and tensor-heavy), for >= 0.6 s. ------------
+    sc, te = segment(0, W)
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 0.4:
-        for _ in range(20):
-            ctx.matmul(xs, xs, True)
+    while time.perf_counter() - t_spin < 0.6:
+        ctx.sample(pf, sc, te, noise_dev[:W], self_condition=False)
         torch.cuda.synchronize(dev)
-    del xs
 
     # ---------------- warm-up (untimed) ----------------
     sc, te = segment(0, W)
@@ -280,15 +297,24 @@ def main():
     # ---------------- timed region: K steps, inputs resident in HBM ----------------
     sc, te = segment(W, K)
     te = te.to(dev)
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    out_buf = ctx.alloc_traj(B, N, K)  # trajectory buffers allocated before the clock starts (a cold cudaMalloc costs 1 - 60 ms)
     l0 = ctx.launch_count()
     barrier()
+    if clocks:
+        clocks.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cap0, wall0 = ctx.stat(0), time.perf_counter()
     ev0.record()
-    out = ctx.sample(pf, sc, te, noise_dev[W:], self_condition=False)
+    wall_a = time.perf_counter()
+    out = ctx.sample(pf, sc, te, noise_dev[W:], self_condition=False, out=out_buf)
+    wall_b = time.perf_counter()
     ev1.record()
+    wall_enqueue = time.perf_counter() - wall0
     barrier()
     ms = ev0.elapsed_time(ev1)
+    # host-side sanity of the timed region: no graph capture inside it, and the enqueue (Python + C call) is a small part of it
+    diag = {"graph_captures_in_timed_region": ctx.stat(0) - cap0, "enqueue_wall_ms": round(wall_enqueue * 1e3, 3),
+            "sample_host_ms": {k: round(v, 3) for k, v in ctx.last_sample_host_ms.items()}}
     launches = ctx.launch_count() - l0
     clk = clocks.stop() if clocks else None
     t_all = torch.tensor([ms], device=dev)
@@ -358,7 +384,7 @@ def main():
                    "share_of_forward": shares["edge_transition"], "peak_source": peaks["source"] + " (sustained bf16)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "timesteps_per_sec": world * K / (ms_max * 1e-3), "gpu_launches": int(launches), "clocks": clk,
+                "timesteps_per_sec": world * K / (ms_max * 1e-3), "gpu_launches": int(launches), "clocks": clk, "diag": diag,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "roofline": roof_et if dominant == "edge_transition" else roof_ipa,
                 "roofline_ipa": roof_ipa, "roofline_edge_transition": roof_et,

@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -112,6 +113,8 @@ struct fdpt_ctx {
     int64_t launches = 0;
   } step_graph;
   int use_graph = 1;
+  int64_t stat_captures = 0;      // per-timestep graphs captured so far
+  int64_t stat_sample_host_us = 0; // host time the last fdpt_sample call spent enqueueing
   int et_pair = 0;  // 1: EdgeTransition on CTA pairs (et_fused2.cuh, experimental: slower); 0: single-CTA kernel (et_fused.cuh)
   cudaStream_t own_stream = nullptr;   // the legacy default stream cannot be captured: fdpt_sample then runs on this stream,
   cudaEvent_t fence_in = nullptr, fence_out = nullptr;  // fenced against the caller's stream with these events
@@ -971,6 +974,14 @@ int fdpt_profile_read(fdpt_ctx* ctx, int slot, int* count, double* total_ms) {
 
 int64_t fdpt_workspace_bytes(const fdpt_ctx* ctx) { return ctx ? (int64_t)ctx->ws.bytes : 0; }
 int64_t fdpt_launch_count(const fdpt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t fdpt_stat(const fdpt_ctx* ctx, int which) {
+  if (!ctx) return 0;
+  switch (which) {
+    case FDPT_STAT_GRAPH_CAPTURES: return ctx->stat_captures;
+    case FDPT_STAT_SAMPLE_HOST_US: return ctx->stat_sample_host_us;
+    default: return 0;
+  }
+}
 
 int fdpt_forward(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_out* out, void* stream) {
   if (!ctx || !in) return FDPT_ERR_INVALID;
@@ -1032,6 +1043,11 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
   if (!ctx || !feats || !sched || !t_emb_tab || !out || num_t <= 0 || num_t > 4096) return FDPT_ERR_INVALID;
   if (num_t > 1 && !noise) return FDPT_ERR_INVALID;  /* noise rows are indexed by step: every step whose IS_LAST flag is 0 reads row s */
   cudaSetDevice(ctx->device);
+  const auto host_t0 = std::chrono::steady_clock::now();
+  struct HostTimer {
+    fdpt_ctx* c; std::chrono::steady_clock::time_point t0;
+    ~HostTimer() { c->stat_sample_host_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count(); }
+  } host_timer{ctx, host_t0};
   cudaStream_t user_st = (cudaStream_t)stream, st = user_st;
   RET(reserve_ws(ctx, B, N));
   const bool fenced = ctx->use_graph && (user_st == nullptr || user_st == cudaStreamLegacy || user_st == cudaStreamPerThread);
@@ -1173,6 +1189,7 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
       cudaGraphDestroy(g);
       if (ie != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
       sg.key = key;
+      ctx->stat_captures++;
     }
     CK(cudaGraphLaunch(sg.exec, st));
     ctx->launches += sg.launches;

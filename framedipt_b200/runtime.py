@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
         L.fdpt_workspace_bytes.argtypes = [C.c_void_p]
         L.fdpt_launch_count.restype = C.c_int64
         L.fdpt_launch_count.argtypes = [C.c_void_p]
+        L.fdpt_stat.restype = C.c_int64
+        L.fdpt_stat.argtypes = [C.c_void_p, C.c_int]
         L.fdpt_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_Feats), C.POINTER(_Out), C.c_void_p]
         L.fdpt_reverse.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int,
                                                                                     C.c_void_p, C.c_void_p]
@@ -205,6 +207,10 @@ class Context:
     def launch_count(self) -> int:
         return int(lib().fdpt_launch_count(self._h))
 
+    def stat(self, which: int) -> int:
+        """0: per-timestep graphs captured so far; 1: host microseconds spent inside the last fdpt_sample call."""
+        return int(lib().fdpt_stat(self._h, which))
+
     def workspace_bytes(self) -> int:
         return int(lib().fdpt_workspace_bytes(self._h))
 
@@ -263,17 +269,22 @@ class Context:
 
     # ---- sampling loop
     def sample(self, pf: PreparedFeats, sched: np.ndarray, t_emb_tab: torch.Tensor, noise: torch.Tensor | None, self_condition=True,
-               center=True, diffuse_rot=True, diffuse_trans=True, final_only=False) -> dict[str, torch.Tensor]:
+               center=True, diffuse_rot=True, diffuse_trans=True, final_only=False, out: dict | None = None) -> dict[str, torch.Tensor]:
+        """Enqueue the whole reverse-diffusion loop (fdpt_sample).  `out` may hold pre-allocated trajectory buffers from
+        `alloc_traj` (a fresh cudaMalloc inside torch.empty can take tens of milliseconds; callers that time the loop allocate first)."""
+        import time as _time
+
+        _t0 = _time.perf_counter()
         B, N, dev = pf.B, pf.N, self.device
         T = sched.shape[0]
         sched = np.ascontiguousarray(sched, np.float64)
         assert sched.shape == (T, SCHED_COLS)
-        Ts = 1 if final_only else T
-        out = {
-            "prot_traj": torch.empty(Ts, B, N, 5, 3, device=dev), "rigid_traj": torch.empty(Ts if final_only else T + 1, B, N, 7, device=dev),
-            "trans_traj": torch.empty(Ts, B, N, 3, device=dev), "rigid_0_traj": torch.empty(Ts, B, N, 5, 3, device=dev),
-            "psi_pred": torch.empty(B, N, 2, device=dev),
-        }
+        if out is None:
+            out = self.alloc_traj(B, N, T, final_only)
+        else:
+            ref = self.alloc_shapes(B, N, T, final_only)
+            assert all(tuple(out[k].shape) == ref[k] and out[k].is_cuda and out[k].dtype == torch.float32 for k in ref), "out buffers do not match"
+        _t1 = _time.perf_counter()
         tr = _Traj(_ptr(out["prot_traj"]), _ptr(out["rigid_traj"]), _ptr(out["trans_traj"]), _ptr(out["rigid_0_traj"]),
                    _ptr(out["psi_pred"]), int(final_only))
         t_emb_tab = t_emb_tab.to(dev, torch.float32).contiguous()
@@ -282,11 +293,23 @@ class Context:
             assert noise.dtype == torch.float64 and noise.is_cuda and noise.shape[0] >= max(n_rev, T - 1) and \
                 tuple(noise.shape[1:]) == (2, B, N, 3), (noise.shape, noise.dtype)
         fs = pf.struct()
+        _t2 = _time.perf_counter()
         self._ck(lib().fdpt_sample(self._h, B, N, C.byref(fs), T, sched.ctypes.data_as(C.POINTER(C.c_double)), _ptr(t_emb_tab),
                                    _ptr(noise), int(self_condition), int(center), int(diffuse_rot), int(diffuse_trans), C.byref(tr),
                                    self.stream))
+        _t3 = _time.perf_counter()
+        self.last_sample_host_ms = {"alloc": (_t1 - _t0) * 1e3, "prep": (_t2 - _t1) * 1e3, "c_call": (_t3 - _t2) * 1e3}
         out["_keepalive"] = (t_emb_tab, noise, sched)
         return out
+
+    @staticmethod
+    def alloc_shapes(B, N, T, final_only=False) -> dict:
+        Ts = 1 if final_only else T
+        return {"prot_traj": (Ts, B, N, 5, 3), "rigid_traj": (Ts if final_only else T + 1, B, N, 7), "trans_traj": (Ts, B, N, 3),
+                "rigid_0_traj": (Ts, B, N, 5, 3), "psi_pred": (B, N, 2)}
+
+    def alloc_traj(self, B, N, T, final_only=False) -> dict[str, torch.Tensor]:
+        return {k: torch.empty(*shp, device=self.device) for k, shp in self.alloc_shapes(B, N, T, final_only).items()}
 
     # ---- unit entry points
     def linear(self, x, w, b, act=0):

@@ -157,6 +157,10 @@ int64_t fdpt_to_pdb(const float* atom37_bb, const int32_t* aatype, const int32_t
 
 /* number of kernel launches enqueued by this context since creation (bench.py's gpu_launches) */
 int64_t fdpt_launch_count(const fdpt_ctx* ctx);
+/* Diagnostics counters (bench.py reports them next to the timed region). */
+enum { FDPT_STAT_GRAPH_CAPTURES = 0 /* per-timestep CUDA graphs captured so far */,
+       FDPT_STAT_SAMPLE_HOST_US = 1 /* host microseconds the last fdpt_sample call spent before returning */ };
+int64_t fdpt_stat(const fdpt_ctx* ctx, int which);
 
 /* Live per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
  * When enabled, every launch of the listed kernels / kernel groups inside fdpt_forward / fdpt_sample is bracketed
