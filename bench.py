@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-spinup", action="store_true", help="skip the untimed clock spin-up (for ncu launch lists, where every launch is expensive)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2_tcr350")
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the CPU baseline leg (bounded sample)")
@@ -283,7 +284,7 @@ def main():
     # slow while the later e2e pass never was.  The load is the workload itself (memory- and tensor-heavy), for >= 0.6 s. ------------
     sc, te = segment(0, W)
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 0.6:
+    while time.perf_counter() - t_spin < 0.6 and not args.no_spinup:
         ctx.sample(pf, sc, te, noise_dev[:W], self_condition=False)
         torch.cuda.synchronize(dev)
 

@@ -368,10 +368,11 @@ struct Lin {
         a.X = x; a.ldx = lda; a.M = (int)M; a.K = K; a.N = N; a.Wimg = pw.img; a.nkb = pw.nkb; a.n_tiles = pw.n_tiles;
         const int m_tiles = (int)((M + 127) / 128);
         a.tiles_per_cta = std::min(pw.n_tiles, std::max(1, (m_tiles * pw.n_tiles + ctx->num_sms - 1) / ctx->num_sms));
-        a.stg_cols = pw.nkb <= 4 ? 32 : 16;
+        a.stg_cols = (ctx->dbg_flags & 1024) ? 32 : 16;  // 16-column staging patches: measured faster than 32 for every layer shape (profiles/r01_bench_lin_ablation.txt)
         a.units = std::min(8, (int)((ctx->max_smem_optin - tc::lin_tc_fixed_bytes(pw.nkb, a.stg_cols)) / tc::LT_UNIT_BYTES));
         a.bias = bias; a.relu = relu; a.rowmask = rowmask; a.residual = residual; a.ldr = ldr; a.Y = y; a.ldy = ldc;
         a.dbg_flags = ctx->dbg_flags;
+        a.dbg = (ctx->dbg_flags & 512) ? ctx->et_dbg : nullptr;
         a.x_vec = tc::aligned16(x, lda, 0, 0);
         a.y_vec = 0;
         dim3 grid(m_tiles, (pw.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta);

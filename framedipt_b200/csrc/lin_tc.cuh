@@ -36,7 +36,13 @@ struct LinTcArgs {
   float* Y; int ldy;
   int x_vec, y_vec;
   int dbg_flags;               // bring-up: bit 0 skip the epilogue stores, bit 1 skip the MMAs
+  long long* dbg;              // optional clock64 timeline of CTA (0,0): 16 stamps (tools/lin_timeline.py), or nullptr
 };
+
+#define LT_TS(id)                                                                  \
+  do {                                                                             \
+    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[(id)] = clock64();      \
+  } while (0)
 
 __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -57,6 +63,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
   const int nt_begin = blockIdx.y * a.tiles_per_cta;
   const int nt_end = min(a.n_tiles, nt_begin + a.tiles_per_cta);
   const int ntiles = nt_end - nt_begin;
+  if (tid == 0) LT_TS(0);
 
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) {
@@ -76,6 +83,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
+  if (tid == 0) LT_TS(1);
 
   if (warp == 9) {
     // ============================ weight loader (weights are static: no need to wait for the predecessor kernel) ============================
@@ -104,10 +112,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         const uint32_t acc_main = tmem_base + as * 256, acc_x = acc_main + 128;
         for (int kb = 0; kb < a.nkb; ++kb, it += 2) {
           if (t == 0) mbar_wait(&a_full[kb], 0);
+          if (t == 0 && kb == 0) LT_TS(6);
           const int sh = it % a.units, sl = (it + 1) % a.units;
           mbar_wait(&w_full[sh], (it / a.units) & 1);
           mbar_wait(&w_full[sl], ((it + 1) / a.units) & 1);
           tc_fence_after();
+          if (t == 0 && kb == 0) LT_TS(7);
           const uint32_t ah = smem_u32(Aimg + (size_t)kb * LT_STAGE_BYTES), al = ah + 16384;
           const uint32_t bh = smem_u32(Wst + (size_t)sh * LT_UNIT_BYTES), bl = smem_u32(Wst + (size_t)sl * LT_UNIT_BYTES);
 #pragma unroll
@@ -124,11 +134,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
           umma_commit(&w_empty[sl]);
         }
         umma_commit(&acc_full[as]);
+        if (t == 0) LT_TS(8);
       }
     }
   } else {
     // ============================ workers: stage X once, then epilogues ============================
     pdl_wait();  // X (and residual / Y) belong to the predecessor kernel until it has completed
+    if (tid == 0) LT_TS(2);
     {
       ChunkPlan pa;
       const int r0 = tid >> 3, c = tid & 7;
@@ -139,11 +151,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
       pa.row0 = m0 + r0; pa.row_step = 32; pa.row_lim = a.M; pa.col0 = 8 * c; pa.col_lim = a.K; pa.vec = a.x_vec;
       RegTile ta[2];
       load_tile(pa, 0, ta[0]);
+      if (tid == 0) LT_TS(3);
       for (int kb = 0; kb < a.nkb; kb += 2) {
         if (kb + 1 < a.nkb) load_tile(pa, kb + 1, ta[1]);
         store_tile(pa, Aimg + (size_t)kb * LT_STAGE_BYTES, ta[0]);
         fence_proxy_async();
         mbar_arrive(&a_full[kb]);
+        if (tid == 0 && kb == 0) LT_TS(4);
         if (kb + 1 < a.nkb) {
           if (kb + 2 < a.nkb) load_tile(pa, kb + 2, ta[0]);
           store_tile(pa, Aimg + (size_t)(kb + 1) * LT_STAGE_BYTES, ta[1]);
@@ -152,6 +166,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         }
       }
     }
+    if (tid == 0) LT_TS(5);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int c_half = (warp >> 2) * 64;
     const int sw = a.stg_cols, sld = sw + 1;           // staging width / padded row stride
@@ -165,6 +180,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
       const int n0 = (nt_begin + t) * 128;
       mbar_wait(&acc_full[as], (t >> 1) & 1);
       tc_fence_after();
+      if (tid == 0 && t == 0) LT_TS(9);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int cb = c_half + q * 32;
@@ -175,6 +191,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         if (q == 1) {  // both halves of this thread's columns are in registers: the accumulator pair can be overwritten
           tc_fence_before();
           mbar_arrive(&acc_empty[as]);
+          if (tid == 0 && t == 0) LT_TS(10);
         }
         if (n0 + cb >= a.N || (a.dbg_flags & 1)) continue;
 #pragma unroll
@@ -184,10 +201,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         else
           store_transposed<16>(ep, v, stg, lane, mw, n0 + cb);
       }
+      if (tid == 0 && t == ntiles - 1) LT_TS(11);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) LT_TS(12);
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
