@@ -411,7 +411,8 @@ def so3_diffusion_coef(t):
     return np.sqrt(2 * (np.exp(MAX_SIGMA) - np.exp(MIN_SIGMA)) * s / np.exp(s))
 
 
-def reverse_step(rigids_t, rot_score_t, trans_score_t, diffuse_mask, t, dt, z_rot, z_trans, center=True, noise_scale=1.0):
+def reverse_step(rigids_t, rot_score_t, trans_score_t, diffuse_mask, t, dt, z_rot, z_trans, center=True, noise_scale=1.0,
+                 diffuse_rot=True, diffuse_trans=True):
     """SE3Diffuser.reverse with explicit noise (z_rot drawn before z_trans in the reference, §3.4).
     rigids_t: float32 tensor7 numpy [B,N,7]; scores numpy; z_*: N(0,1) numpy [B,N,3].
     Returns (rotmats float32 [B,N,3,3], trans float32 [B,N,3]) as _assemble_rigid stores them."""
@@ -435,6 +436,10 @@ def reverse_step(rigids_t, rot_score_t, trans_score_t, diffuse_mask, t, dt, z_ro
         com = np.sum(x_t_1, axis=-2) / np.sum(diffuse_mask, axis=-1)[..., None]
         x_t_1 = x_t_1 - com[..., None, :]
     trans_t_1 = x_t_1 / COORD_SCALE
+    if not diffuse_rot:  # se3_diffuser.py:373-385: an undiffused component is passed through unchanged
+        rot_t_1 = rot_t
+    if not diffuse_trans:
+        trans_t_1 = trans_t
     dm = diffuse_mask[..., None]
     trans_t_1 = dm * trans_t_1 + (1 - dm) * trans_t
     rot_t_1 = dm * rot_t_1 + (1 - dm) * rot_t
@@ -481,7 +486,7 @@ def compute_backbone(rotmats, trans, psi, aatype):
 # sampling loop  (experiments/utils.py:511-626, 292-412)
 # --------------------------------------------------------------------------------------------
 def inference_loop(sd, feats, num_t, min_t, noise, noise_scale=1.0, center=True, inpainting=True,
-                   input_aatype=True, dtype=torch.float32, teacher=None):
+                   input_aatype=True, dtype=torch.float32, teacher=None, self_condition=True, diffuse_rot=True, diffuse_trans=True):
     """inference_fn with aux_traj=True, self_condition=True, embed_self_conditioning=True.
     noise: float64 [num_t-1, 2, B, N, 3] standard normals in the reference's draw order (rot, then trans).
     Returns dict(prot_traj [T,B,N,37,3], rigid_traj [T+1,B,N,7] (quats from scipy; sign may differ), rigid_0_traj)."""
@@ -495,8 +500,9 @@ def inference_loop(sd, feats, num_t, min_t, noise, noise_scale=1.0, center=True,
     rigid_traj = [feats["rigids_t"].numpy().copy()]
     prot, prot0 = [], []
     with torch.no_grad():
-        feats["t"] = steps[0] * ones
-        feats["sc_ca_t"] = score_network_forward(sd, feats, inpainting, input_aatype, dtype)["rigids"][..., 4:].float()
+        if self_condition:  # experiments/utils.py:571-578: the pre-pass is the only thing `self_condition` switches
+            feats["t"] = steps[0] * ones
+            feats["sc_ca_t"] = score_network_forward(sd, feats, inpainting, input_aatype, dtype)["rigids"][..., 4:].float()
         for si, t in enumerate(steps):
             feats["t"] = t * ones
             out = score_network_forward(sd, feats, inpainting, input_aatype, dtype)
@@ -505,7 +511,7 @@ def inference_loop(sd, feats, num_t, min_t, noise, noise_scale=1.0, center=True,
                 feats["sc_ca_t"] = rig_pred[..., 4:]
                 R1, T1 = reverse_step(feats["rigids_t"].float().numpy(), out["rot_score"].numpy().astype(np.float64),
                                       out["trans_score"].float().numpy(), diffuse_mask, t, dt, noise[si, 0], noise[si, 1],
-                                      center=center, noise_scale=noise_scale)
+                                      center=center, noise_scale=noise_scale, diffuse_rot=diffuse_rot, diffuse_trans=diffuse_trans)
             else:
                 R1 = quat_to_rot(rig_pred[..., :4]).numpy()
                 T1 = rig_pred[..., 4:].numpy()
