@@ -94,3 +94,18 @@ def test_trajectory_small(golden_dir, state_dict):
     r = bb_rmsd(out["prot_traj"][0], np.pad(g["prot_traj"][0], ((0, 0), (0, 0), (0, 32), (0, 0))))
     assert r.max() < 1e-3, r.max()
     assert out["prot_traj"].shape == (10, 2, 24, 37, 3)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_trajectory_option_variants(golden_dir, state_dict, tag):
+    """The oracle's center / noise_scale / self_condition / diffuse_rot / diffuse_trans switches against trajectories of the unmodified
+    reference run with the same switches (oracle/make_golden_variants.py)."""
+    g = _load(golden_dir, "traj_variants.npz")
+    center, ns, sc, drot, dtrans = g[f"{tag}_opts"]
+    feats = _feats(g)
+    out = orc.inference_loop(state_dict, feats, num_t=int(g["num_t"]), min_t=0.01, noise=g[f"{tag}_noise"], noise_scale=float(ns),
+                             center=bool(center), self_condition=bool(sc), diffuse_rot=bool(drot), diffuse_trans=bool(dtrans))
+    r = bb_rmsd(out["prot_traj"][0][:, :, :5], g[f"{tag}_prot_traj"][0])
+    assert r.max() < 1e-3, r.max()
+    r_mid = bb_rmsd(out["prot_traj"][3][:, :, :5], g[f"{tag}_prot_traj"][3])
+    assert r_mid.max() < 1e-3, r_mid.max()
