@@ -71,8 +71,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
   float* g_s = b4_s + 128;
   float* be_s = g_s + 128;
   float* lower_s = be_s + 128;  // [24]
-  float* red_s = lower_s + 24;  // [2][128] LayerNorm partial sums of the two worker groups
-  float* red_q = red_s + 256;   // [2][128]
+  float* PA_s2 = lower_s + 24;  // [128] second PA buffer (tiles alternate between PA_s and PA_s2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long per = (a.tiles + gridDim.x - 1) / gridDim.x;
@@ -240,16 +239,29 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
       mbar_arrive(&a0_full[(t - t_begin) & 1]);
     };
 
-    if (t_begin < t_end) build_a0(t_begin);
+    // Two CTA-wide barriers per tile (none with a global-memory latency behind it): the per-tile vector PA_i is double buffered and
+    // fetched one tile ahead, the LayerNorm statistics need no exchange between the two groups (each thread re-reads the other half
+    // of its row from TMEM), and the wait for the asynchronous store of tile t sits in front of the first write into its staging
+    // buffer in tile t+1.
+    if (t_begin < t_end) {
+      build_a0(t_begin);
+      int jb0, b0;
+      const long long m0 = tile_m(t_begin, jb0, b0);
+      if (threadIdx.x < 128) PA_s[threadIdx.x] = a.PA[m0 * 128 + threadIdx.x];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     for (long long t = t_begin; t < t_end; ++t) {
       const uint32_t ph = (uint32_t)(t - t_begin) & 1;
       int jb, b;
       const long long m = tile_m(t, jb, b);
       const int j = jb * 128 + row;
-      if (t + 1 < t_end) build_a0(t + 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers of PA_s are done
-      if (threadIdx.x < 128) PA_s[threadIdx.x] = a.PA[m * 128 + threadIdx.x];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* PA_t = ph ? PA_s2 : PA_s;
+      float pa_next = 0.f;
+      if (t + 1 < t_end && threadIdx.x < 128) {
+        int jbn, bn;
+        const long long mn = tile_m(t + 1, jbn, bn);
+        pa_next = a.PA[mn * 128 + threadIdx.x];  // consumed at the end of this iteration
+      }
       float v[64];
       // ---- E0
       mbar_wait(d0_full, ph);
@@ -257,10 +269,15 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
       load_half(D0, v);
       tc_fence_before();
 #pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + PA_s[cg + n], 0.f);
+      for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + PA_t[cg + n], 0.f);
+      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tile t-1's store has left A1
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       store_half(A1, v);
       fence_proxy_async();
       mbar_arrive(a1_full);
+      // the next tile's feature block is gathered here: its two dependent global loads (seq_idx -> rel_tab row) hide under GEMM 1 of
+      // this tile, which the workers would otherwise just wait for; GEMM 0 of the next tile is issued after GEMM 1 anyway
+      if (t + 1 < t_end) build_a0(t + 1);
       // ---- E1
       mbar_wait(d1_full, ph);
       tc_fence_after();
@@ -271,43 +288,58 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
       store_half(A2, v);
       fence_proxy_async();
       mbar_arrive(a2_full);
-      // ---- E2: LayerNorm + mask -> fp16 tile image (staged in A1, free since GEMM1 of this tile has completed) -> bulk store
+      // ---- E2: LayerNorm + mask -> fp16 tile image (staged in A1, free since GEMM1 of this tile has completed) -> bulk store.
+      //      Statistics of the whole row per thread: own 64 columns + the other group's 64 re-read from TMEM, single pass with the
+      //      own-half mean as shift (as in et_fused.cuh)
       mbar_wait(d2_full, ph);
       tc_fence_after();
       load_half(D2, v);
-      tc_fence_before();
-      float s = 0.f;
+      float s0 = 0.f;
 #pragma unroll
       for (int n = 0; n < 64; ++n) {
         v[n] += b4_s[cg + n];
-        s += v[n];
+        s0 += v[n];
       }
-      red_s[wg * 128 + row] = s;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mean = (red_s[row] + red_s[128 + row]) * (1.f / 128.f);
-      float q2 = 0.f;
+      const float shift = s0 * (1.f / 64.f);
+      float sd = 0.f, sq = 0.f;
 #pragma unroll
       for (int n = 0; n < 64; ++n) {
-        const float d = v[n] - mean;
-        q2 += d * d;
+        const float d = v[n] - shift;
+        sd += d;
+        sq += d * d;
       }
-      red_q[wg * 128 + row] = q2;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float rstd = rsqrtf((red_q[row] + red_q[128 + row]) * (1.f / 128.f) + 1e-5f);
+      const int og = 64 - cg;
+      {
+        float w[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld32(D2 + lane_base + og + 32 * h, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int n = 0; n < 32; ++n) {
+            const float d = w[n] + b4_s[og + 32 * h + n] - shift;
+            sd += d;
+            sq += d * d;
+          }
+        }
+      }
+      tc_fence_before();
+      const float dm = sd * (1.f / 128.f);
+      const float mean = shift + dm;
+      const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - dm * dm, 0.f) + 1e-5f);
       float mk = 0.f;
       if (j < a.N) mk = a.mask[m] * a.mask[(long long)b * a.N + j];
 #pragma unroll
       for (int n = 0; n < 64; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
       store_half(A1, v);
       fence_proxy_async();
+      if (threadIdx.x < 128 && t + 1 < t_end) (ph ? PA_s : PA_s2)[threadIdx.x] = pa_next;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) {
         uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * 32768LL);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(A1)), "r"(32768) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // A1 may be overwritten by the next tile's E0
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
