@@ -13,8 +13,8 @@
 //
 // All three weight matrices (96 KB as fp16 swizzled images) stay resident in shared memory.  Warps 0-7: workers in two groups of 128
 // (thread <-> pair row <-> TMEM lane; group g owns columns [64g, 64g+64) = k-block g of every buffer it writes; group 0 builds the
-// idx_emb half of the per-tile feature block, group 1 the distogram half), warp 8: MMA issuer + TMEM owner, warp 9: loader.  MMA issue order G0(t+1) between G1(t) and G2(t), so the first GEMM
-// of the next tile is already done when the workers get there.  fp16 operands (10-bit mantissa = TF32 class, which the pair side
+// idx_emb half of the per-tile feature block, group 1 the distogram half), warp 8: MMA issuer + TMEM owner, warp 9: loader.  MMA issue order G1(t), G2(t), G0(t+1): the first GEMM
+// of the next tile runs under the LayerNorm epilogue of this one and is done when the workers get there.  fp16 operands (10-bit mantissa = TF32 class, which the pair side
 // tolerates: SURVEY §7 hard part 1), fp32 accumulate, positional tables evaluated on the host and gathered here.
 #pragma once
 #include "tc_common.cuh"
@@ -38,7 +38,13 @@ struct EeArgs {
   const __half* W2img;        // image [2 kb][128][128 B]
   const __half* W4img;
   long long tiles;            // B*N*JB
+  long long* dbg;             // optional clock64 timeline of worker thread 0 of CTA 0: [tile][16] stamps (tools/ee_timeline.py), or nullptr
 };
+
+#define EE_TS(id)                                                                                                  \
+  do {                                                                                                             \
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && (t - t_begin) < 8) a.dbg[(t - t_begin) * 16 + (id)] = clock64(); \
+  } while (0)
 
 constexpr int EE_W_BYTES = 32768;
 constexpr int EE_WORKERS = 256;
@@ -106,12 +112,14 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
   const uint32_t D0 = tmem_base, D1 = tmem_base + 128, D2 = tmem_base + 256;
 
   // tiles are ordered (b, jb, i) with i fastest; the f_j image changes when (b, jb) changes
-  auto tile_bjb = [&](long long t) -> long long { return t / a.N; };
+  // (32-bit arithmetic: tiles < 2^31, and a 64-bit division costs ~100 instructions -- three of them per tile and thread were 1.5 k
+  //  of the 10.6 k cycles of a tile)
+  auto tile_bjb = [&](long long t) -> long long { return (long long)((unsigned)t / (unsigned)a.N); };
   auto tile_m = [&](long long t, int& jb, int& b) -> long long {
-    const long long bjb = t / a.N;
-    const int i = (int)(t - bjb * a.N);
-    b = (int)(bjb / a.JB);
-    jb = (int)(bjb - (long long)b * a.JB);
+    const unsigned bjb = (unsigned)t / (unsigned)a.N;
+    const int i = (int)((unsigned)t - bjb * (unsigned)a.N);
+    b = (int)(bjb / (unsigned)a.JB);
+    jb = (int)(bjb - (unsigned)b * (unsigned)a.JB);
     return (long long)b * a.N + i;
   };
 
@@ -170,11 +178,11 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
         tc_fence_after();
         gemm128(D1, a1, a1 + 16384, w2);
         umma_commit(d1_full);
-        if (t + 1 < t_end) G0(t + 1);
         mbar_wait(a2_full, ph);
         tc_fence_after();
         gemm128(D2, a2, a2 + 16384, w4);
         umma_commit(d2_full);
+        if (t + 1 < t_end) G0(t + 1);  // runs under this tile's LayerNorm epilogue (the workers load D0 of this tile long before)
       }
     }
   } else {
@@ -263,24 +271,31 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
         pa_next = a.PA[mn * 128 + threadIdx.x];  // consumed at the end of this iteration
       }
       float v[64];
+      EE_TS(0);
       // ---- E0
       mbar_wait(d0_full, ph);
       tc_fence_after();
+      EE_TS(1);
       load_half(D0, v);
       tc_fence_before();
 #pragma unroll
       for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + PA_t[cg + n], 0.f);
       if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tile t-1's store has left A1
+      EE_TS(2);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      EE_TS(3);
       store_half(A1, v);
       fence_proxy_async();
       mbar_arrive(a1_full);
+      EE_TS(4);
       // the next tile's feature block is gathered here: its two dependent global loads (seq_idx -> rel_tab row) hide under GEMM 1 of
       // this tile, which the workers would otherwise just wait for; GEMM 0 of the next tile is issued after GEMM 1 anyway
       if (t + 1 < t_end) build_a0(t + 1);
+      EE_TS(5);
       // ---- E1
       mbar_wait(d1_full, ph);
       tc_fence_after();
+      EE_TS(6);
       load_half(D1, v);
       tc_fence_before();
 #pragma unroll
@@ -288,11 +303,13 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
       store_half(A2, v);
       fence_proxy_async();
       mbar_arrive(a2_full);
+      EE_TS(7);
       // ---- E2: LayerNorm + mask -> fp16 tile image (staged in A1, free since GEMM1 of this tile has completed) -> bulk store.
       //      Statistics of the whole row per thread: own 64 columns + the other group's 64 re-read from TMEM, single pass with the
       //      own-half mean as shift (as in et_fused.cuh)
       mbar_wait(d2_full, ph);
       tc_fence_after();
+      EE_TS(8);
       load_half(D2, v);
       float s0 = 0.f;
 #pragma unroll
@@ -324,6 +341,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
         }
       }
       tc_fence_before();
+      EE_TS(9);
       const float dm = sd * (1.f / 128.f);
       const float mean = shift + dm;
       const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - dm * dm, 0.f) + 1e-5f);
@@ -334,7 +352,9 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
       store_half(A1, v);
       fence_proxy_async();
       if (threadIdx.x < 128 && t + 1 < t_end) (ph ? PA_s : PA_s2)[threadIdx.x] = pa_next;
+      EE_TS(10);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      EE_TS(11);
       if (threadIdx.x == 0) {
         uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * 32768LL);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(A1)), "r"(32768) : "memory");

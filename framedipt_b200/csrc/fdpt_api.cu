@@ -454,6 +454,8 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
   a.ln_g = T.eln_g; a.ln_b = T.eln_b; a.mask = in->res_mask; a.W0img = T.imgE0; a.W2img = T.imgE2; a.W4img = T.imgE4;
   a.tiles = M * w.JB;
   (void)P;
+  a.dbg = (ctx->dbg_flags & 8192) ? ctx->et_dbg : nullptr;
+  if (a.tiles >= (1LL << 31)) return fail(ctx, FDPT_ERR_INVALID, "B*N*ceil(N/128) = %lld tiles: the pair kernels index tiles with 32 bits", a.tiles);
   tc::ee_fused_kernel<<<(unsigned)std::min<long long>(ctx->num_sms, a.tiles), tc::EE_THREADS, tc::ee_smem_bytes(), st>>>(a);
   LAUNCH_CHECK();
   return FDPT_OK;
