@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--debug-flags", type=int, default=0, help="FDPT_OPT_DEBUG_FLAGS bit set (A/B switches of include/fdpt.h)")
     ap.add_argument("--no-spinup", action="store_true", help="skip the untimed clock spin-up (for ncu launch lists, where every launch is expensive)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2_tcr350")
@@ -272,6 +273,8 @@ def main():
     noise_host = torch.from_numpy(np.random.normal(size=(K + W, 2, B, N, 3))).pin_memory()
     noise_dev = noise_host.to(dev)
     ctx.reserve(B, N)
+    if args.debug_flags:
+        ctx.set_option(3, args.debug_flags)
 
     def barrier():
         if dist is not None:

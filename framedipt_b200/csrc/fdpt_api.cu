@@ -506,15 +506,17 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
   }
   ipa_opt_kernel<<<(unsigned)M, NH * PV, 0, st>>>((int)M, w.cat, quats, trans);
   LAUNCH_CHECK();
-  if (ln_out && ctx->gemm_tc && !(ctx->dbg_flags & 256) && (CAT / 64) % 2 == 0) {
-    // linear_out as a 2-way split-K GEMM (K = 2432 is one long serial k-loop per CTA otherwise: 88 CTAs x 38 k-blocks); the two
+  const int OUT_SPLIT = (ctx->dbg_flags & 16384) ? 2 : 3;  // K = 2688 = 42 k-blocks = 3 x 14 (debug flag 16384: 2 x 21)
+  if (ln_out && ctx->gemm_tc && !(ctx->dbg_flags & 256) && (CAT / 64) % OUT_SPLIT == 0 && w.tmpB - w.tmpA == w.tmpC - w.tmpB) {
+    // linear_out as a 3-way split-K GEMM (one long serial k-loop per CTA otherwise: 88 CTAs x 42 k-blocks; split: 264 CTAs x 14); the
     // partial products are summed, biased, masked and added to the residual inside the LayerNorm kernel that follows
     GemmArgs g;
-    g.A = w.cat; g.lda = CAT; g.sA1 = CAT / 2; g.B = p.Wout_perm; g.ldb = CAT; g.sB1 = CAT / 2;
-    g.C = w.tmpB; g.ldc = C_S; g.sC1 = w.tmpC - w.tmpB; g.M = (int)M; g.N = C_S; g.K = CAT / 2;
-    CK(gemm_dispatch(ctx, g, true, 2, st));
+    g.A = w.cat; g.lda = CAT; g.sA1 = CAT / OUT_SPLIT; g.B = p.Wout_perm; g.ldb = CAT; g.sB1 = CAT / OUT_SPLIT;
+    g.C = w.tmpA; g.ldc = C_S; g.sC1 = w.tmpB - w.tmpA; g.M = (int)M; g.N = C_S; g.K = CAT / OUT_SPLIT;
+    CK(gemm_dispatch(ctx, g, true, OUT_SPLIT, st));
     ctx->launches++;
-    sum2_layernorm_kernel<C_S><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(w.tmpB, w.tmpC, p.bout, residual, outmask, ln_out, ln_g, ln_b, M);
+    sumk_layernorm_kernel<C_S><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(w.tmpA, w.tmpB - w.tmpA, OUT_SPLIT, p.bout, residual, outmask, ln_out, ln_g,
+                                                                        ln_b, M);
     LAUNCH_CHECK();
     return FDPT_OK;
   }

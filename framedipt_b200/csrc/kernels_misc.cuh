@@ -11,10 +11,11 @@ namespace fdpt {
 //   y = LN(x) * gamma + beta ; optionally y *= rowmask[row] (node mask) or pair mask m[b,i]*m[b,j].
 // x and y may alias.
 // ------------------------------------------------------------------------------------------------
-// y = LN(residual + inmask * (p0 + p1 + bias)): the reduce step of a 2-way split-K GEMM fused into the LayerNorm that follows it
-// (IPA linear_out, K = 2432: two K halves run as two batches of the GEMM kernel and halve its per-CTA latency).
+// y = LN(residual + inmask * (sum_k part_k + bias)): the reduce step of a split-K GEMM fused into the LayerNorm that follows it
+// (IPA linear_out, K = 2688: the K thirds run as three batches of the GEMM kernel and cut its per-CTA latency; parts are `pstride`
+// floats apart).
 template <int C>
-__global__ void __launch_bounds__(256) sum2_layernorm_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+__global__ void __launch_bounds__(256) sumk_layernorm_kernel(const float* __restrict__ parts, long long pstride, int nparts,
                                                              const float* __restrict__ bias, const float* __restrict__ residual,
                                                              const float* __restrict__ inmask, float* __restrict__ y,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta, long long rows) {
@@ -28,7 +29,9 @@ __global__ void __launch_bounds__(256) sum2_layernorm_kernel(const float* __rest
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int c = lane + 32 * i;
-    float x = (p0[row * C + c] + p1[row * C + c] + bias[c]) * im;
+    float acc = parts[row * C + c];
+    for (int k = 1; k < nparts; ++k) acc += parts[k * pstride + row * C + c];  // fixed order: deterministic
+    float x = (acc + bias[c]) * im;
     if (residual) x += residual[row * C + c];
     v[i] = x;
     s += x;

@@ -195,9 +195,10 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *      4  route the clock64 timeline buffer to the IPA core kernel instead of EdgeTransition
  *      8  gemm_tc: 128-column tiles whenever N > 128  16  launch the GEMM kernels without programmatic dependent launch
  *     32 / 64 / 128  CTA-pair EdgeTransition experiments: no weight waits / no MMAs / every MMA twice (results are garbage)
- *    256  IPA linear_out as one GEMM instead of 2-way split-K + fused reduce
+ *    256  IPA linear_out as one GEMM instead of split-K + fused reduce
  *    512  lin_tc: write the clock64 timeline of CTA (0,0)   1024  lin_tc: 32-column epilogue staging passes
- *   8192  edge embedder: write the clock64 timeline of worker thread 0 of CTA 0 */
+ *   8192  edge embedder: write the clock64 timeline of worker thread 0 of CTA 0
+ *  16384  IPA linear_out: 2-way instead of 3-way split-K */
 enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
        FDPT_OPT_ET_PAIR = 5 /* 1: EdgeTransition kernel on CTA pairs (cta_group::2; experimental, slower); 0 (default): single-CTA kernel */ };
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
