@@ -60,6 +60,8 @@ struct Workspace {
   int capB = 0, capN = 0;
   // node side
   float *node_feat, *feat1d, *node0, *node, *tmpA, *tmpB, *tmpC;  // tmp: [M,320]-capable
+  __half *imgF = nullptr, *imgT1 = nullptr, *imgT2 = nullptr, *imgN = nullptr;  // operand images passed between consecutive Linear layers (lin_tc Ximg / Yimg)
+  size_t img_bytes = 0;
   float *PA;  // edge embedder layer-1 per-residue partial A f_i + b0
   float *proj, *kn, *cat;  // IPA: fused projections [M,6816], -gamma/2 |k_pts|^2 [M,8], concat [M,2688]
   int ldS;
@@ -342,6 +344,8 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.pred_rigids = carve<float>(p, M * 7); w.trans_score = carve<float>(p, M * 3); w.psi = carve<float>(p, M * 2);
     w.rig_cur = carve<float>(p, M * 7); w.rig_next = carve<float>(p, M * 7); w.sc_ca = carve<float>(p, M * 3);
     w.t_emb_b = carve<float>(p, (size_t)B * EMB); w.t32_b = carve<float>(p, B); w.bb_tmp = carve<float>(p, M * 15);
+    w.img_bytes = ((M + 127) / 128) * (size_t)tc::LT_MAX_KB * tc::LT_STAGE_BYTES;
+    w.imgF = carve<__half>(p, w.img_bytes / 2); w.imgT1 = carve<__half>(p, w.img_bytes / 2); w.imgT2 = carve<__half>(p, w.img_bytes / 2); w.imgN = carve<__half>(p, w.img_bytes / 2);
     w.rot_score = carve<double>(p, M * 3); w.sigma_b = carve<double>(p, B); w.sched_dev = carve<double>(p, 4096 * FDPT_SCHED_COLS); w.step_dev = carve<int>(p, 64); w.call_ptrs = carve<void*>(p, 16); w.temb_tab = carve<float>(p, 4096 * EMB);
     if (!pass) {
       w.bytes = (size_t)(p - (char*)nullptr);
@@ -350,6 +354,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
   }
   w.capB = B; w.capN = N; w.JB = (N + 127) / 128; w.ldS = (N + 3) & ~3;
   CK(cudaMemset(w.z, 0, sizeof(__half) * M * w.JB * 16384));  // padded rows (j >= N) of the tile images stay zero
+  CK(cudaMemset(w.imgF, 0, 4 * w.img_bytes));                  // rows >= M of the last m-tile of the chained operand images stay zero
   return FDPT_OK;
 }
 
@@ -359,7 +364,9 @@ struct Lin {
   cudaStream_t st;
   // y[M,N] (ldc) = epi(x[M,K] (lda) @ W[N,K]^T (ldb))
   int operator()(const float* x, int lda, const float* W, int ldb, const float* bias, float* y, int ldc, long long M, int N, int K,
-                 int relu = 0, const float* residual = nullptr, int ldr = 0, const float* rowmask = nullptr, int accumulate = 0) const {
+                 int relu = 0, const float* residual = nullptr, int ldr = 0, const float* rowmask = nullptr, int accumulate = 0,
+                 const __half* x_img = nullptr, __half* y_img = nullptr) const {
+    // x_img / y_img: operand-image chaining between consecutive Linear layers (lin_tc.cuh); only valid on the packed lin_tc path
     if (ctx->gemm_tc && !accumulate && M > 0) {
       auto it = ctx->packed.find(std::make_tuple(W, ldb, N, K));
       if (it != ctx->packed.end()) {
@@ -373,6 +380,8 @@ struct Lin {
         a.bias = bias; a.relu = relu; a.rowmask = rowmask; a.residual = residual; a.ldr = ldr; a.Y = y; a.ldy = ldc;
         a.dbg_flags = ctx->dbg_flags;
         a.dbg = (ctx->dbg_flags & 512) ? ctx->et_dbg : nullptr;
+        if (y_img) a.dbg = reinterpret_cast<long long*>(y_img);  // lin_tc_kernel<*, YIMG = true> writes the output image through this field
+        if (x_img) a.X = reinterpret_cast<const float*>(x_img);  // lin_tc_kernel<XIMG = true> reads X as the operand image
         a.x_vec = tc::aligned16(x, lda, 0, 0);
         a.y_vec = 0;
         dim3 grid(m_tiles, (pw.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta);
@@ -386,12 +395,17 @@ struct Lin {
         attr[0].val.programmaticStreamSerializationAllowed = tc::g_use_pdl;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel, a);
+        cudaError_t e;
+        if (x_img && y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, true>, a);
+        else if (x_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, false>, a);
+        else if (y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, true>, a);
+        else e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, false>, a);
         ctx->launches++;
         if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "lin_tc launch: %s", cudaGetErrorString(e));
         return FDPT_OK;
       }
     }
+    if (x_img || y_img) return fail(ctx, FDPT_ERR_STATE, "operand-image chaining needs the packed lin_tc path");
     GemmArgs g;
     g.A = x; g.lda = lda; g.B = W; g.ldb = ldb; g.C = y; g.ldc = ldc; g.M = (int)M; g.N = N; g.K = K;
     g.bias = bias; g.relu = relu; g.residual = residual; g.ldr = ldr; g.rowmask = rowmask; g.accumulate = accumulate;
@@ -433,9 +447,15 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
   }
   auto& T = ctx->top;
   // node MLP
-  RET(lin(w.node_feat, FN, T.nW0, FN, T.nb0, w.tmpA, C_S, M, C_S, FN, 1));
-  RET(lin(w.tmpA, C_S, T.nW2, C_S, T.nb2, w.tmpB, C_S, M, C_S, C_S, 1));
-  RET(lin(w.tmpB, C_S, T.nW4, C_S, T.nb4, w.tmpA, C_S, M, C_S, C_S, 0));
+  if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {  // hidden activations as operand images (lin_tc Ximg / Yimg)
+    RET(lin(w.node_feat, FN, T.nW0, FN, T.nb0, nullptr, C_S, M, C_S, FN, 1, nullptr, 0, nullptr, 0, nullptr, w.imgT1));
+    RET(lin(nullptr, C_S, T.nW2, C_S, T.nb2, nullptr, C_S, M, C_S, C_S, 1, nullptr, 0, nullptr, 0, w.imgT1, w.imgT2));
+    RET(lin(nullptr, C_S, T.nW4, C_S, T.nb4, w.tmpA, C_S, M, C_S, C_S, 0, nullptr, 0, nullptr, 0, w.imgT2, nullptr));
+  } else {
+    RET(lin(w.node_feat, FN, T.nW0, FN, T.nb0, w.tmpA, C_S, M, C_S, FN, 1));
+    RET(lin(w.tmpA, C_S, T.nW2, C_S, T.nb2, w.tmpB, C_S, M, C_S, C_S, 1));
+    RET(lin(w.tmpB, C_S, T.nW4, C_S, T.nb4, w.tmpA, C_S, M, C_S, C_S, 0));
+  }
   RET(layernorm<C_S>(ctx, st, w.tmpA, node_out, T.nln_g, T.nln_b, M, in->res_mask));
   // edge embedder (edge_embed_fused.cuh): W0 = [A (F1) | B (F1) | C (32) | D (22)];  PA_i = A f_i + b0 per residue (fp32 class),
   // everything pair-sized inside one fused tcgen05 kernel
@@ -535,9 +555,15 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   const long long M = (long long)B * N;
   Lin lin{ctx, st};
   // per-residue parts: n = initial_embed(node); U_i = W1[:,128:256] n_i + b1; Pf_i = Wf[:,128:256] n_i + bf
-  RET(lin(node, C_S, p.Wie, C_S, p.bie, w.n_emb, C_Z, M, C_Z, C_S));
-  RET(lin(w.n_emb, C_Z, p.We1 + C_Z, ET_HID, p.be1, w.U, ET_HID, M, ET_HID, C_Z));
-  RET(lin(w.n_emb, C_Z, p.Wef + C_Z, ET_HID, p.bef, w.Pf, C_Z, M, C_Z, C_Z));
+  if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {  // n is written as fp32 (for the n_j images) AND as the operand image of the two GEMMs below
+    RET(lin(node, C_S, p.Wie, C_S, p.bie, w.n_emb, C_Z, M, C_Z, C_S, 0, nullptr, 0, nullptr, 0, nullptr, w.imgN));
+    RET(lin(nullptr, C_Z, p.We1 + C_Z, ET_HID, p.be1, w.U, ET_HID, M, ET_HID, C_Z, 0, nullptr, 0, nullptr, 0, w.imgN, nullptr));
+    RET(lin(nullptr, C_Z, p.Wef + C_Z, ET_HID, p.bef, w.Pf, C_Z, M, C_Z, C_Z, 0, nullptr, 0, nullptr, 0, w.imgN, nullptr));
+  } else {
+    RET(lin(node, C_S, p.Wie, C_S, p.bie, w.n_emb, C_Z, M, C_Z, C_S));
+    RET(lin(w.n_emb, C_Z, p.We1 + C_Z, ET_HID, p.be1, w.U, ET_HID, M, ET_HID, C_Z));
+    RET(lin(w.n_emb, C_Z, p.Wef + C_Z, ET_HID, p.bef, w.Pf, C_Z, M, C_Z, C_Z));
+  }
   {
     const long long chunks = (long long)B * w.JB * 128 * 16;
     tc::n_to_image_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(B, N, w.JB, w.n_emb, w.n_img);
@@ -579,6 +605,7 @@ int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaSt
   // x = [node | skip_embed(init_node)]
   copy_cols_kernel<<<(unsigned)((M * C_S + 255) / 256), 256, 0, st>>>(M, C_S, w.node, C_S, w.tf_x, TF_D, 0, nullptr);
   LAUNCH_CHECK();
+  const bool chain = ctx->gemm_tc && !(ctx->dbg_flags & 32768);  // debug flag 32768: no operand-image chaining
   RET(lin(w.node0, C_S, p.Wskip, C_S, p.bskip, w.tf_x + C_S, TF_D, M, C_SKIP, C_S));
   for (int l = 0; l < TF_LAYERS; ++l) {
     const auto& L = p.tf[l];
@@ -608,8 +635,13 @@ int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaSt
     }
     RET(lin(w.att_o, TF_D, L.Wo, TF_D, L.bo, w.tmpA, TF_D, M, TF_D, TF_D, 0, w.tf_x, TF_D));
     RET(layernorm<TF_D>(ctx, st, w.tmpA, w.tf_x, L.n1g, L.n1b, M, nullptr));
-    RET(lin(w.tf_x, TF_D, L.W1, TF_D, L.b1, w.tmpA, TF_D, M, TF_D, TF_D, 1));
-    RET(lin(w.tmpA, TF_D, L.W2, TF_D, L.b2, w.tmpB, TF_D, M, TF_D, TF_D, 0, w.tf_x, TF_D));
+    if (chain) {  // linear1 hands its ReLU output to linear2 as a ready operand image (no fp32 round trip, no re-split)
+      RET(lin(w.tf_x, TF_D, L.W1, TF_D, L.b1, nullptr, TF_D, M, TF_D, TF_D, 1, nullptr, 0, nullptr, 0, nullptr, w.imgF));
+      RET(lin(nullptr, TF_D, L.W2, TF_D, L.b2, w.tmpB, TF_D, M, TF_D, TF_D, 0, w.tf_x, TF_D, nullptr, 0, w.imgF, nullptr));
+    } else {
+      RET(lin(w.tf_x, TF_D, L.W1, TF_D, L.b1, w.tmpA, TF_D, M, TF_D, TF_D, 1));
+      RET(lin(w.tmpA, TF_D, L.W2, TF_D, L.b2, w.tmpB, TF_D, M, TF_D, TF_D, 0, w.tf_x, TF_D));
+    }
     RET(layernorm<TF_D>(ctx, st, w.tmpB, w.tf_x, L.n2g, L.n2b, M, nullptr));
   }
   // node = node + post_tfmr(x)
@@ -638,9 +670,15 @@ int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_o
     RET(run_ipa(ctx, b, B, N, w.node, w.z, w.quats, w.trans, in->res_mask, w.tmpC, C_S, w.node, in->res_mask, st, p.ln_g, p.ln_b, w.node));
     RET(run_seq_tfmr(ctx, b, B, N, in->res_mask, st));
     // node transition
-    RET(lin(w.node, C_S, p.Wt1, C_S, p.bt1, w.tmpA, C_S, M, C_S, C_S, 1));
-    RET(lin(w.tmpA, C_S, p.Wt2, C_S, p.bt2, w.tmpB, C_S, M, C_S, C_S, 1));
-    RET(lin(w.tmpB, C_S, p.Wt3, C_S, p.bt3, w.tmpA, C_S, M, C_S, C_S, 0, w.node, C_S));
+    if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {  // the hidden activations travel as operand images (lin_tc Ximg / Yimg)
+      RET(lin(w.node, C_S, p.Wt1, C_S, p.bt1, nullptr, C_S, M, C_S, C_S, 1, nullptr, 0, nullptr, 0, nullptr, w.imgT1));
+      RET(lin(nullptr, C_S, p.Wt2, C_S, p.bt2, nullptr, C_S, M, C_S, C_S, 1, nullptr, 0, nullptr, 0, w.imgT1, w.imgT2));
+      RET(lin(nullptr, C_S, p.Wt3, C_S, p.bt3, w.tmpA, C_S, M, C_S, C_S, 0, w.node, C_S, nullptr, 0, w.imgT2, nullptr));
+    } else {
+      RET(lin(w.node, C_S, p.Wt1, C_S, p.bt1, w.tmpA, C_S, M, C_S, C_S, 1));
+      RET(lin(w.tmpA, C_S, p.Wt2, C_S, p.bt2, w.tmpB, C_S, M, C_S, C_S, 1));
+      RET(lin(w.tmpB, C_S, p.Wt3, C_S, p.bt3, w.tmpA, C_S, M, C_S, C_S, 0, w.node, C_S));
+    }
     RET(layernorm<C_S>(ctx, st, w.tmpA, w.node, p.tln_g, p.tln_b, M, in->res_mask));
     // backbone update
     RET(lin(w.node, C_S, p.Wbb, C_S, p.bbb, w.upd, 6, M, 6, C_S));
@@ -661,9 +699,15 @@ int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_o
   LAUNCH_CHECK();
   // torsion head (ipa_pytorch.py:347-363)
   auto& T = ctx->top;
-  RET(lin(w.node, C_S, T.tW1, C_S, T.tb1, w.tmpA, C_S, M, C_S, C_S, 1));
-  RET(lin(w.tmpA, C_S, T.tW2, C_S, T.tb2, w.tmpB, C_S, M, C_S, C_S, 0, w.node, C_S));
-  RET(lin(w.tmpB, C_S, T.tWf, C_S, T.tbf, w.tors_u, 2, M, 2, C_S));
+  if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {
+    RET(lin(w.node, C_S, T.tW1, C_S, T.tb1, nullptr, C_S, M, C_S, C_S, 1, nullptr, 0, nullptr, 0, nullptr, w.imgT1));
+    RET(lin(nullptr, C_S, T.tW2, C_S, T.tb2, nullptr, C_S, M, C_S, C_S, 0, w.node, C_S, nullptr, 0, w.imgT1, w.imgT2));
+    RET(lin(nullptr, C_S, T.tWf, C_S, T.tbf, w.tors_u, 2, M, 2, C_S, 0, nullptr, 0, nullptr, 0, w.imgT2, nullptr));
+  } else {
+    RET(lin(w.node, C_S, T.tW1, C_S, T.tb1, w.tmpA, C_S, M, C_S, C_S, 1));
+    RET(lin(w.tmpA, C_S, T.tW2, C_S, T.tb2, w.tmpB, C_S, M, C_S, C_S, 0, w.node, C_S));
+    RET(lin(w.tmpB, C_S, T.tWf, C_S, T.tbf, w.tors_u, 2, M, 2, C_S));
+  }
   float* psi = (out && out->psi) ? out->psi : w.psi;
   psi_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, w.tors_u, in->fixed_mask, in->gt_psi, psi);
   LAUNCH_CHECK();
@@ -751,7 +795,10 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaFuncSetAttribute(tc::ee_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ee_smem_bytes());
   cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::tc_linear_smem_bytes(512));
   cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_tc_smem_bytes(128));
-  cudaFuncSetAttribute(tc::lin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
   float lower[NBINS];
   {

@@ -37,13 +37,23 @@ struct LinTcArgs {
   int x_vec, y_vec;
   int dbg_flags;               // bring-up: bit 0 skip the epilogue stores, bit 1 skip the MMAs
   long long* dbg;              // optional clock64 timeline of CTA (0,0): 16 stamps (tools/lin_timeline.py), or nullptr
+  // Operand-image chaining between consecutive Linear layers (both optional):
+  //   XIMG: X points to the split operand image, i.e. X is already available as the split operand image [m-tile][k-block][hi|lo][128 rows][128 B] written by the previous
+  //         layer's epilogue -> the staging phase (fp32 loads + split + swizzled stores by 256 threads) becomes nkb bulk copies;
+  //   Yimg: the epilogue writes the result in that same layout for the next layer (k-block = 64 output columns; rows >= M and
+  //         columns >= N are never written and stay zero from the allocation-time memset).  Y may then be null.
+  // (no extra fields: the input image travels in X when the kernel is instantiated with XIMG, the output image in `dbg` when it is
+  //  instantiated with YIMG -- a longer parameter block costs the plain instantiation 16 bytes of spills)
 };
 
 #define LT_TS(id)                                                                  \
   do {                                                                             \
-    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[(id)] = clock64();      \
+    if (!YIMG && a.dbg && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[(id)] = clock64(); \
   } while (0)
 
+// YIMG: the epilogue also (or only) writes the operand image of the next layer; a separate instantiation so that the plain kernel keeps
+// its register allocation
+template <bool XIMG, bool YIMG>
 __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -70,7 +80,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
-    for (int k = 0; k < LT_MAX_KB; ++k) mbar_init(&a_full[k], LT_WORKERS);
+    for (int k = 0; k < LT_MAX_KB; ++k) mbar_init(&a_full[k], XIMG ? 1 : LT_WORKERS);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], LT_WORKERS);
@@ -141,7 +151,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
     // ============================ workers: stage X once, then epilogues ============================
     pdl_wait();  // X (and residual / Y) belong to the predecessor kernel until it has completed
     if (tid == 0) LT_TS(2);
-    {
+    if constexpr (XIMG) {
+      if (tid == 0) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.X) + (size_t)blockIdx.x * a.nkb * LT_STAGE_BYTES;
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          mbar_arrive_expect_tx(&a_full[kb], LT_STAGE_BYTES);
+          bulk_g2s(Aimg + (size_t)kb * LT_STAGE_BYTES, src + (size_t)kb * LT_STAGE_BYTES, LT_STAGE_BYTES, &a_full[kb]);
+        }
+      }
+    } else {
       ChunkPlan pa;
       const int r0 = tid >> 3, c = tid & 7;
       pa.src = a.X + (long long)(m0 + r0) * a.ldx + 8 * c;
@@ -196,6 +214,34 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         if (n0 + cb >= a.N || (a.dbg_flags & 1)) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
+        if constexpr (YIMG) {
+          // thread = row, 32 consecutive columns in registers = four 16-byte chunks of the next layer's operand image
+          const int r = (warp & 3) * 32 + lane;
+          if (m0 + r < a.M) {
+            const float rm = a.rowmask ? __ldg(a.rowmask + m0 + r) : 1.f;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const int col = n0 + cb + 8 * cc;
+              if (col >= a.N) break;
+              float y[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float t = v[8 * cc + e] + ((a.bias && col + e < a.N) ? __ldg(a.bias + col + e) : 0.f);
+                if (a.relu) t = fmaxf(t, 0.f);
+                t *= rm;
+                if (a.residual && col + e < a.N) t += a.residual[(long long)(m0 + r) * a.ldr + col + e];
+                y[e] = (col + e < a.N) ? t : 0.f;
+              }
+              uint4 hi, lo;
+              split8(make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), hi, lo);
+              uint8_t* dst = reinterpret_cast<uint8_t*>(a.dbg) + ((size_t)blockIdx.x * ((a.N + 63) >> 6) + (col >> 6)) * LT_STAGE_BYTES +
+                             sw128_chunk_off(r, (col & 63) >> 3);
+              *reinterpret_cast<uint4*>(dst) = hi;
+              *reinterpret_cast<uint4*>(dst + 16384) = lo;
+            }
+          }
+          if (!a.Y) continue;
+        }
         if (sw == 32)
           store_transposed<32>(ep, v, stg, lane, mw, n0 + cb);
         else

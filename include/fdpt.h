@@ -198,7 +198,8 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *    256  IPA linear_out as one GEMM instead of split-K + fused reduce
  *    512  lin_tc: write the clock64 timeline of CTA (0,0)   1024  lin_tc: 32-column epilogue staging passes
  *   8192  edge embedder: write the clock64 timeline of worker thread 0 of CTA 0
- *  16384  IPA linear_out: 2-way instead of 3-way split-K */
+ *  16384  IPA linear_out: 2-way instead of 3-way split-K
+ *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition) */
 enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
        FDPT_OPT_ET_PAIR = 5 /* 1: EdgeTransition kernel on CTA pairs (cta_group::2; experimental, slower); 0 (default): single-CTA kernel */ };
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
