@@ -573,6 +573,7 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   a.B = B; a.N = N; a.JB = w.JB; a.z_in = z_in; a.z_out = z_out; a.n_img = w.n_img; a.Ui = w.U; a.Pf = w.Pf; a.b2 = p.be2;
   a.ln_g = p.eln_g; a.ln_b = p.eln_b; a.mask = mask; a.W1cat = p.imgW1cat; a.W2 = p.imgW2; a.W3cat = p.imgW3cat;
   a.tiles = M * w.JB;
+  if (a.tiles >= (1LL << 31)) return fail(ctx, FDPT_ERR_INVALID, "B*N*ceil(N/128) = %lld tiles: the pair kernels index tiles with 32 bits", a.tiles);
   a.dbg = (ctx->dbg_flags & 4) ? nullptr : ctx->et_dbg;
   if (ctx->et_pair && a.tiles >= 2) {
     const long long pairs = (a.tiles + 1) / 2;
