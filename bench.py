@@ -339,14 +339,15 @@ def main():
     sc_e, te_e = segment(W, K)
     h_out = {"prot_traj": torch.empty(K, B, N, 5, 3).pin_memory(), "rigid_traj": torch.empty(K + 1, B, N, 7).pin_memory(),
              "trans_traj": torch.empty(K, B, N, 3).pin_memory(), "rigid_0_traj": torch.empty(K, B, N, 5, 3).pin_memory()}
-    barrier()
-    t0 = time.perf_counter()
-    nd = noise_host[W:].to(dev, non_blocking=True)
-    o2 = ctx.sample(pf, sc_e, te_e, nd, self_condition=False)
-    for k in h_out:
-        h_out[k].copy_(o2[k], non_blocking=True)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    for e2e_pass in range(2):  # pass 0 is an untimed warm-up of exactly the same call (allocator blocks of these sizes, pinned staging)
+        barrier()
+        t0 = time.perf_counter()
+        nd = noise_host[W:].to(dev, non_blocking=True)
+        o2 = ctx.sample(pf, sc_e, te_e, nd, self_condition=False)
+        for k in h_out:
+            h_out[k].copy_(o2[k], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
     t_all = torch.tensor([e2e_s], device=dev)
     if dist is not None:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
