@@ -35,6 +35,14 @@ __global__ void __launch_bounds__(256) rot_score_kernel(int M, int N, const floa
                                                         const float* __restrict__ quats_0, int ld0,
                                                         const double* __restrict__ sigma_b, const float* __restrict__ mask,
                                                         double* __restrict__ out) {
+  __shared__ double coef_s[1000];
+  {
+    const int bc = min(blockIdx.x * 8, M - 1) / N;
+    const double sg = sigma_b[bc];
+    const double h = 0.5 * sg * sg;
+    for (int l = threadIdx.x; l < 1000; l += blockDim.x) coef_s[l] = (double)(2 * l + 1) * exp(-(double)l * (double)(l + 1) * h);
+  }
+  __syncthreads();
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -65,18 +73,26 @@ __global__ void __launch_bounds__(256) rot_score_kernel(int M, int N, const floa
   const float lo = sinf(omega / 2.f);
   const float dlo = 0.5f * cosf(omega / 2.f);
   const float lo2 = lo * lo;
+  // series coefficients (2l+1) exp(-l(l+1) sigma^2/2): they depend on the sample only (sigma is per sample), so the CTA evaluates
+  // the 1000 float64 exponentials once for the sample of its first residue; a warp whose residue belongs to the next sample (CTA
+  // straddling a sample boundary) evaluates its own
+  const int b_cta = min(blockIdx.x * 8, M - 1) / N;
+  const bool shared_coef = (b == b_cta);
   double f = 0.0, df = 0.0;
+  // the two divisions by lo / lo^2 are taken out of the sums (same value up to float64 rounding of the last bit)
   for (int l = lane; l < 1000; l += 32) {
     const float lh = (float)l + 0.5f;
     const float arg = __fmul_rn(omega, lh);
     float hi, c;
     sincosf(arg, &hi, &c);
     const float dhi = lh * c;
-    const double coef = (double)(2 * l + 1) * exp(-(double)l * (double)(l + 1) * hs2);
-    f += coef * (double)hi / (double)lo;
+    const double coef = shared_coef ? coef_s[l] : (double)(2 * l + 1) * exp(-(double)l * (double)(l + 1) * hs2);
+    f += coef * (double)hi;
     const float num = __fsub_rn(__fmul_rn(lo, dhi), __fmul_rn(hi, dlo));
-    df += coef * (double)num / (double)lo2;
+    df += coef * (double)num;
   }
+  f /= (double)lo;
+  df /= (double)lo2;
   f = warp_sum(f);
   df = warp_sum(df);
   if (lane < 3) {
