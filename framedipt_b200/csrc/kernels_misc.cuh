@@ -215,7 +215,18 @@ __global__ void compose_update_kernel(int M, const float* __restrict__ upd, cons
 // Rows have stride ld (multiple of 4, >= N, <= 1024); the row lives in registers between the single read and the single write.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long rows, int N, int ld, int rows_per_batch,
                                                            float scale, const float* __restrict__ keymask) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  // key mask of the CTA's sample, staged once in shared memory (16-byte reads, no bank conflicts): read per element from global
+  // memory it cost four L1 wavefronts per instruction, four times the traffic of the logits themselves.  The 8 rows of a CTA share
+  // one sample whenever rows_per_batch is a multiple of 8; otherwise (odd N) the rows read the mask from global memory.
+  __shared__ __align__(16) float km_s[1024];
+  const long long row0 = (long long)blockIdx.x * 8;
+  const bool one_sample = (rows_per_batch & 7) == 0;
+  if (one_sample) {
+    const float* kmg = keymask + (row0 / rows_per_batch) * N;
+    for (int j = threadIdx.x; j < ((N + 3) & ~3); j += blockDim.x) km_s[j] = j < N ? kmg[j] : 0.f;
+  }
+  __syncthreads();
+  const long long row = row0 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const long long b = row / rows_per_batch;
@@ -231,10 +242,19 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long r
     if (c < nch) {
       const float4 x = s4[c];
       const int j = 4 * c;
-      v[q].x = (j < N && km[j] != 0.f) ? x.x * scale : -INFINITY;
-      v[q].y = (j + 1 < N && km[j + 1] != 0.f) ? x.y * scale : -INFINITY;
-      v[q].z = (j + 2 < N && km[j + 2] != 0.f) ? x.z * scale : -INFINITY;
-      v[q].w = (j + 3 < N && km[j + 3] != 0.f) ? x.w * scale : -INFINITY;
+      float4 k4;
+      if (one_sample) {
+        k4 = *reinterpret_cast<const float4*>(km_s + j);  // entries >= N are 0
+      } else {
+        k4.x = j < N ? km[j] : 0.f;
+        k4.y = j + 1 < N ? km[j + 1] : 0.f;
+        k4.z = j + 2 < N ? km[j + 2] : 0.f;
+        k4.w = j + 3 < N ? km[j + 3] : 0.f;
+      }
+      v[q].x = k4.x != 0.f ? x.x * scale : -INFINITY;
+      v[q].y = k4.y != 0.f ? x.y * scale : -INFINITY;
+      v[q].z = k4.z != 0.f ? x.z * scale : -INFINITY;
+      v[q].w = k4.w != 0.f ? x.w * scale : -INFINITY;
       mx = fmaxf(mx, fmaxf(fmaxf(v[q].x, v[q].y), fmaxf(v[q].z, v[q].w)));
     }
   }
