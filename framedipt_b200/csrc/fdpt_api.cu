@@ -77,6 +77,7 @@ struct Workspace {
   // outputs / sampling state
   float *pred_rigids, *trans_score, *psi, *rig_cur, *rig_next, *sc_ca, *t_emb_b, *t32_b, *bb_tmp;
   double *rot_score, *sigma_b, *sched_dev;
+  int* sigma_idx_b;  // [B] row of the cached score table at the current step
   int* step_dev;  // [0] device step counter of the sampling loop, [1] number of steps T (the captured step graph reads both)
   void** call_ptrs;  // per-call buffer bases read by the captured step: [0] noise, [1] prot_traj, [2] rigid_0_traj, [3] trans_traj, [4] rigid_traj
   float* temb_tab;   // [4096, 32] this call's timestep-embedding table
@@ -121,6 +122,13 @@ struct fdpt_ctx {
   cudaStream_t own_stream = nullptr;   // the legacy default stream cannot be captured: fdpt_sample then runs on this stream,
   cudaEvent_t fence_in = nullptr, fence_out = nullptr;  // fenced against the caller's stream with these events
   long long* et_dbg = nullptr;  // optional clock64 timeline buffer of the EdgeTransition kernel (FDPT_OPT_ET_TIMELINE)
+  // so3.use_cached_score=True: [num_sigma, num_omega] score-norm table + omega boundaries (fdpt_set_score_table); null = series
+  double *score_table = nullptr, *omega_bounds = nullptr;
+  int tab_sigma = 0, tab_omega = 0;
+  // streaming read-back: an event after every progress_chunk timesteps of the most recent fdpt_sample call
+  int progress_chunk = 0, progress_steps = 0;
+  std::vector<cudaEvent_t> progress_ev;   // pool, grown on demand
+  int progress_used = 0;
   // live profiling (event pairs per slot)
   bool prof_on = false;
   struct ProfRec { cudaEvent_t a, b; int slot; };
@@ -129,6 +137,27 @@ struct fdpt_ctx {
 };
 
 namespace {
+
+int fail(fdpt_ctx* c, int code, const char* fmt, ...);
+
+// Every C-ABI entry point runs on the context's device and leaves the caller's current device (torch.cuda.current_device()) as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define GUARD(ctx)                                                                                          \
+  DeviceGuard dg__((ctx)->device);                                                                          \
+  if (!dg__.ok) return fail((ctx), FDPT_ERR_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
 
 int fail(fdpt_ctx* c, int code, const char* fmt, ...) {
   char buf[1024];
@@ -183,6 +212,8 @@ struct ProfScope {
 };
 
 int f1_dim(const fdpt_ctx* c) { return c->cfg.with_aatype ? 54 : 33; }
+// edge embedder input width: [f_i | f_j | relpos 32 | distogram 22 (only with embed_self_conditioning, score_network.py:95-96)]
+int ein_dim(const fdpt_ctx* c) { return 2 * f1_dim(c) + EMB + (c->cfg.embed_self_conditioning ? NBINS : 0); }
 
 std::vector<std::pair<std::string, std::vector<int64_t>>> expected_params(const fdpt_ctx* c) {
   std::vector<std::pair<std::string, std::vector<int64_t>>> v;
@@ -197,7 +228,7 @@ std::vector<std::pair<std::string, std::vector<int64_t>>> expected_params(const 
   const int f1 = f1_dim(c);
   const std::string ne = "embedding_layer.node_embedder", ee = "embedding_layer.edge_embedder";
   lin(ne + ".0", C_S, f1 + EMB); lin(ne + ".2", C_S, C_S); lin(ne + ".4", C_S, C_S); ln(ne + ".5", C_S);
-  lin(ee + ".0", C_Z, 2 * f1 + EMB + NBINS); lin(ee + ".2", C_Z, C_Z); lin(ee + ".4", C_Z, C_Z); ln(ee + ".5", C_Z);
+  lin(ee + ".0", C_Z, ein_dim(c)); lin(ee + ".2", C_Z, C_Z); lin(ee + ".4", C_Z, C_Z); ln(ee + ".5", C_Z);
   const std::string t = "score_model.trunk.";
   for (int b = 0; b < NBLK; ++b) {
     const std::string bs = std::to_string(b), p = t + "ipa_" + bs;
@@ -346,7 +377,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.t_emb_b = carve<float>(p, (size_t)B * EMB); w.t32_b = carve<float>(p, B); w.bb_tmp = carve<float>(p, M * 15);
     w.img_bytes = ((M + 127) / 128) * (size_t)tc::LT_MAX_KB * tc::LT_STAGE_BYTES;
     w.imgF = carve<__half>(p, w.img_bytes / 2); w.imgT1 = carve<__half>(p, w.img_bytes / 2); w.imgT2 = carve<__half>(p, w.img_bytes / 2); w.imgN = carve<__half>(p, w.img_bytes / 2);
-    w.rot_score = carve<double>(p, M * 3); w.sigma_b = carve<double>(p, B); w.sched_dev = carve<double>(p, 4096 * FDPT_SCHED_COLS); w.step_dev = carve<int>(p, 64); w.call_ptrs = carve<void*>(p, 16); w.temb_tab = carve<float>(p, 4096 * EMB);
+    w.rot_score = carve<double>(p, M * 3); w.sigma_b = carve<double>(p, B); w.sigma_idx_b = carve<int>(p, B); w.sched_dev = carve<double>(p, 4096 * FDPT_SCHED_COLS); w.step_dev = carve<int>(p, 64); w.call_ptrs = carve<void*>(p, 16); w.temb_tab = carve<float>(p, 4096 * EMB);
     if (!pass) {
       w.bytes = (size_t)(p - (char*)nullptr);
       CK(cudaMalloc(&w.base, w.bytes));
@@ -436,7 +467,7 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
   ProfScope ps(ctx, FDPT_PROF_EDGE_EMBED, st);
   Workspace& w = ctx->ws;
   const long long M = (long long)B * N, P = M * N;
-  const int F1 = f1_dim(ctx), FN = F1 + EMB, EIN = 2 * F1 + EMB + NBINS;
+  const int F1 = f1_dim(ctx), FN = F1 + EMB, EIN = ein_dim(ctx);
   Lin lin{ctx, st};
   if (in->rel_count <= 0 || in->rel_count > 4 * 4096) return fail(ctx, FDPT_ERR_INVALID, "rel_count %d out of range", in->rel_count);
   {
@@ -692,11 +723,15 @@ int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_o
   finish_frames_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, w.quats, w.trans, cs, rig);
   LAUNCH_CHECK();
   double* rs = (out && out->rot_score) ? out->rot_score : w.rot_score;
-  rot_score_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>((int)M, N, in->rigids_t, 7, w.quats, 4, in->sigma, in->res_mask, rs);
+  if (ctx->score_table && !in->sigma_idx) return fail(ctx, FDPT_ERR_INVALID, "a cached score table is installed: feats.sigma_idx is required");
+  if (!ctx->score_table && !in->sigma) return fail(ctx, FDPT_ERR_INVALID, "feats.sigma is required");
+  rot_score_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>((int)M, N, in->rigids_t, 7, w.quats, 4, in->sigma, in->res_mask, rs, ctx->score_table,
+                                                            ctx->omega_bounds, ctx->tab_omega, in->sigma_idx);
   LAUNCH_CHECK();
   float* ts = (out && out->trans_score) ? out->trans_score : w.trans_score;
   trans_score_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, N, in->rigids_t + 4, 7, rig + 4, 7, 1.0f, in->t32,
-                                                                  (float)ctx->cfg.r3_min_b, (float)ctx->cfg.r3_max_b, cs, 1, in->res_mask, ts);
+                                                                  (float)ctx->cfg.r3_min_b, (float)ctx->cfg.r3_max_b, ctx->cfg.r3_coordinate_scaling, 1,
+                                                                  in->res_mask, ts);
   LAUNCH_CHECK();
   // torsion head (ipa_pytorch.py:347-363)
   auto& T = ctx->top;
@@ -735,13 +770,15 @@ int z_image_to_fp32(fdpt_ctx* ctx, int B, int N, float* z, cudaStream_t st) {
 }
 
 __global__ void set_step_kernel(int B, const int* __restrict__ step_ptr, const float* __restrict__ t_emb_tab, const double* __restrict__ sched,
-                                float* __restrict__ t_emb_b, float* __restrict__ t32_b, double* __restrict__ sigma_b) {
+                                float* __restrict__ t_emb_b, float* __restrict__ t32_b, double* __restrict__ sigma_b,
+                                int* __restrict__ sigma_idx_b) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int step = *step_ptr;
   if (idx < B * EMB) t_emb_b[idx] = t_emb_tab[step * EMB + (idx % EMB)];
   if (idx < B) {
     t32_b[idx] = (float)sched[step * FDPT_SCHED_COLS + FDPT_SCHED_T32];
     sigma_b[idx] = sched[step * FDPT_SCHED_COLS + FDPT_SCHED_SIGMA];
+    sigma_idx_b[idx] = (int)sched[step * FDPT_SCHED_COLS + FDPT_SCHED_SIGMA_IDX];
   }
 }
 
@@ -781,9 +818,11 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
       cfg->no_qk_points != PQ || cfg->no_v_points != PV || cfg->num_blocks != NBLK || cfg->index_embed_size != EMB ||
       cfg->num_bins != NBINS || cfg->seq_tfmr_num_heads != TF_H || cfg->seq_tfmr_num_layers != TF_LAYERS)
     return FDPT_ERR_INVALID;  // kernels are specialised for the reference's default dims (config/base.yaml:55-79)
+  if (!(cfg->coordinate_scaling > 0.f) || !(cfg->r3_coordinate_scaling > 0.f)) return FDPT_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return FDPT_ERR_CUDA;
-  if (cudaSetDevice(device) != cudaSuccess) return FDPT_ERR_CUDA;
+  DeviceGuard dg(device);
+  if (!dg.ok) return FDPT_ERR_CUDA;
   fdpt_ctx* ctx = new fdpt_ctx();
   ctx->cfg = *cfg;
   ctx->device = device;
@@ -824,7 +863,7 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
 
 int fdpt_destroy(fdpt_ctx* ctx) {
   if (!ctx) return FDPT_OK;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   cudaDeviceSynchronize();
   for (auto& kv : ctx->params) cudaFree(kv.second.dev);
   for (auto& b : ctx->blk) {
@@ -843,6 +882,9 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaEventDestroy(ctx->fence_out);
   }
   cudaFreeHost(ctx->et_dbg);
+  cudaFree(ctx->score_table);
+  cudaFree(ctx->omega_bounds);
+  for (auto e : ctx->progress_ev) cudaEventDestroy(e);
   for (auto& kv : ctx->packed) cudaFree(kv.second.img);
   cudaFree(ctx->top.imgE0);
   cudaFree(ctx->top.imgE2);
@@ -860,6 +902,7 @@ int fdpt_num_params_expected(const fdpt_ctx* ctx) { return ctx ? (int)expected_p
 
 int fdpt_load_param(fdpt_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim) {
   if (!ctx || !key || !data || !shape) return FDPT_ERR_INVALID;
+  GUARD(ctx);
   const std::string k(key);
   if (is_unused_key(k)) return FDPT_OK;  // accepted and ignored, like dead parameters in the reference
   bool found = false;
@@ -884,6 +927,7 @@ int fdpt_load_param(fdpt_ctx* ctx, const char* key, const float* data, const int
 
 int fdpt_finalize_params(fdpt_ctx* ctx) {
   if (!ctx) return FDPT_ERR_INVALID;
+  GUARD(ctx);
   std::string missing;
   for (auto& e : expected_params(ctx))
     if (!ctx->params.count(e.first)) missing += (missing.empty() ? "" : ", ") + e.first;
@@ -899,7 +943,7 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
   T.tW1 = P(tp + ".linear_1.weight"); T.tb1 = P(tp + ".linear_1.bias"); T.tW2 = P(tp + ".linear_2.weight"); T.tb2 = P(tp + ".linear_2.bias");
   T.tWf = P(tp + ".linear_final.weight"); T.tbf = P(tp + ".linear_final.bias");
   {
-    const int F1 = f1_dim(ctx), EIN = 2 * F1 + EMB + NBINS;
+    const int F1 = f1_dim(ctx), EIN = ein_dim(ctx);
     if (!T.imgE0) CK(cudaMalloc(&T.imgE0, 32768));
     if (!T.imgE2) CK(cudaMalloc(&T.imgE2, 32768));
     if (!T.imgE4) CK(cudaMalloc(&T.imgE4, 32768));
@@ -907,7 +951,9 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
       const long long chunks = (long long)C_Z * (K / 8);
       tc::pack_weight_image_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(W, ldw, C_Z, K, Kvalid, img);
     };
-    pack(T.eW0 + 2 * F1, EIN, 64, EMB + NBINS, T.imgE0);   // k-block 0: [C | D | 0]
+    // k-block 0: [C | D | 0]; without self-conditioning features the D columns do not exist: their image columns stay zero, so the
+    // one-hot distogram bits the kernel builds multiply zeros
+    pack(T.eW0 + 2 * F1, EIN, 64, EIN - 2 * F1, T.imgE0);
     pack(T.eW0 + F1, EIN, 64, F1, T.imgE0 + 8192);          // k-block 1: [B | 0]
     pack(T.eW2, C_Z, C_Z, C_Z, T.imgE2);
     pack(T.eW4, C_Z, C_Z, C_Z, T.imgE4);
@@ -963,7 +1009,7 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
     }
   }
   {  // pre-split every Linear weight the node side multiplies with (lin_tc.cuh)
-    const int F1 = f1_dim(ctx), FN = F1 + EMB, EIN = 2 * F1 + EMB + NBINS;
+    const int F1 = f1_dim(ctx), FN = F1 + EMB, EIN = ein_dim(ctx);
     RET(pack_linear(ctx, T.nW0, FN, C_S, FN)); RET(pack_linear(ctx, T.nW2, C_S, C_S, C_S)); RET(pack_linear(ctx, T.nW4, C_S, C_S, C_S));
     RET(pack_linear(ctx, T.eW0, EIN, C_Z, F1));
     RET(pack_linear(ctx, T.tW1, C_S, C_S, C_S)); RET(pack_linear(ctx, T.tW2, C_S, C_S, C_S)); RET(pack_linear(ctx, T.tWf, C_S, 2, C_S));
@@ -991,7 +1037,7 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
 
 int fdpt_reserve(fdpt_ctx* ctx, int B, int N) {
   if (!ctx || B <= 0 || N <= 0) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   return reserve_ws(ctx, B, N);
 }
 
@@ -1003,7 +1049,7 @@ int fdpt_profile_enable(fdpt_ctx* ctx, int on) {
 
 int fdpt_profile_read(fdpt_ctx* ctx, int slot, int* count, double* total_ms) {
   if (!ctx || !count || !total_ms || slot < 0 || slot >= FDPT_PROF_SLOTS) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   CK(cudaDeviceSynchronize());
   *count = 0;
   *total_ms = 0.0;
@@ -1038,7 +1084,7 @@ int64_t fdpt_stat(const fdpt_ctx* ctx, int which) {
 
 int fdpt_forward(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_out* out, void* stream) {
   if (!ctx || !in) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   return forward_impl(ctx, B, N, in, out, (cudaStream_t)stream);
 }
 
@@ -1046,14 +1092,14 @@ int fdpt_reverse(fdpt_ctx* ctx, int B, int N, const float* rigids_t, const doubl
                  const float* diffuse_mask, const double* z_rot, const double* z_trans, const double* sched_row, int center,
                  int diffuse_rot, int diffuse_trans, float* rigids_out, void* stream) {
   if (!ctx || !rigids_t || !rot_score || !trans_score || !diffuse_mask || !z_rot || !z_trans || !sched_row || !rigids_out) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   RET(reserve_ws(ctx, std::max(B, ctx->ws.capB), std::max(N, ctx->ws.capN)));
   CK(cudaMemcpyAsync(ctx->ws.sched_dev, sched_row, sizeof(double) * FDPT_SCHED_COLS, cudaMemcpyHostToDevice, st));
   ReverseArgs a;
   a.N = N; a.rigids_t = rigids_t; a.rot_score = rot_score; a.trans_score = trans_score; a.dmask = diffuse_mask; a.z_rot = z_rot;
   a.z_trans = z_trans; a.sched = ctx->ws.sched_dev; a.center = center; a.diffuse_rot = diffuse_rot; a.diffuse_trans = diffuse_trans;
-  a.cs = ctx->cfg.coordinate_scaling; a.rigids_out = rigids_out;
+  a.cs = ctx->cfg.r3_coordinate_scaling; a.rigids_out = rigids_out;
   reverse_kernel<<<B, 256, 0, st>>>(a);
   LAUNCH_CHECK();
   return FDPT_OK;
@@ -1062,7 +1108,7 @@ int fdpt_reverse(fdpt_ctx* ctx, int B, int N, const float* rigids_t, const doubl
 int fdpt_backbone(fdpt_ctx* ctx, int B, int N, const float* rigids, const float* psi, const int32_t* aatype, float* atom37_bb,
                   void* stream) {
   if (!ctx || !rigids || !psi || !atom37_bb) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   const int M = B * N;
   backbone_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(M, rigids, psi, aatype, ctx->ideal, ctx->psi_frame, ctx->atom_mask, atom37_bb);
   LAUNCH_CHECK();
@@ -1072,7 +1118,7 @@ int fdpt_backbone(fdpt_ctx* ctx, int B, int N, const float* rigids, const float*
 int fdpt_rot_score(fdpt_ctx* ctx, int B, int N, const float* quats_t, const float* quats_0, const double* sigma, const float* mask,
                    double* out, void* stream) {
   if (!ctx || !quats_t || !quats_0 || !sigma || !out) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   const int M = B * N;
   rot_score_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(M, N, quats_t, 4, quats_0, 4, sigma, mask, out);
   LAUNCH_CHECK();
@@ -1082,20 +1128,20 @@ int fdpt_rot_score(fdpt_ctx* ctx, int B, int N, const float* quats_t, const floa
 int fdpt_trans_score(fdpt_ctx* ctx, int B, int N, const float* trans_t, const float* trans_0, const float* t32, const float* mask,
                      int scale, float* out, void* stream) {
   if (!ctx || !trans_t || !trans_0 || !t32 || !out) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   const int M = B * N;
   trans_score_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(M, N, trans_t, 3, trans_0, 3, 1.0f, t32, (float)ctx->cfg.r3_min_b,
-                                                                        (float)ctx->cfg.r3_max_b, ctx->cfg.coordinate_scaling, scale, mask, out);
+                                                                        (float)ctx->cfg.r3_max_b, ctx->cfg.r3_coordinate_scaling, scale, mask, out);
   LAUNCH_CHECK();
   return FDPT_OK;
 }
 
 int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t, const double* sched, const float* t_emb_tab,
-                const double* noise, int self_condition, int center, int diffuse_rot, int diffuse_trans, const fdpt_traj* out,
-                void* stream) {
+                const double* noise, uint64_t philox_seed, int self_condition, int center, int diffuse_rot, int diffuse_trans,
+                const fdpt_traj* out, void* stream) {
   if (!ctx || !feats || !sched || !t_emb_tab || !out || num_t <= 0 || num_t > 4096) return FDPT_ERR_INVALID;
-  if (num_t > 1 && !noise) return FDPT_ERR_INVALID;  /* noise rows are indexed by step: every step whose IS_LAST flag is 0 reads row s */
-  cudaSetDevice(ctx->device);
+  const int use_philox = noise == nullptr;  /* throughput mode: normals drawn on the device; otherwise noise rows are indexed by step */
+  GUARD(ctx);
   const auto host_t0 = std::chrono::steady_clock::now();
   struct HostTimer {
     fdpt_ctx* c; std::chrono::steady_clock::time_point t0;
@@ -1123,7 +1169,7 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
   const int fo = out->final_only;
   if (out->rigid_traj && !fo) CK(cudaMemcpyAsync(out->rigid_traj + (long long)T * M * 7, w.rig_cur, sizeof(float) * M * 7, cudaMemcpyDeviceToDevice, st));
   fdpt_feats f = *feats;
-  f.rigids_t = w.rig_cur; f.sc_ca_t = w.sc_ca; f.t_emb = w.t_emb_b; f.t32 = w.t32_b; f.sigma = w.sigma_b;
+  f.rigids_t = w.rig_cur; f.sc_ca_t = w.sc_ca; f.t_emb = w.t_emb_b; f.t32 = w.t32_b; f.sigma = w.sigma_b; f.sigma_idx = w.sigma_idx_b;
   fdpt_out o;
   memset(&o, 0, sizeof(o));
   o.rigids = w.pred_rigids; o.rot_score = w.rot_score; o.trans_score = w.trans_score; o.psi = w.psi;
@@ -1137,32 +1183,38 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
     // (pageable host sources: the runtime stages them before returning, so the stack arrays may go out of scope)
   }
   auto set_step = [&]() -> int {
-    set_step_kernel<<<(B * EMB + 255) / 256, 256, 0, st>>>(B, w.step_dev, w.temb_tab, w.sched_dev, w.t_emb_b, w.t32_b, w.sigma_b);
+    set_step_kernel<<<(B * EMB + 255) / 256, 256, 0, st>>>(B, w.step_dev, w.temb_tab, w.sched_dev, w.t_emb_b, w.t32_b, w.sigma_b, w.sigma_idx_b);
     LAUNCH_CHECK();
     return FDPT_OK;
   };
-  if (self_condition) {  // experiments/utils.py:571-578 (step counter = 0: t = 1.0)
+  const bool update_sc = !(self_condition & 2);  // inference_fn(embed_self_conditioning=False): sc_ca_t keeps its initial value
+  if (self_condition & 1) {  // experiments/utils.py:571-578 (step counter = 0: t = 1.0)
     RET(set_step());
     RET(forward_impl(ctx, B, N, &f, &o, st));
     copy_trans_kernel<<<gM3, 256, 0, st>>>((int)M, w.pred_rigids, w.sc_ca);
     LAUNCH_CHECK();
   }
-  const int32_t* aat = ctx->cfg.with_aatype ? feats->aatype : nullptr;
+  // residue types of the trajectory's backbone atoms: the inference_fn call's own inpainting / input_aatype flags decide
+  // (experiments/utils.py:549-555), independently of the model's
+  const int32_t* aat = feats->aatype_bb_given ? feats->aatype_bb : (ctx->cfg.with_aatype ? feats->aatype : nullptr);
   // One timestep.  Per-step slices (noise, schedule row, trajectory slots) are resolved on the device from the step counter, so the
   // same enqueue sequence -- and therefore one captured CUDA graph -- serves every step that does a reverse update.
   auto enqueue_step = [&](bool last) -> int {
     RET(set_step());
     RET(forward_impl(ctx, B, N, &f, &o, st));
     if (!last) {
-      copy_trans_kernel<<<gM3, 256, 0, st>>>((int)M, w.pred_rigids, w.sc_ca);
-      LAUNCH_CHECK();
+      if (update_sc) {  // experiments/utils.py:356-358
+        copy_trans_kernel<<<gM3, 256, 0, st>>>((int)M, w.pred_rigids, w.sc_ca);
+        LAUNCH_CHECK();
+      }
       ReverseArgs a;
       a.N = N; a.rigids_t = w.rig_cur; a.rot_score = w.rot_score; a.trans_score = w.trans_score; a.dmask = w.dmask;
       a.z_rot = nullptr; a.z_trans = nullptr; a.noise_half = M * 3;
+      a.use_philox = use_philox; a.philox_seed = philox_seed;
       a.noise_ref.step = w.step_dev; a.noise_ref.stride = 2 * M * 3; a.noise_ref.base = w.call_ptrs + 0;
       a.sched = w.sched_dev; a.sched_ref.step = w.step_dev; a.sched_ref.stride = FDPT_SCHED_COLS;
       a.center = center; a.diffuse_rot = diffuse_rot; a.diffuse_trans = diffuse_trans;
-      a.cs = ctx->cfg.coordinate_scaling; a.rigids_out = w.rig_next;
+      a.cs = ctx->cfg.r3_coordinate_scaling; a.rigids_out = w.rig_next;
       reverse_kernel<<<B, 256, 0, st>>>(a);
       LAUNCH_CHECK();
     } else {
@@ -1205,8 +1257,12 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
   auto put = [&](const void* p, size_t n) { key.insert(key.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
   {
     const int ints[12] = {B, N, fo, center, diffuse_rot, diffuse_trans, ctx->gemm_tc, out->prot_traj != nullptr, out->rigid_0_traj != nullptr,
-                          out->trans_traj != nullptr, out->rigid_traj != nullptr, 0};
+                          out->trans_traj != nullptr, out->rigid_traj != nullptr, use_philox};
     put(ints, sizeof(ints));
+    put(&philox_seed, sizeof(philox_seed));
+    put(&self_condition, sizeof(self_condition));
+    put(&aat, sizeof(aat));
+    put(&ctx->score_table, sizeof(ctx->score_table));
     put(&f, sizeof(f));
     put(&st, sizeof(st));
     put(&w.base, sizeof(w.base));
@@ -1214,10 +1270,23 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
   int n_graph_steps = 0;
   for (int s = 0; s < T; ++s) n_graph_steps += sched[s * FDPT_SCHED_COLS + FDPT_SCHED_IS_LAST] == 0.0;
   const bool use_graph = ctx->use_graph && !ctx->prof_on && n_graph_steps >= 2;
+  ctx->progress_used = 0;
+  ctx->progress_steps = T;
+  auto mark_progress = [&](int s) -> int {  // event after step s when it closes a chunk (or the call)
+    if (ctx->progress_chunk <= 0 || ((s + 1) % ctx->progress_chunk != 0 && s != T - 1)) return FDPT_OK;
+    if (ctx->progress_used == (int)ctx->progress_ev.size()) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->progress_ev.push_back(e);
+    }
+    CK(cudaEventRecord(ctx->progress_ev[ctx->progress_used++], st));
+    return FDPT_OK;
+  };
   for (int s = 0; s < T; ++s) {
     const bool last = sched[s * FDPT_SCHED_COLS + FDPT_SCHED_IS_LAST] != 0.0;  // !(t > min_t)
     if (last || !use_graph) {
       RET(enqueue_step(last));
+      RET(mark_progress(s));
       continue;
     }
     auto& sg = ctx->step_graph;
@@ -1246,12 +1315,94 @@ int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t,
     }
     CK(cudaGraphLaunch(sg.exec, st));
     ctx->launches += sg.launches;
+    RET(mark_progress(s));
   }
   if (out->psi_pred) CK(cudaMemcpyAsync(out->psi_pred, w.psi, sizeof(float) * M * 2, cudaMemcpyDeviceToDevice, st));
   if (fenced) {
     CK(cudaEventRecord(ctx->fence_out, st));
     CK(cudaStreamWaitEvent(user_st, ctx->fence_out, 0));
   }
+  return FDPT_OK;
+}
+
+int fdpt_set_progress_chunk(fdpt_ctx* ctx, int chunk_steps) {
+  if (!ctx || chunk_steps < 0) return FDPT_ERR_INVALID;
+  ctx->progress_chunk = chunk_steps;
+  return FDPT_OK;
+}
+
+int fdpt_wait_step(fdpt_ctx* ctx, int step) {
+  if (!ctx) return FDPT_ERR_INVALID;
+  GUARD(ctx);
+  if (ctx->progress_chunk <= 0 || step < 0 || step >= ctx->progress_steps) return fail(ctx, FDPT_ERR_STATE, "no progress event covers step %d", step);
+  int idx = step / ctx->progress_chunk;  // the chunk's closing event (the last chunk may be short: its event is the last one recorded)
+  if (idx >= ctx->progress_used) idx = ctx->progress_used - 1;
+  if (idx < 0) return fail(ctx, FDPT_ERR_STATE, "no fdpt_sample call recorded progress events");
+  CK(cudaEventSynchronize(ctx->progress_ev[idx]));
+  return FDPT_OK;
+}
+
+int fdpt_set_score_table(fdpt_ctx* ctx, const double* score_norms, int num_sigma, int num_omega, const double* omega_bounds) {
+  if (!ctx) return FDPT_ERR_INVALID;
+  GUARD(ctx);
+  CK(cudaDeviceSynchronize());
+  cudaFree(ctx->score_table);
+  cudaFree(ctx->omega_bounds);
+  ctx->score_table = ctx->omega_bounds = nullptr;
+  ctx->tab_sigma = ctx->tab_omega = 0;
+  ctx->step_graph.key.clear();
+  if (!score_norms) return FDPT_OK;
+  if (!omega_bounds || num_sigma <= 0 || num_omega <= 1) return FDPT_ERR_INVALID;
+  CK(cudaMalloc(&ctx->score_table, sizeof(double) * (size_t)num_sigma * num_omega));
+  CK(cudaMalloc(&ctx->omega_bounds, sizeof(double) * (size_t)(num_omega - 1)));
+  CK(cudaMemcpy(ctx->score_table, score_norms, sizeof(double) * (size_t)num_sigma * num_omega, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->omega_bounds, omega_bounds, sizeof(double) * (size_t)(num_omega - 1), cudaMemcpyHostToDevice));
+  ctx->tab_sigma = num_sigma;
+  ctx->tab_omega = num_omega;
+  return FDPT_OK;
+}
+
+int fdpt_rot_score_idx(fdpt_ctx* ctx, int B, int N, const float* quats_t, const float* quats_0, const int32_t* sigma_idx, const float* mask,
+                       double* out, void* stream) {
+  if (!ctx || !quats_t || !quats_0 || !sigma_idx || !out) return FDPT_ERR_INVALID;
+  if (!ctx->score_table) return fail(ctx, FDPT_ERR_STATE, "no cached score table installed (fdpt_set_score_table)");
+  GUARD(ctx);
+  const int M = B * N;
+  rot_score_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(M, N, quats_t, 4, quats_0, 4, nullptr, mask, out, ctx->score_table, ctx->omega_bounds,
+                                                                  ctx->tab_omega, sigma_idx);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+
+int fdpt_sample_ref(fdpt_ctx* ctx, int B, int N, const float* impute, const float* diffuse_mask, const double* cdf, const double* omega_grid,
+                    int num_omega, const double* draws, uint64_t philox_seed, int diffuse_rot, int diffuse_trans, float* rigids_out,
+                    void* stream) {
+  if (!ctx || B <= 0 || N <= 0 || !cdf || !omega_grid || num_omega < 2 || !rigids_out) return FDPT_ERR_INVALID;
+  // se3_diffuser.py:484-507: without imputation values everything must be diffused
+  if (!impute && (!diffuse_rot || !diffuse_trans || diffuse_mask)) return fail(ctx, FDPT_ERR_INVALID, "Must provide imputation values");
+  GUARD(ctx);
+  SampleRefArgs a;
+  a.N = N; a.impute = impute; a.dmask = diffuse_mask; a.cdf = cdf; a.omega_grid = omega_grid; a.num_omega = num_omega; a.draws = draws;
+  a.philox_seed = philox_seed; a.diffuse_rot = diffuse_rot; a.diffuse_trans = diffuse_trans; a.cs = ctx->cfg.r3_coordinate_scaling; a.out = rigids_out;
+  sample_ref_kernel<<<dim3((N + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(a);
+  LAUNCH_CHECK();
+  return FDPT_OK;
+}
+
+int fdpt_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* node0, const float* mask, float* tfmr_out,
+                  float* node_out, void* stream) {
+  if (!ctx || blk < 0 || blk >= NBLK || !node || !node0 || !mask) return FDPT_ERR_INVALID;
+  if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
+  GUARD(ctx);
+  RET(reserve_ws(ctx, B, N));
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace& w = ctx->ws;
+  const size_t M = (size_t)B * N;
+  CK(cudaMemcpyAsync(w.node, node, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(w.node0, node0, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
+  RET(run_seq_tfmr(ctx, blk, B, N, mask, st));
+  if (tfmr_out) CK(cudaMemcpyAsync(tfmr_out, w.tf_x, sizeof(float) * M * TF_D, cudaMemcpyDeviceToDevice, st));
+  if (node_out) CK(cudaMemcpyAsync(node_out, w.node, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
   return FDPT_OK;
 }
 
@@ -1314,7 +1465,7 @@ int64_t fdpt_to_pdb(const float* atom37_bb, const int32_t* aatype, const int32_t
 // ---- unit entry points ------------------------------------------------------------------------------------
 int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act, float* y, void* stream) {
   if (!ctx || !x || !w || !y) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   // unit entry: Linear layers run on lin_tc with pre-split weights, so split this weight too (re-done on every call: the caller's
   // buffer is not a registered parameter and may have changed)
   if (ctx->gemm_tc) {
@@ -1328,6 +1479,7 @@ int fdpt_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float*
 
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
   if (!ctx) return FDPT_ERR_INVALID;
+  GUARD(ctx);
   switch (option) {
     case FDPT_OPT_GEMM_TC: ctx->gemm_tc = value != 0; return FDPT_OK;
     case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
@@ -1349,6 +1501,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
 
 int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n) {
   if (!ctx || !out || !ctx->et_dbg || n > 8 * 48 + 32) return FDPT_ERR_INVALID;
+  GUARD(ctx);
   cudaDeviceSynchronize();  // may report a sticky error after a trap: the host-mapped buffer is still readable
   memcpy(out, ctx->et_dbg, n * sizeof(long long));
   return FDPT_OK;
@@ -1357,7 +1510,7 @@ int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n) {
 int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, int lda, long long sa, const float* b, int ldb, long long sb,
                 int b_kmajor, float alpha, float* c, int ldc, long long sc, void* stream) {
   if (!ctx || !a || !b || !c || batch <= 0) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   GemmArgs g;
   g.A = a; g.lda = lda; g.sA1 = sa; g.B = b; g.ldb = ldb; g.sB1 = sb; g.C = c; g.ldc = ldc; g.sC1 = sc;
   g.M = M; g.N = N; g.K = K; g.alpha = alpha;
@@ -1369,7 +1522,7 @@ int fdpt_matmul(fdpt_ctx* ctx, int batch, int M, int N, int K, const float* a, i
 int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, float* y, int reps,
                       float* ms_per_call) {
   if (!ctx || !x || !w || !y || !ms_per_call || reps <= 0) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   CK(cudaDeviceSynchronize());
   RET(pack_linear(ctx, w, K, N, K));
   Lin lin{ctx, nullptr};
@@ -1392,7 +1545,7 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
 int fdpt_tc_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act, float* y,
                    void* stream) {
   if (!ctx || !x || !w || !y || M <= 0 || N % 128 || K % 64 || K > 512 || K <= 0 || N <= 0) return FDPT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   cudaStream_t st = (cudaStream_t)stream;
   __half* img = nullptr;
   CK(cudaMalloc(&img, (size_t)N * K * sizeof(__half)));
@@ -1413,7 +1566,7 @@ int fdpt_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* 
              const float* mask, float* out, void* stream) {
   if (!ctx || blk < 0 || blk >= NBLK || !s || !z || !quats || !trans || !mask || !out) return FDPT_ERR_INVALID;
   if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   RET(reserve_ws(ctx, B, N));
   RET(z_fp32_to_image(ctx, B, N, z, (cudaStream_t)stream));
   return run_ipa(ctx, blk, B, N, s, ctx->ws.z, quats, trans, mask, out, C_S, nullptr, nullptr, (cudaStream_t)stream);
@@ -1423,7 +1576,7 @@ int fdpt_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node
                          void* stream) {
   if (!ctx || blk < 0 || blk >= NBLK - 1 || !node || !z_in || !mask || !z_out) return FDPT_ERR_INVALID;
   if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   RET(reserve_ws(ctx, B, N));
   RET(z_fp32_to_image(ctx, B, N, z_in, (cudaStream_t)stream));
   RET(run_edge_transition(ctx, blk, B, N, node, ctx->ws.z, mask, ctx->ws.z, (cudaStream_t)stream));
@@ -1433,7 +1586,7 @@ int fdpt_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node
 int fdpt_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, float* edge_out, void* stream) {
   if (!ctx || !in || !node_out || !edge_out) return FDPT_ERR_INVALID;
   if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   RET(reserve_ws(ctx, B, N));
   RET(run_embed(ctx, B, N, in, node_out, ctx->ws.z, (cudaStream_t)stream));
   return z_image_to_fp32(ctx, B, N, edge_out, (cudaStream_t)stream);

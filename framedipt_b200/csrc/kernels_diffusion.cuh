@@ -34,9 +34,13 @@ FDPT_DEVINL P* step_resolve(P* direct, const StepRef& r) {
 __global__ void __launch_bounds__(256) rot_score_kernel(int M, int N, const float* __restrict__ quats_t, int ldt,
                                                         const float* __restrict__ quats_0, int ld0,
                                                         const double* __restrict__ sigma_b, const float* __restrict__ mask,
-                                                        double* __restrict__ out) {
+                                                        double* __restrict__ out, const double* __restrict__ table = nullptr,
+                                                        const double* __restrict__ bounds = nullptr, int num_omega = 0,
+                                                        const int32_t* __restrict__ sigma_idx = nullptr) {
+  // table != nullptr: so3.use_cached_score=True (so3_diffuser.py:389-396): the score norm is looked up in the precomputed
+  // [num_sigma, num_omega] table (row t_to_idx(t), column torch.bucketize(omega, discrete_omega[:-1])) instead of the series
   __shared__ double coef_s[1000];
-  {
+  if (!table) {
     const int bc = min(blockIdx.x * 8, M - 1) / N;
     const double sg = sigma_b[bc];
     const double h = 0.5 * sg * sg;
@@ -68,6 +72,21 @@ __global__ void __launch_bounds__(256) rot_score_kernel(int M, int N, const floa
   const float scale = (angle <= 1e-3f) ? (2.f + a2 / 12.f + 7.f * a2 * a2 / 2880.f) : angle / sinf(angle / 2.f + 1e-6f);
   const float v[3] = {scale * q[1], scale * q[2], scale * q[3]};
   const float omega = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) + 1e-6f;
+  if (table) {
+    if (lane < 3) {
+      // torch.bucketize(omega, bounds), right=False: number of boundaries strictly below omega (bounds has num_omega - 1 entries)
+      int lo_i = 0, hi_i = num_omega - 1;
+      const double om = (double)omega;
+      while (lo_i < hi_i) {
+        const int mid = (lo_i + hi_i) >> 1;
+        if (bounds[mid] < om) lo_i = mid + 1; else hi_i = mid;
+      }
+      const double nrm = table[(long long)sigma_idx[b] * num_omega + lo_i];
+      const double mk = mask ? (double)mask[m] : 1.0;
+      out[(long long)m * 3 + lane] = nrm * (double)v[lane] / (double)omega * mk;
+    }
+    return;
+  }
   const double sig = sigma_b[b];
   const double hs2 = 0.5 * sig * sig;
   const float lo = sinf(omega / 2.f);
@@ -187,6 +206,39 @@ FDPT_DEVINL void rotvec_to_quat_d(const double v[3], double q[4]) {
 //   sched: device row of FDPT_SCHED_COLS doubles.
 // last_step (t == min_t): rigids_out = rigids_pred (experiments/utils.py:372-374).
 // ------------------------------------------------------------------------------------------------
+// Counter-based RNG for the throughput mode of the sampler (SURVEY §8b `philox_seed`): Philox4x32-10 (Salmon et al., SC'11; the
+// generator behind curand / torch.cuda), keyed by the 64-bit seed, counter = (residue index lo, hi, timestep, draw index).  Parity
+// runs never use it: they consume the reference's legacy numpy stream drawn on the host.
+FDPT_DEVINL void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += W0; k1 += W1;
+  }
+}
+// two independent N(0,1) doubles from one Philox block (Box-Muller on two 53-bit uniforms in (0,1))
+FDPT_DEVINL void philox_normal2(unsigned long long seed, unsigned long long idx, uint32_t step, uint32_t draw, double& z0, double& z1) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), step, draw};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double u0 = ((double)((((unsigned long long)c[0]) << 21) ^ (c[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u1 = ((double)((((unsigned long long)c[2]) << 21) ^ (c[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double r = sqrt(-2.0 * log(u0));
+  double sn, cs;
+  sincospi(2.0 * u1, &sn, &cs);
+  z0 = r * cs;
+  z1 = r * sn;
+}
+// six normals of residue m at a timestep: z_rot[3], z_trans[3]
+FDPT_DEVINL void philox_normal6(unsigned long long seed, unsigned long long m, uint32_t step, double zr[3], double zt[3]) {
+  philox_normal2(seed, m, step, 0u, zr[0], zr[1]);
+  philox_normal2(seed, m, step, 1u, zr[2], zt[0]);
+  philox_normal2(seed, m, step, 2u, zt[1], zt[2]);
+}
+
 struct ReverseArgs {
   int N;
   const float* rigids_t;      // [B,N,7]
@@ -201,11 +253,18 @@ struct ReverseArgs {
   float* rigids_out;          // [B,N,7]
   StepRef noise_ref, sched_ref;  // optional device-resolved per-step slices of the noise block and the schedule table
   long long noise_half = 0;      // elements between the rot and the trans half of a step's noise block (indirect mode)
+  int use_philox = 0;            // 1: draw the normals on the device (z_rot / z_trans / noise_ref bases are ignored)
+  unsigned long long philox_seed = 0;
+  int philox_step = 0;           // timestep index when no device step counter is attached (noise_ref.step == nullptr)
 };
 
 __global__ void __launch_bounds__(256) reverse_kernel(ReverseArgs a) {
   const int b = blockIdx.x, N = a.N;
-  {
+  uint32_t pstep = (uint32_t)a.philox_step;
+  if (a.use_philox) {
+    if (a.noise_ref.step) pstep = (uint32_t)*a.noise_ref.step;
+    a.sched = step_resolve(a.sched, a.sched_ref);
+  } else {
     const double* zr = step_resolve(a.z_rot, a.noise_ref);  // base of this step's [2][B,N,3] noise block when indirect
     a.z_trans = a.noise_ref.base ? zr + a.noise_half : step_resolve(a.z_trans, a.noise_ref);
     a.z_rot = zr;
@@ -222,12 +281,15 @@ __global__ void __launch_bounds__(256) reverse_kernel(ReverseArgs a) {
     const double mk = (double)a.dmask[m];
     sm += mk;
     double xp[3];
+    double zr3[3], zt3[3];
+    if (a.use_philox) philox_normal6(a.philox_seed, (unsigned long long)m, pstep, zr3, zt3);
+    else { zt3[0] = a.z_trans[m * 3]; zt3[1] = a.z_trans[m * 3 + 1]; zt3[2] = a.z_trans[m * 3 + 2]; }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const float x32 = __fmul_rn(a.rigids_t[m * 7 + 4 + k], a.cs);  // float32 array * python float
       const double x = (double)x32;
       const double f = -0.5 * b_t * x;
-      const double perturb = ((f - b_t * (double)a.trans_score[m * 3 + k]) * dt + rn * a.z_trans[m * 3 + k]) * mk;
+      const double perturb = ((f - b_t * (double)a.trans_score[m * 3 + k]) * dt + rn * zt3[k]) * mk;
       xp[k] = x - perturb;
     }
     sx += xp[0];
@@ -263,6 +325,12 @@ __global__ void __launch_bounds__(256) reverse_kernel(ReverseArgs a) {
     const long long m = (long long)b * N + n;
     const double mk = (double)a.dmask[m];
     float outv[7];
+    double zr3[3], zt3[3];
+    if (a.use_philox) philox_normal6(a.philox_seed, (unsigned long long)m, pstep, zr3, zt3);
+    else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { zr3[k] = a.z_rot[m * 3 + k]; zt3[k] = a.z_trans[m * 3 + k]; }
+    }
     // ---- translation
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -271,7 +339,7 @@ __global__ void __launch_bounds__(256) reverse_kernel(ReverseArgs a) {
       if (a.diffuse_trans) {
         const double x = (double)__fmul_rn(xt, a.cs);
         const double f = -0.5 * b_t * x;
-        const double perturb = ((f - b_t * (double)a.trans_score[m * 3 + k]) * dt + rn * a.z_trans[m * 3 + k]) * mk;
+        const double perturb = ((f - b_t * (double)a.trans_score[m * 3 + k]) * dt + rn * zt3[k]) * mk;
         double xp = x - perturb;
         if (a.center) xp -= com[k];
         xp = xp / csd;
@@ -292,7 +360,7 @@ __global__ void __launch_bounds__(256) reverse_kernel(ReverseArgs a) {
     if (a.diffuse_rot) {
       double pv[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) pv[k] = (g2dt * a.rot_score[m * 3 + k] + gn * a.z_rot[m * 3 + k]) * mk;
+      for (int k = 0; k < 3; ++k) pv[k] = (g2dt * a.rot_score[m * 3 + k] + gn * zr3[k]) * mk;
       double qp[4];
       rotvec_to_quat_d(pv, qp);
       quat_mul(qt, qp, qn);  // right multiply: R_t * exp(perturb)
@@ -367,6 +435,125 @@ __global__ void backbone_kernel(int M, const float* __restrict__ rigids, const f
         v = R[r * 3] * p[0] + R[r * 3 + 1] * p[1] + R[r * 3 + 2] * p[2] + t[r];
       out[((long long)m * 5 + sl) * 3 + r] = v * mk;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x_T for B samples of one structure (SE3Diffuser.sample_ref se3_diffuser.py:455-529; SO3Diffuser.sample so3_diffuser.py:325-357:
+// unit(randn(n,3)) * omega with omega = np.interp(rand(n), cdf_row, discrete_omega); R3Diffuser.sample_stationary_distribution
+// r3_diffuser.py:294-331: N(0,1) on the diffused residues in scaled coordinates; mask blend with the imputed (ground-truth) frames;
+// _assemble_rigid: float32 rotation matrices, to_tensor_7: quaternion of that matrix).  float64 like the reference's numpy path.
+// ------------------------------------------------------------------------------------------------
+FDPT_DEVINL void quat_to_rotvec_d(const double qin[4], double v[3]) {  // scipy Rotation.as_rotvec
+  double q[4] = {qin[0], qin[1], qin[2], qin[3]};
+  if (q[0] < 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = -q[k];
+  }
+  const double n = sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double angle = 2.0 * atan2(n, q[0]);
+  const double a2 = angle * angle;
+  const double sc = angle <= 1e-3 ? 2.0 + a2 / 12.0 + 7.0 * a2 * a2 / 2880.0 : angle / sin(angle / 2.0);
+  v[0] = sc * q[1];
+  v[1] = sc * q[2];
+  v[2] = sc * q[3];
+}
+
+struct SampleRefArgs {
+  int N;
+  const float* impute;        // [N,7] or nullptr
+  const float* dmask;         // [N] or nullptr
+  const double* cdf;          // [num_omega]
+  const double* omega_grid;   // [num_omega]
+  int num_omega;
+  const double* draws;        // [B][7N]: randn [N,3] | rand [N] | normal [N,3] (by residue), or nullptr (Philox)
+  unsigned long long philox_seed;
+  int diffuse_rot, diffuse_trans;
+  float cs;
+  float* out;                 // [B,N,7]
+};
+
+__global__ void __launch_bounds__(128) sample_ref_kernel(SampleRefArgs a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, N = a.N;
+  if (n >= N) return;
+  const long long m = (long long)b * N + n;
+  double g[3], u, z[3];
+  if (a.draws) {
+    const double* d = a.draws + (long long)b * 7 * N;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      g[k] = d[n * 3 + k];
+      z[k] = d[4 * N + n * 3 + k];
+    }
+    u = d[3 * N + n];
+  } else {
+    double t0, t1;
+    philox_normal2(a.philox_seed, (unsigned long long)m, 0xFFFFFFFFu, 0u, g[0], g[1]);
+    philox_normal2(a.philox_seed, (unsigned long long)m, 0xFFFFFFFFu, 1u, g[2], z[0]);
+    philox_normal2(a.philox_seed, (unsigned long long)m, 0xFFFFFFFFu, 2u, z[1], z[2]);
+    uint32_t c[4] = {(uint32_t)m, (uint32_t)((unsigned long long)m >> 32), 0xFFFFFFFFu, 3u};
+    philox4x32_10(c, (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
+    u = (double)((((unsigned long long)c[0]) << 21) ^ (c[1] >> 11)) * (1.0 / 9007199254740992.0);  // [0, 1) like numpy.random.rand
+    (void)t0; (void)t1;
+  }
+  const double dm = a.dmask ? (double)a.dmask[n] : 1.0;
+  // imputed frame
+  double rot_imp[3] = {0, 0, 0};
+  float t_imp[3] = {0.f, 0.f, 0.f};
+  if (a.impute) {
+    float qf[4] = {a.impute[n * 7], a.impute[n * 7 + 1], a.impute[n * 7 + 2], a.impute[n * 7 + 3]};
+    float Rf[9];
+    quat_to_rot(qf, Rf);  // fp32 rotation matrix (Rigid.get_rots().get_rot_mats())
+    double Rd[9], qd[4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rd[k] = (double)Rf[k];
+    rot_to_quat_d(Rd, qd);
+    quat_to_rotvec_d(qd, rot_imp);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t_imp[k] = a.impute[n * 7 + 4 + k];
+  }
+  // rotation
+  double rv[3] = {rot_imp[0], rot_imp[1], rot_imp[2]};
+  if (a.diffuse_rot) {
+    const double gn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    // np.interp(u, cdf, omega)
+    double ang;
+    const int K = a.num_omega;
+    if (u <= a.cdf[0]) ang = a.omega_grid[0];
+    else if (u >= a.cdf[K - 1]) ang = a.omega_grid[K - 1];
+    else {
+      int lo = 0, hi = K - 1;  // invariant: cdf[lo] <= u < cdf[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a.cdf[mid] <= u) lo = mid; else hi = mid;
+      }
+      const double slope = (a.omega_grid[lo + 1] - a.omega_grid[lo]) / (a.cdf[lo + 1] - a.cdf[lo]);
+      ang = slope * (u - a.cdf[lo]) + a.omega_grid[lo];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double s = g[k] / gn * ang;
+      rv[k] = a.dmask ? dm * s + (1.0 - dm) * rot_imp[k] : s;
+    }
+  }
+  double qn[4], Rn[9], qo[4];
+  rotvec_to_quat_d(rv, qn);
+  quat_to_rot(qn, Rn);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rn[k] = (double)(float)Rn[k];  // torch.Tensor(rotmat): float32 storage
+  rot_to_quat_d(Rn, qo);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a.out[m * 7 + k] = (float)qo[k];
+  // translation
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float x = t_imp[k];
+    if (a.diffuse_trans) {
+      float xs = __fmul_rn(t_imp[k], a.cs);
+      if (dm != 0.0) xs = (float)z[k];
+      x = __fdiv_rn(xs, a.cs);
+    }
+    a.out[m * 7 + 4 + k] = x;
   }
 }
 

@@ -46,14 +46,64 @@ def _expand37(bb5: np.ndarray) -> np.ndarray:
     return out
 
 
+class _TrajReader:
+    """Streams fdpt_sample's trajectory slots to the host while later timesteps are still running: after every `chunk` steps the
+    finished slots are copied device -> pinned staging on a side stream and scattered into the caller-owned numpy arrays (the
+    backbone trajectories are expanded to the reference's [T,B,N,37,3] layout on the way; only 5 of the 37 atom slots are ever
+    non-zero).  The reference materialises the same arrays with np.stack at the end (experiments/utils.py:610-626)."""
+
+    def __init__(self, ctx, out: dict, T: int, chunk: int, keys: list[str]):
+        self.ctx, self.out, self.T, self.chunk, self.keys = ctx, out, T, chunk, keys
+        self.side = torch.cuda.Stream(device=ctx.device)
+        self.host = {}
+        for k in keys:
+            shp = tuple(out[k].shape)
+            if k in ("prot_traj", "rigid_0_traj"):
+                shp = shp[:-2] + (37, 3)
+            self.host[k] = np.empty(shp, np.float32)
+        self.stage = {k: torch.empty((min(chunk, T) + 1,) + tuple(out[k].shape[1:]), dtype=torch.float32).pin_memory() for k in keys}
+
+    def _copy(self, key: str, lo: int, hi: int):
+        """slots [lo, hi) of trajectory `key`"""
+        n = hi - lo
+        st = self.stage[key][:n]
+        with torch.cuda.stream(self.side):
+            st.copy_(self.out[key][lo:hi], non_blocking=True)
+        self.side.synchronize()
+        dst = self.host[key]
+        if key in ("prot_traj", "rigid_0_traj"):
+            dst[lo:hi, ..., :5, :] = st.numpy()
+            dst[lo:hi, ..., 5:, :] = 0.0
+        else:
+            dst[lo:hi] = st.numpy()
+
+    def run(self) -> dict[str, np.ndarray]:
+        T, c = self.T, self.chunk
+        for s0 in range(0, T, c):
+            s1 = min(s0 + c, T)
+            self.ctx.wait_step(s1 - 1)
+            lo, hi = T - s1, T - s0  # step s writes slot T-1-s (index 0 = final sample)
+            for k in self.keys:
+                if k == "rigid_traj":  # [T+1]: slot T is x_T (written before the loop), slots shift by none otherwise
+                    self._copy(k, lo, hi + (1 if s0 == 0 else 0))
+                else:
+                    self._copy(k, lo, hi)
+        return self.host
+
+
 def inference_fn(model: ScoreNetwork, diffuser, data_init: dict, num_t: int, min_t: float, center: bool = True,
                  aux_traj: bool = False, self_condition: bool = True, noise_scale: float = 1.0,
                  embed_self_conditioning: bool = True, inpainting: bool = False, input_aatype: bool = False,
-                 noise: np.ndarray | None = None) -> dict[str, np.ndarray]:
+                 noise: np.ndarray | None = None, rng: str = "numpy", philox_seed: int | None = None,
+                 readback_chunk: int = 25) -> dict[str, np.ndarray]:
+    """experiments/utils.py:511-626 with the same arguments and return dict.  Extra keyword arguments (not in the reference):
+    `noise` (pre-drawn [num_t-1, 2, B, N, 3] float64 normals), `rng` = "numpy" (default: the reference's legacy global numpy
+    stream, bit-identical draws) or "philox" (throughput mode: normals drawn on the device, seed `philox_seed` or one drawn from
+    numpy's global RNG), `readback_chunk` (timesteps per streamed trajectory read-back)."""
     if not isinstance(model, ScoreNetwork):
         raise TypeError("framedipt_b200.inference_fn drives framedipt_b200.ScoreNetwork (there is no eager fallback)")
-    if not embed_self_conditioning:
-        raise NotImplementedError("embed_self_conditioning=False is not supported by the CUDA path")
+    if rng not in ("numpy", "philox"):
+        raise ValueError(f"rng should be 'numpy' or 'philox', got {rng}")
     feats = dict(data_init)  # shallow: nothing is mutated
     if feats["rigids_t"].ndim == 2:
         feats = {k: (v[None] if torch.is_tensor(v) and v.ndim >= 1 and k != "t" else v) for k, v in feats.items()}
@@ -61,24 +111,37 @@ def inference_fn(model: ScoreNetwork, diffuser, data_init: dict, num_t: int, min
     if dev.type != "cuda":
         raise runtime.FdptError("inference_fn needs the features on a CUDA device (no CPU fallback)")
     ctx = model.context(dev)
-    pf = model.prepare(feats, dev)
+    # backbone residue types follow the CALL's flags (experiments/utils.py:549-555), the embedder's follow the model's
+    from .score_network import preprocess_aatype
+
+    aatype_bb = preprocess_aatype(feats.get("aatype"), torch.as_tensor(feats["fixed_mask"]), inpainting, input_aatype)
+    pf = model.prepare(feats, dev, aatype_bb=aatype_bb)
     B, N = pf.B, pf.N
     steps, sched, t_emb_tab = build_schedule(diffuser, num_t, min_t, noise_scale)
     n_rev = int((sched[:, 7] == 0).sum())
     if n_rev != num_t - 1 or sched[-1, 7] != 1.0:
         raise ValueError("unexpected schedule: exactly the last step must satisfy t <= min_t")
-    if noise is None:
-        noise = draw_noise(diffuser, n_rev, B, N)
-    noise_d = torch.as_tensor(np.ascontiguousarray(noise, np.float64)).to(dev) if n_rev > 0 else None
-    out = ctx.sample(pf, sched, t_emb_tab, noise_d, self_condition=self_condition, center=center,
-                     diffuse_rot=diffuser._diffuse_rot, diffuse_trans=diffuser._diffuse_trans, final_only=False)
+    noise_d = None
+    seed = 0
+    if noise is not None or rng == "numpy":
+        if noise is None:
+            noise = draw_noise(diffuser, n_rev, B, N)
+        noise_d = torch.as_tensor(np.ascontiguousarray(noise, np.float64)).to(dev) if n_rev > 0 else torch.zeros(1, 2, B, N, 3, dtype=torch.float64, device=dev)
+    else:
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) if philox_seed is None else int(philox_seed)
+    flags = (1 if (embed_self_conditioning and self_condition) else 0) | (0 if embed_self_conditioning else 2)
+    chunk = max(1, min(int(readback_chunk), num_t))
+    out = ctx.sample(pf, sched, t_emb_tab, noise_d, self_condition=flags, center=center, diffuse_rot=diffuser._diffuse_rot,
+                     diffuse_trans=diffuser._diffuse_trans, final_only=False, philox_seed=seed, progress_chunk=chunk)
+    keys = ["prot_traj"] + (["rigid_traj", "trans_traj", "rigid_0_traj"] if aux_traj else [])
+    host = _TrajReader(ctx, out, num_t, chunk, keys).run()
     torch.cuda.current_stream(dev).synchronize()
-    ret = {"prot_traj": _expand37(out["prot_traj"].cpu().numpy())}
+    ret = {"prot_traj": host["prot_traj"]}
     if aux_traj:
-        ret["rigid_traj"] = out["rigid_traj"].cpu().numpy()
-        ret["trans_traj"] = out["trans_traj"].cpu().numpy()
+        ret["rigid_traj"] = host["rigid_traj"]
+        ret["trans_traj"] = host["trans_traj"]
         ret["psi_pred"] = out["psi_pred"].cpu().numpy()[None]
-        ret["rigid_0_traj"] = _expand37(out["rigid_0_traj"].cpu().numpy())
+        ret["rigid_0_traj"] = host["rigid_0_traj"]
     return ret
 
 

@@ -34,6 +34,7 @@ class ModelDims:
     seq_tfmr_num_heads: int = 4
     seq_tfmr_num_layers: int = 2
     coordinate_scaling: float = 0.1
+    embed_self_conditioning: bool = True  # model.embed.embed_self_conditioning (score_network.py:95-96, 185)
 
     @property
     def concat_dim(self) -> int:
@@ -48,7 +49,7 @@ def param_specs(d: ModelDims = ModelDims(), with_aatype: bool = True):
     """Yields (key, shape, kind); kind in {w, relu, final, bias, bias_default, bias_final, ln_w, ln_b, head, unused}."""
     f1 = node_feat_dim(d, with_aatype)
     node_in = f1 + d.index_embed_size
-    edge_in = 2 * f1 + d.index_embed_size + d.num_bins
+    edge_in = 2 * f1 + d.index_embed_size + (d.num_bins if d.embed_self_conditioning else 0)
     out = []
 
     def lin(name, o, i, kind="w", bias="bias"):

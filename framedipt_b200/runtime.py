@@ -18,7 +18,7 @@ from .params import ModelDims, param_specs
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfdpt.so")
-SCHED_COLS = 8
+SCHED_COLS = 10  # FDPT_SCHED_COLS (include/fdpt.h)
 
 
 class FdptError(RuntimeError):
@@ -32,6 +32,7 @@ class _Config(C.Structure):
         ("index_embed_size", C.c_int32), ("num_bins", C.c_int32), ("min_bin", C.c_float), ("max_bin", C.c_float),
         ("seq_tfmr_num_heads", C.c_int32), ("seq_tfmr_num_layers", C.c_int32), ("coordinate_scaling", C.c_float),
         ("with_aatype", C.c_int32), ("r3_min_b", C.c_double), ("r3_max_b", C.c_double),
+        ("r3_coordinate_scaling", C.c_float), ("embed_self_conditioning", C.c_int32),
     ]
 
 
@@ -40,7 +41,8 @@ class _Feats(C.Structure):
         ("rigids_t", C.c_void_p), ("sc_ca_t", C.c_void_p), ("res_mask", C.c_void_p), ("fixed_mask", C.c_void_p),
         ("seq_idx", C.c_void_p), ("aatype", C.c_void_p), ("gt_psi", C.c_void_p), ("idx_emb", C.c_void_p),
         ("rel_emb", C.c_void_p), ("rel_min", C.c_int32), ("rel_count", C.c_int32), ("t_emb", C.c_void_p),
-        ("t_emb_eps", C.c_void_p), ("t32", C.c_void_p), ("sigma", C.c_void_p),
+        ("t_emb_eps", C.c_void_p), ("t32", C.c_void_p), ("sigma", C.c_void_p), ("sigma_idx", C.c_void_p),
+        ("aatype_bb", C.c_void_p), ("aatype_bb_given", C.c_int32),
     ]
 
 
@@ -87,7 +89,14 @@ def lib() -> C.CDLL:
         L.fdpt_trans_score.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_void_p]
         L.fdpt_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_Feats), C.c_int, C.POINTER(C.c_double), C.c_void_p,
-                                  C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_Traj), C.c_void_p]
+                                  C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_Traj), C.c_void_p]
+        L.fdpt_set_progress_chunk.argtypes = [C.c_void_p, C.c_int]
+        L.fdpt_wait_step.argtypes = [C.c_void_p, C.c_int]
+        L.fdpt_set_score_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.fdpt_rot_score_idx.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        L.fdpt_sample_ref.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.fdpt_seq_tfmr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
         L.fdpt_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_void_p]
         L.fdpt_tc_linear.argtypes = L.fdpt_linear.argtypes
@@ -142,8 +151,11 @@ def _dev(x: Any, device, dtype) -> torch.Tensor:
 class PreparedFeats:
     """Device-resident, dtype-normalised view of a reference feature dict."""
 
-    def __init__(self, feats: dict, device, dims: ModelDims, with_aatype: bool, aatype_pre: torch.Tensor | None):
+    def __init__(self, feats: dict, device, dims: ModelDims, with_aatype: bool, aatype_pre: torch.Tensor | None,
+                 aatype_bb: torch.Tensor | None | bool = False):
         f32, i32 = torch.float32, torch.int32
+        if with_aatype and aatype_pre is None:
+            raise ValueError("When inpainting is True, aatype should be given, got None.")
         self.B, self.N = feats["res_mask"].shape
         self.rigids_t = _dev(feats["rigids_t"], device, f32)
         self.sc_ca_t = _dev(feats["sc_ca_t"], device, f32)
@@ -152,8 +164,9 @@ class PreparedFeats:
         seq = torch.as_tensor(feats["seq_idx"]).to("cpu", torch.int64)
         self.seq_idx = seq.to(device=device, dtype=i32).contiguous()
         self.aatype = _dev(aatype_pre, device, i32) if with_aatype else None
-        if with_aatype and aatype_pre is None:
-            raise ValueError("When inpainting is True, aatype should be given, got None.")
+        # residue types of the trajectory's backbone atoms (inference_fn's own flags, experiments/utils.py:549-555); False = not given
+        self.aatype_bb_given = aatype_bb is not False
+        self.aatype_bb = _dev(aatype_bb, device, i32) if (self.aatype_bb_given and aatype_bb is not None) else None
         self.gt_psi = _dev(torch.as_tensor(feats["torsion_angles_sin_cos"])[..., 2, :], device, f32)
         self.idx_emb = index_embedding(seq, dims.index_embed_size).to(device).contiguous()
         lo = int((seq.min(-1).values - seq.max(-1).values).min())
@@ -161,26 +174,29 @@ class PreparedFeats:
         self.rel_min, self.rel_count = lo, hi - lo + 1
         self.rel_emb = index_embedding(torch.arange(lo, hi + 1), dims.index_embed_size).to(device).contiguous()
         self.t_emb_eps = timestep_embedding(torch.tensor([1e-5]), dims.index_embed_size)[0].to(device).contiguous()
-        self.t_emb = self.t32 = self.sigma = None
+        self.t_emb = self.t32 = self.sigma = self.sigma_idx = None
 
     def struct(self) -> _Feats:
         return _Feats(_ptr(self.rigids_t), _ptr(self.sc_ca_t), _ptr(self.res_mask), _ptr(self.fixed_mask), _ptr(self.seq_idx),
                       _ptr(self.aatype), _ptr(self.gt_psi), _ptr(self.idx_emb), _ptr(self.rel_emb), self.rel_min, self.rel_count,
-                      _ptr(self.t_emb), _ptr(self.t_emb_eps), _ptr(self.t32), _ptr(self.sigma))
+                      _ptr(self.t_emb), _ptr(self.t_emb_eps), _ptr(self.t32), _ptr(self.sigma), _ptr(self.sigma_idx),
+                      _ptr(self.aatype_bb), int(self.aatype_bb_given))
 
 
 class Context:
     """One libfdpt context (one GPU)."""
 
     def __init__(self, dims: ModelDims = ModelDims(), with_aatype: bool = True, device: int | torch.device = 0,
-                 r3_min_b: float = 0.1, r3_max_b: float = 20.0):
+                 r3_min_b: float = 0.1, r3_max_b: float = 20.0, r3_coordinate_scaling: float = 0.1):
         if not torch.cuda.is_available():
             raise FdptError("framedipt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
         self.dims, self.with_aatype = dims, with_aatype
         cfg = _Config(dims.c_s, dims.c_z, dims.c_hidden, dims.c_skip, dims.no_heads, dims.no_qk_points, dims.no_v_points,
                       dims.num_blocks, dims.index_embed_size, dims.num_bins, dims.min_bin, dims.max_bin, dims.seq_tfmr_num_heads,
-                      dims.seq_tfmr_num_layers, dims.coordinate_scaling, int(with_aatype), r3_min_b, r3_max_b)
+                      dims.seq_tfmr_num_layers, dims.coordinate_scaling, int(with_aatype), r3_min_b, r3_max_b,
+                      r3_coordinate_scaling, int(dims.embed_self_conditioning))
+        self.r3_key = (float(r3_min_b), float(r3_max_b), float(r3_coordinate_scaling))
         self._h = C.c_void_p()
         rc = lib().fdpt_create(C.byref(cfg), self.device.index, C.byref(self._h))
         if rc != 0:
@@ -247,7 +263,18 @@ class Context:
         self._ck(lib().fdpt_reserve(self._h, B, N))
 
     # ---- forward
-    def forward(self, pf: PreparedFeats, t: torch.Tensor, sigma: np.ndarray, want_backbone: bool = True) -> dict[str, torch.Tensor]:
+    def set_score_table(self, score_norms: np.ndarray | None, omega_bounds: np.ndarray | None = None):
+        """Installs (or with None removes) the cached IGSO(3) score-norm table of so3.use_cached_score=True."""
+        if score_norms is None:
+            self._ck(lib().fdpt_set_score_table(self._h, None, 0, 0, None))
+            return
+        tab = np.ascontiguousarray(score_norms, np.float64)
+        bnd = np.ascontiguousarray(omega_bounds, np.float64)
+        assert tab.ndim == 2 and bnd.shape == (tab.shape[1] - 1,)
+        self._ck(lib().fdpt_set_score_table(self._h, tab.ctypes.data, tab.shape[0], tab.shape[1], bnd.ctypes.data))
+
+    def forward(self, pf: PreparedFeats, t: torch.Tensor, sigma: np.ndarray, want_backbone: bool = True,
+                sigma_idx: np.ndarray | None = None) -> dict[str, torch.Tensor]:
         B, N, dev = pf.B, pf.N, self.device
         t32 = torch.as_tensor(t).to("cpu", torch.float32).reshape(-1)
         if t32.numel() != B:
@@ -255,6 +282,7 @@ class Context:
         pf.t_emb = timestep_embedding(t32, self.dims.index_embed_size).to(dev).contiguous()
         pf.t32 = t32.to(dev)
         pf.sigma = torch.as_tensor(np.asarray(sigma, np.float64).reshape(B)).to(dev)
+        pf.sigma_idx = None if sigma_idx is None else torch.as_tensor(np.asarray(sigma_idx).reshape(B).astype(np.int32)).to(dev)
         out = {
             "rigids": torch.empty(B, N, 7, device=dev), "rot_score": torch.empty(B, N, 3, device=dev, dtype=torch.float64),
             "trans_score": torch.empty(B, N, 3, device=dev), "psi": torch.empty(B, N, 2, device=dev),
@@ -269,9 +297,12 @@ class Context:
 
     # ---- sampling loop
     def sample(self, pf: PreparedFeats, sched: np.ndarray, t_emb_tab: torch.Tensor, noise: torch.Tensor | None, self_condition=True,
-               center=True, diffuse_rot=True, diffuse_trans=True, final_only=False, out: dict | None = None) -> dict[str, torch.Tensor]:
+               center=True, diffuse_rot=True, diffuse_trans=True, final_only=False, out: dict | None = None,
+               philox_seed: int = 0, progress_chunk: int = 0) -> dict[str, torch.Tensor]:
         """Enqueue the whole reverse-diffusion loop (fdpt_sample).  `out` may hold pre-allocated trajectory buffers from
-        `alloc_traj` (a fresh cudaMalloc inside torch.empty can take tens of milliseconds; callers that time the loop allocate first)."""
+        `alloc_traj` (a fresh cudaMalloc inside torch.empty can take tens of milliseconds; callers that time the loop allocate first).
+        noise=None: throughput mode, normals drawn on the device (Philox, `philox_seed`).  progress_chunk > 0: an event is recorded
+        every that many steps so that `wait_step` lets the caller read finished trajectory slots while later steps run."""
         import time as _time
 
         _t0 = _time.perf_counter()
@@ -294,13 +325,18 @@ class Context:
                 tuple(noise.shape[1:]) == (2, B, N, 3), (noise.shape, noise.dtype)
         fs = pf.struct()
         _t2 = _time.perf_counter()
+        self._ck(lib().fdpt_set_progress_chunk(self._h, int(progress_chunk)))
         self._ck(lib().fdpt_sample(self._h, B, N, C.byref(fs), T, sched.ctypes.data_as(C.POINTER(C.c_double)), _ptr(t_emb_tab),
-                                   _ptr(noise), int(self_condition), int(center), int(diffuse_rot), int(diffuse_trans), C.byref(tr),
-                                   self.stream))
+                                   _ptr(noise), int(philox_seed) & 0xFFFFFFFFFFFFFFFF, int(self_condition), int(center), int(diffuse_rot),
+                                   int(diffuse_trans), C.byref(tr), self.stream))
         _t3 = _time.perf_counter()
         self.last_sample_host_ms = {"alloc": (_t1 - _t0) * 1e3, "prep": (_t2 - _t1) * 1e3, "c_call": (_t3 - _t2) * 1e3}
         out["_keepalive"] = (t_emb_tab, noise, sched)
         return out
+
+    def wait_step(self, step: int):
+        """Blocks until timestep `step` of the most recent `sample(..., progress_chunk=c)` call has completed on the device."""
+        self._ck(lib().fdpt_wait_step(self._h, int(step)))
 
     @staticmethod
     def alloc_shapes(B, N, T, final_only=False) -> dict:
@@ -392,6 +428,30 @@ class Context:
         self._ck(lib().fdpt_backbone(self._h, B, N, _ptr(rigids), _ptr(psi), _ptr(aatype), _ptr(out), self.stream))
         return out
 
+    def rot_score_idx(self, quats_t, quats_0, sigma_idx, mask=None):
+        """Rotation score by look-up in the installed score table (so3.use_cached_score=True)."""
+        B, N, _ = quats_t.shape
+        out = torch.empty(B, N, 3, device=self.device, dtype=torch.float64)
+        self._ck(lib().fdpt_rot_score_idx(self._h, B, N, _ptr(quats_t), _ptr(quats_0), _ptr(sigma_idx), _ptr(mask), _ptr(out), self.stream))
+        return out
+
+    def sample_ref(self, B, N, impute, diffuse_mask, cdf, omega_grid, draws=None, philox_seed=0, diffuse_rot=True, diffuse_trans=True):
+        """x_T of B samples of one structure on the device (fdpt_sample_ref).  impute [N,7] / diffuse_mask [N] float32 or None;
+        cdf / omega_grid float64 [num_omega]; draws float64 [B,7N] (parity mode) or None (Philox)."""
+        out = torch.empty(B, N, 7, device=self.device)
+        self._ck(lib().fdpt_sample_ref(self._h, B, N, _ptr(impute), _ptr(diffuse_mask), _ptr(cdf), _ptr(omega_grid), int(cdf.numel()),
+                                       _ptr(draws), int(philox_seed) & 0xFFFFFFFFFFFFFFFF, int(diffuse_rot), int(diffuse_trans), _ptr(out),
+                                       self.stream))
+        return out
+
+    def seq_tfmr(self, blk, node, node0, mask):
+        """(encoder output [B,N,320], node + post_tfmr(...) [B,N,256]) of block `blk`'s sequence-transformer sub-block."""
+        B, N, _ = node.shape
+        tf = torch.empty(B, N, self.dims.c_s + self.dims.c_skip, device=self.device)
+        out = torch.empty(B, N, self.dims.c_s, device=self.device)
+        self._ck(lib().fdpt_seq_tfmr(self._h, blk, B, N, _ptr(node), _ptr(node0), _ptr(mask), _ptr(tf), _ptr(out), self.stream))
+        return tf, out
+
     def rot_score(self, quats_t, quats_0, sigma, mask=None):
         B, N, _ = quats_t.shape
         out = torch.empty(B, N, 3, device=self.device, dtype=torch.float64)
@@ -408,13 +468,19 @@ class Context:
 # --------------------------------------------------------------------------------------------------------
 # device-executed SE3Diffuser methods (bound from se3_diffuser.py)
 # --------------------------------------------------------------------------------------------------------
-_default_ctx: dict[int, Context] = {}
+_default_ctx: dict[tuple, Context] = {}
 
 
-def default_context(device: int = 0) -> Context:
-    if device not in _default_ctx:
-        _default_ctx[device] = Context(device=device)
-    return _default_ctx[device]
+def default_context(device: int | None = None, diffuser=None) -> Context:
+    """Context for the standalone diffuser calls (reverse / calc_*_score), built from the diffuser's OWN r3 configuration
+    (min_b, max_b, coordinate_scaling: r3_diffuser.py:15-35) on the current CUDA device."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    r3 = getattr(diffuser, "_r3_diffuser", None)
+    key = (device, float(r3.min_b) if r3 else 0.1, float(r3.max_b) if r3 else 20.0, float(r3.coordinate_scaling) if r3 else 0.1)
+    if key not in _default_ctx:
+        _default_ctx[key] = Context(device=device, r3_min_b=key[1], r3_max_b=key[2], r3_coordinate_scaling=key[3])
+    return _default_ctx[key]
 
 
 def reverse_host_api(diffuser, rigid_t, rot_score, trans_score, t, dt, diffuse_mask, center, noise_scale):
@@ -422,7 +488,7 @@ def reverse_host_api(diffuser, rigid_t, rot_score, trans_score, t, dt, diffuse_m
     global legacy numpy RNG in the reference's order (rot, then trans)."""
     from .rigid import Rigid
 
-    ctx = default_context()
+    ctx = default_context(diffuser=diffuser)
     dev = ctx.device
     r7 = rigid_t.to_tensor_7().to(dev, torch.float32)
     squeeze = r7.dim() == 2
@@ -443,17 +509,27 @@ def reverse_host_api(diffuser, rigid_t, rot_score, trans_score, t, dt, diffuse_m
 
 
 def rot_score_host_api(diffuser, rots_t, rots_0, t):
-    ctx = default_context()
+    ctx = default_context(diffuser=diffuser)
     dev = ctx.device
     qt = rots_t.get_quats().to(dev, torch.float32).contiguous()
     q0 = rots_0.get_quats().to(dev, torch.float32).contiguous()
     t_np = torch.as_tensor(t).detach().cpu().numpy()
-    sigma = torch.as_tensor(np.asarray(diffuser._so3_diffuser.grid_sigma(t_np), np.float64).reshape(-1)).to(dev)
+    so3 = diffuser._so3_diffuser
+    if so3.use_cached_score:
+        if getattr(ctx, "_table_of", None) is not so3:
+            ctx.set_score_table(so3.score_norms, so3.discrete_omega[:-1])
+            ctx._table_of = so3
+        idx = torch.as_tensor(np.asarray(so3.t_to_idx(t_np)).reshape(-1).astype(np.int32)).to(dev)
+        return ctx.rot_score_idx(qt, q0, idx)
+    if getattr(ctx, "_table_of", None) is not None:
+        ctx.set_score_table(None)
+        ctx._table_of = None
+    sigma = torch.as_tensor(np.asarray(so3.grid_sigma(t_np), np.float64).reshape(-1)).to(dev)
     return ctx.rot_score(qt, q0, sigma)
 
 
 def trans_score_host_api(diffuser, trans_t, trans_0, t, scale):
-    ctx = default_context()
+    ctx = default_context(diffuser=diffuser)
     dev = ctx.device
     xt = torch.as_tensor(trans_t).to(dev, torch.float32).contiguous()
     x0 = torch.as_tensor(trans_0).to(dev, torch.float32).contiguous()

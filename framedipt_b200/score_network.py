@@ -34,13 +34,12 @@ def dims_from_conf(model_conf) -> ModelDims:
     if model_conf is None:
         return ModelDims()
     ipa, emb = model_conf.ipa, model_conf.embed
-    if not bool(_get(emb, "embed_self_conditioning", True)):
-        raise NotImplementedError("embed_self_conditioning=False is not supported by the CUDA path")
     return ModelDims(c_s=int(ipa.c_s), c_z=int(ipa.c_z), c_hidden=int(ipa.c_hidden), c_skip=int(ipa.c_skip), no_heads=int(ipa.no_heads),
                      no_qk_points=int(ipa.no_qk_points), no_v_points=int(ipa.no_v_points), num_blocks=int(ipa.num_blocks),
                      index_embed_size=int(emb.index_embed_size), num_bins=int(emb.num_bins), min_bin=float(emb.min_bin),
                      max_bin=float(emb.max_bin), seq_tfmr_num_heads=int(ipa.seq_tfmr_num_heads),
-                     seq_tfmr_num_layers=int(ipa.seq_tfmr_num_layers), coordinate_scaling=float(ipa.coordinate_scaling))
+                     seq_tfmr_num_layers=int(ipa.seq_tfmr_num_layers), coordinate_scaling=float(ipa.coordinate_scaling),
+                     embed_self_conditioning=bool(_get(emb, "embed_self_conditioning", True)))
 
 
 def _register(root: nn.Module, key: str, value: torch.Tensor):
@@ -82,17 +81,23 @@ class ScoreNetwork(nn.Module):
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if self._ctx is None or self._ctx.device.index != idx:
             r3 = self.diffuser._r3_diffuser if self.diffuser is not None else None
-            self._ctx = runtime.Context(self._dims, self._with_aatype, idx, r3.min_b if r3 else 0.1, r3.max_b if r3 else 20.0)
+            self._ctx = runtime.Context(self._dims, self._with_aatype, idx, r3.min_b if r3 else 0.1, r3.max_b if r3 else 20.0,
+                                        r3.coordinate_scaling if r3 else 0.1)
+            so3 = self.diffuser._so3_diffuser if self.diffuser is not None else None
+            if so3 is not None and so3.use_cached_score:  # so3_diffuser.py:389-396: table look-up instead of the series
+                self._ctx.set_score_table(so3.score_norms, so3.discrete_omega[:-1])
             self._dirty = True
         if self._dirty:
             self._ctx.load_state_dict(dict(self.state_dict()), strict=False)
             self._dirty = False
         return self._ctx
 
-    def prepare(self, input_feats: dict, device: torch.device) -> runtime.PreparedFeats:
+    def prepare(self, input_feats: dict, device: torch.device, aatype_bb=False) -> runtime.PreparedFeats:
+        """aatype_bb: residue types for the trajectory's backbone atoms when they are decided by the caller's own flags
+        (inference_fn, experiments/utils.py:549-555); False = follow the model's."""
         fixed_mask = torch.as_tensor(input_feats["fixed_mask"]).type(torch.float32)
         aatype = preprocess_aatype(input_feats.get("aatype"), fixed_mask, self.inpainting, self._input_aatype)
-        return runtime.PreparedFeats(input_feats, device, self._dims, self._with_aatype, aatype)
+        return runtime.PreparedFeats(input_feats, device, self._dims, self._with_aatype, aatype, aatype_bb)
 
     @torch.no_grad()
     def forward(self, input_feats: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
@@ -102,8 +107,9 @@ class ScoreNetwork(nn.Module):
         ctx = self.context(dev)
         pf = self.prepare(input_feats, dev)
         t = input_feats["t"]
-        sigma = self.diffuser._so3_diffuser.grid_sigma(torch.as_tensor(t).detach().to("cpu", torch.float32).numpy())
-        out = ctx.forward(pf, t, np.asarray(sigma, np.float64).reshape(-1))
+        t_np = torch.as_tensor(t).detach().to("cpu", torch.float32).numpy()
+        so3 = self.diffuser._so3_diffuser
+        out = ctx.forward(pf, t, np.asarray(so3.grid_sigma(t_np), np.float64).reshape(-1), sigma_idx=np.asarray(so3.t_to_idx(t_np)).reshape(-1))
         bb = out.pop("atom37_bb")
         B, N = pf.B, pf.N
         atom37 = torch.zeros(B, N, 37, 3, device=dev)

@@ -39,10 +39,53 @@ class SO3Schedule:
         self.num_sigma = int(_get(so3_conf, "num_sigma", 1000))
         self.num_omega = int(_get(so3_conf, "num_omega", 1000))
         self.use_cached_score = bool(_get(so3_conf, "use_cached_score", False))
-        if self.use_cached_score:
-            raise NotImplementedError("use_cached_score=True (table lookup score) is out of scope; the series is evaluated on device")
+        self.cache_dir = _get(so3_conf, "cache_dir", None)
         self.discrete_omega = np.linspace(0, np.pi, self.num_omega + 1)[1:]
         self._cdf_rows: dict[int, np.ndarray] = {}
+        self._score_norms: np.ndarray | None = None
+
+    def _cache_path(self) -> str | None:
+        """Directory of the reference's IGSO(3) cache for this configuration (so3_diffuser.py:207-233): the same files are read
+        and written, so a cache built by either implementation serves both."""
+        import os
+
+        if not self.cache_dir:
+            return None
+        rp = lambda x: str(x).replace(".", "_")  # noqa: E731
+        return os.path.join(self.cache_dir, f"eps_{self.num_sigma}_omega_{self.num_omega}_min_sigma_{rp(self.min_sigma)}_"
+                                            f"max_sigma_{rp(self.max_sigma)}_schedule_{self.schedule}")
+
+    @property
+    def score_norms(self) -> np.ndarray:
+        """The reference's `_score_norms` table [num_sigma, num_omega] (so3_diffuser.py:264-273: `score(exp_vals[i], discrete_omega,
+        sigma_i)` per grid sigma), needed only for so3.use_cached_score=True.  Loaded from the reference's cache file when present,
+        else computed once (float64 numpy, 1000-term series; about a minute) and saved there."""
+        import os
+
+        if self._score_norms is None:
+            d = self._cache_path()
+            f = os.path.join(d, "score_norms.npy") if d else None
+            if f and os.path.exists(f):
+                self._score_norms = np.load(f)
+            else:
+                lv = np.arange(1000)[None]
+                om = self.discrete_omega[:, None]
+                hi, dhi = np.sin(om * (lv + 0.5)), (lv + 0.5) * np.cos(om * (lv + 0.5))
+                lo, dlo = np.sin(om / 2), 0.5 * np.cos(om / 2)
+                base = (lo * dhi - hi * dlo) / lo ** 2
+                ser = hi / lo
+                rows = []
+                for sig in self.discrete_sigma:
+                    c = (2 * lv + 1) * np.exp(-lv * (lv + 1) * sig ** 2 / 2)
+                    rows.append((c * base).sum(-1) / ((c * ser).sum(-1) + 1e-4))
+                self._score_norms = np.asarray(rows)
+                if f:
+                    try:
+                        os.makedirs(d, exist_ok=True)
+                        np.save(f, self._score_norms)
+                    except OSError:
+                        pass
+        return self._score_norms
 
     def sigma(self, t):
         t = np.asarray(t)
@@ -282,8 +325,9 @@ class SE3Diffuser:
         b_t = float(r3.b_t(t))
         t32f = np.float32(t)
         mb = np.float32(t32f * np.float32(r3.min_b) + np.float32(0.5) * (t32f * t32f) * np.float32(r3.max_b - r3.min_b))
+        idx = float(so3.t_to_idx(np.array(np.float32(t))))  # row of the cached score table (use_cached_score)
         return np.array([t32, sigma, g * g * dt, g * np.sqrt(dt) * noise_scale, b_t, dt, np.sqrt(b_t) * np.sqrt(dt) * noise_scale,
-                         float(mb)], dtype=np.float64)
+                         float(mb), idx, 0.0], dtype=np.float64)
 
     # ---- x_T ------------------------------------------------------------------------------------
     def sample_ref(self, n_samples: int, chain_index=None, impute: Rigid | None = None, diffuse_mask=None,

@@ -44,6 +44,9 @@ typedef struct {
   float coordinate_scaling;
   int32_t with_aatype;      /* 1: node features carry the 21-way aatype one-hot (inpainting / input_aatype) */
   double r3_min_b, r3_max_b;
+  float r3_coordinate_scaling;     /* diffuser.r3.coordinate_scaling: used by the translation score and the reverse step
+                                      (r3_diffuser.py:30, 344-440); `coordinate_scaling` above is model.ipa's (ipa_pytorch.py:472) */
+  int32_t embed_self_conditioning; /* model.embed.embed_self_conditioning (score_network.py:95-96, 185): 0 = no distogram features */
 } fdpt_config;
 
 /* Per-step schedule row (doubles), filled on the host with the reference's numpy expressions
@@ -57,7 +60,8 @@ enum {
   FDPT_SCHED_DT = 5,         /* dt */
   FDPT_SCHED_R3_NOISE = 6,   /* sqrt(b_t) * sqrt(dt) * noise_scale */
   FDPT_SCHED_IS_LAST = 7,    /* 1.0 when !(t > min_t): take the x0 prediction instead of a reverse step */
-  FDPT_SCHED_COLS = 8
+  FDPT_SCHED_SIGMA_IDX = 8,  /* t_to_idx(t): row of the cached score table (so3.use_cached_score=True, so3_diffuser.py:389-396) */
+  FDPT_SCHED_COLS = 10
 };
 
 /* Input features of one forward = the feature dict of experiments/sampler.py:69-111, 267-354. */
@@ -76,6 +80,11 @@ typedef struct {
   const float* t_emb_eps;    /* [E]     get_timestep_embedding(1e-5) */
   const float* t32;          /* [B]     feats["t"] */
   const double* sigma;       /* [B]     discrete_sigma[t_to_idx(t)] */
+  const int32_t* sigma_idx;  /* [B]     t_to_idx(t); only read when a cached score table is installed (fdpt_set_score_table) */
+  const int32_t* aatype_bb;  /* [B,N]   residue types used for the backbone atoms of fdpt_sample's trajectories =
+                                        preprocess_aatype(aatype, fixed_mask, inpainting, input_aatype) of the inference_fn CALL
+                                        (experiments/utils.py:549-555), which may differ from the model's flags; NULL = ALA frames */
+  int32_t aatype_bb_given;   /* 0: fall back to `aatype` (when the model takes aatype) */
 } fdpt_feats;
 
 /* Outputs of one forward = ScoreNetwork.forward's dict (score_network.py:262-275). Any pointer may be NULL. */
@@ -142,11 +151,41 @@ int fdpt_trans_score(fdpt_ctx* ctx, int B, int N, const float* trans_t, const fl
  * at the first t, then num_t x (forward -> reverse | take x0 at the last step -> backbone).
  *   sched      host [num_t, FDPT_SCHED_COLS] doubles, step 0 = t=1.0 ... last = min_t
  *   t_emb_tab  device [num_t, E] timestep embeddings per step; feats->t_emb / t32 / sigma are ignored
- *   noise      device float64 [num_t-1, 2, B, N, 3] standard normals (rot then trans), reference draw order
+ *   noise      device float64 [num_t-1, 2, B, N, 3] standard normals (rot then trans), reference draw order (parity mode: the
+ *              reference's legacy numpy stream, drawn on the host); NULL = throughput mode: the reverse step draws its normals on
+ *              the device from a counter-based Philox4x32-10 generator keyed by `philox_seed` (counter = step, residue, component)
+ *   self_condition  bit 0: run the self-conditioning pre-pass at the first t (experiments/utils.py:571-578);
+ *                   bit 1: never update sc_ca_t inside the loop (inference_fn(embed_self_conditioning=False), utils.py:356-358)
  *   feats->rigids_t is read as x_T and not modified; feats->sc_ca_t is the initial self-conditioning (zeros). */
 int fdpt_sample(fdpt_ctx* ctx, int B, int N, const fdpt_feats* feats, int num_t, const double* sched,
-                const float* t_emb_tab, const double* noise, int self_condition, int center,
+                const float* t_emb_tab, const double* noise, uint64_t philox_seed, int self_condition, int center,
                 int diffuse_rot, int diffuse_trans, const fdpt_traj* out, void* stream);
+
+/* Streaming read-back of fdpt_sample's trajectories: with a chunk size c > 0 the next fdpt_sample calls record an event after every
+ * c timesteps (and after the last one); fdpt_wait_step(ctx, s) blocks the calling host thread until timestep s (0-based) of the most
+ * recent fdpt_sample call has completed on the device, so the caller can copy finished trajectory slots to the host while later steps
+ * are still running (inference_fn's [T,B,N,37,3] arrays, experiments/utils.py:610-626).  c = 0 turns the events off. */
+int fdpt_set_progress_chunk(fdpt_ctx* ctx, int chunk_steps);
+int fdpt_wait_step(fdpt_ctx* ctx, int step);
+
+/* replaces: SO3Diffuser.torch_score's table look-up when so3.use_cached_score=True (so3_diffuser.py:389-396): installs the
+ * [num_sigma, num_omega] float64 score-norm table (host pointer, copied) and the omega grid boundaries discrete_omega[:-1]
+ * ([num_omega-1] float64, host); afterwards fdpt_forward / fdpt_sample / fdpt_rot_score_idx look the score norm up
+ * (row = sigma_idx, column = torch.bucketize(omega, boundaries)) instead of evaluating the series.  NULL table = back to the series. */
+int fdpt_set_score_table(fdpt_ctx* ctx, const double* score_norms, int num_sigma, int num_omega, const double* omega_bounds);
+int fdpt_rot_score_idx(fdpt_ctx* ctx, int B, int N, const float* quats_t, const float* quats_0, const int32_t* sigma_idx,
+                       const float* mask, double* out, void* stream);
+
+/* replaces: SE3Diffuser.sample_ref for B samples of ONE structure (se3_diffuser.py:455-529; SO3Diffuser.sample so3_diffuser.py:325-357,
+ * R3Diffuser.sample_stationary_distribution r3_diffuser.py:294-331), SURVEY §8(f3): x_T built on the device instead of B host calls.
+ *   impute [N,7] ground-truth frames (quat + trans, Angstrom) or NULL (de novo: identity / zeros), diffuse_mask [N] float or NULL (all diffused)
+ *   cdf / omega_grid: device float64 [num_omega]: the row _cdf[t_to_idx(1.0)] and discrete_omega (inverse-CDF by np.interp's rule)
+ *   draws: device float64 [B][7N] = per sample randn [N,3], rand [N], normal [N,3] in the reference's draw order (parity mode; the
+ *          k-th diffused residue takes row k of the last block), or NULL = Philox keyed by philox_seed (throughput mode)
+ *   out [B,N,7]. */
+int fdpt_sample_ref(fdpt_ctx* ctx, int B, int N, const float* impute, const float* diffuse_mask, const double* cdf,
+                    const double* omega_grid, int num_omega, const double* draws, uint64_t philox_seed, int diffuse_rot,
+                    int diffuse_trans, float* rigids_out, void* stream);
 
 /* replaces: framedipt.protein.protein.to_pdb (protein.py:165-279) as called by analysis.utils.write_prot_to_pdb (utils.py:78-156)
  * for one model of backbone atoms.  HOST function (no GPU work): atom37_bb [n_res,5,3] host floats (atom37 slots 0..4 = N,CA,C,CB,O;
@@ -216,6 +255,11 @@ int fdpt_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* 
 /* EdgeTransition.forward (ipa_pytorch.py:84-102) of block `blk`, followed by *edge_mask: z_out may alias z_in */
 int fdpt_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* z_in,
                          const float* mask, float* z_out, void* stream);
+/* The sequence-transformer sub-block of IpaScore.forward (ipa_pytorch.py:533-539) of block `blk`:
+ *   x = cat[node, skip_embed(node0)] -> TransformerEncoder (2 post-norm layers) -> tfmr_out [B,N,320];
+ *   node_out = node + post_tfmr(tfmr_out) [B,N,256].  Either output may be NULL. */
+int fdpt_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const float* node0, const float* mask,
+                  float* tfmr_out, float* node_out, void* stream);
 /* Embedder.forward (score_network.py:129-197) incl. the mask multiply of score_network.py:252-253 */
 int fdpt_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out, float* edge_out, void* stream);
 
