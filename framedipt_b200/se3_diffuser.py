@@ -68,17 +68,7 @@ class SO3Schedule:
             if f and os.path.exists(f):
                 self._score_norms = np.load(f)
             else:
-                lv = np.arange(1000)[None]
-                om = self.discrete_omega[:, None]
-                hi, dhi = np.sin(om * (lv + 0.5)), (lv + 0.5) * np.cos(om * (lv + 0.5))
-                lo, dlo = np.sin(om / 2), 0.5 * np.cos(om / 2)
-                base = (lo * dhi - hi * dlo) / lo ** 2
-                ser = hi / lo
-                rows = []
-                for sig in self.discrete_sigma:
-                    c = (2 * lv + 1) * np.exp(-lv * (lv + 1) * sig ** 2 / 2)
-                    rows.append((c * base).sum(-1) / ((c * ser).sum(-1) + 1e-4))
-                self._score_norms = np.asarray(rows)
+                self._score_norms = np.asarray([self.score_norm_row(i) for i in range(self.num_sigma)])
                 if f:
                     try:
                         os.makedirs(d, exist_ok=True)
@@ -86,6 +76,20 @@ class SO3Schedule:
                     except OSError:
                         pass
         return self._score_norms
+
+    def score_norm_row(self, idx: int) -> np.ndarray:
+        """Row `idx` of `_score_norms`: d/d omega log f(omega; sigma_idx) on the omega grid (so3_diffuser.py:122-191, 264-273)."""
+        if not hasattr(self, "_series_basis"):
+            lv = np.arange(1000)[None]
+            om = self.discrete_omega[:, None]
+            hi, dhi = np.sin(om * (lv + 0.5)), (lv + 0.5) * np.cos(om * (lv + 0.5))
+            lo, dlo = np.sin(om / 2), 0.5 * np.cos(om / 2)
+            self._series_basis = ((lo * dhi - hi * dlo) / lo ** 2, hi / lo)
+        base, ser = self._series_basis
+        lv = np.arange(1000)[None]
+        sig = self.discrete_sigma[idx]
+        c = (2 * lv + 1) * np.exp(-lv * (lv + 1) * sig ** 2 / 2)
+        return (c * base).sum(-1) / ((c * ser).sum(-1) + 1e-4)
 
     def sigma(self, t):
         t = np.asarray(t)

@@ -133,3 +133,101 @@ def test_confidence_score_transition_densities_match_reference(golden_dir):
     a = rotmats_to_rigid(g["c1_a_rot"], g["c1_a_trans"])
     far = rotmats_to_rigid(g["c1_b_rot"], g["c1_b_trans"] + 5.0 * mask[:, None].astype(np.float32))
     assert d.log_prob_forward(far, a, 0.3, 0.1, mask) < float(g["c1_scalars"][3])
+
+
+def test_backbone_constants_match_reference_tables(golden_dir):
+    """framedipt_b200/backbone_constants.py against the tables derived from the reference's residue_constants
+    (oracle/make_constants.py -> tests/golden/backbone_tables.npz), all 20 residue types."""
+    from framedipt_b200 import backbone_constants as bc
+
+    g = np.load(os.path.join(golden_dir, "backbone_tables.npz"))
+    assert bc.IDEAL_BB_POS.shape == (20, 5, 3) and np.array_equal(np.asarray(bc.IDEAL_BB_POS, np.float32), g["ideal"])
+    assert bc.PSI_DEFAULT_FRAME.shape == (20, 4, 4) and np.array_equal(np.asarray(bc.PSI_DEFAULT_FRAME, np.float32), g["psi_frame"])
+    assert np.array_equal(np.asarray(bc.BB_ATOM_MASK, np.float32), g["mask"])
+    assert g["mask"][7, 4] == 0 and g["mask"].sum() == 99  # GLY is the only type without CB
+
+
+def test_score_norm_rows_match_reference_table(golden_dir):
+    """Host builder of the cached IGSO(3) score-norm table (so3.use_cached_score=True) vs rows of the reference's `_score_norms`."""
+    from framedipt_b200 import SE3Diffuser
+    from framedipt_b200.config import default_conf
+
+    g = np.load(os.path.join(golden_dir, "config_variants.npz"))
+    so3 = SE3Diffuser(default_conf().diffuser)._so3_diffuser
+    for r, row in zip(g["cached_table_rows"], g["cached_table"]):
+        assert np.abs(so3.score_norm_row(int(r)) - row).max() <= 1e-9 * np.abs(row).max()
+
+
+def test_sigma_index_is_the_same_for_float32_and_float64_t():
+    """the reference pins numpy 1.22 (value-based casting: sigma(t) of a float32 t stays float32), the fixtures were
+    produced under numpy 2 (float64).  On the schedules actually used the grid index does not depend on that."""
+    from framedipt_b200 import SE3Diffuser
+    from framedipt_b200.config import default_conf
+
+    so3 = SE3Diffuser(default_conf().diffuser)._so3_diffuser
+    for num_t in (50, 100, 200, 500):
+        t = np.linspace(0.01, 1.0, num_t)
+        i64 = so3.t_to_idx(t)
+        i32 = so3.t_to_idx(t.astype(np.float32).astype(np.float64))
+        sig32 = np.log(t.astype(np.float32) * np.float32(np.exp(1.5)) + (np.float32(1) - t.astype(np.float32)) * np.float32(np.exp(0.1)))
+        i32b = np.digitize(sig32.astype(np.float64), so3.discrete_sigma) - 1  # all-float32 evaluation (numpy 1.22 semantics)
+        assert np.array_equal(i64, i32), num_t
+        assert (i64 != i32b).sum() <= 1, (num_t, np.nonzero(i64 != i32b))  # only an exact bin edge (t = 1.0) may flip
+
+
+def test_samplers_keep_the_reference_item_contract(golden_dir):
+    """(key, sample_i, feats) items with batch dim 1 (experiments/sampler.py:121-135, 267-354); the de-novo sampler consumes the
+    legacy numpy stream exactly like the reference (fixture written by the unmodified sample_ref)."""
+    from framedipt_b200 import SE3Diffuser, synthetic
+    from framedipt_b200.config import default_conf, to_attr
+    from framedipt_b200.sampler import SyntheticConditionalSampler, UnconditionalSampler
+
+    g = np.load(os.path.join(golden_dir, "sample_ref.npz"))
+    diffuser = SE3Diffuser(default_conf().diffuser)
+    # the fixture's stream: seed, one inpainting sample (N=64), then two de-novo samples (N=32)
+    cs = SyntheticConditionalSampler(to_attr({"workloads": ["cfg1_monomer64"], "samples": 2, "seed": 0}), diffuser, "cpu")
+    assert len(cs) == 2
+    np.random.seed(123)
+    name, si, f = cs[0]
+    assert (name, si) == ("cfg1_monomer64", 0)
+    for key, shp in {"aatype": (1, 64), "seq_idx": (1, 64), "chain_idx": (1, 64), "res_mask": (1, 64), "fixed_mask": (1, 64),
+                     "torsion_angles_sin_cos": (1, 64, 7, 2), "rigids_0": (1, 64, 7), "sc_ca_t": (1, 64, 3), "rigids_t": (1, 64, 7), "t": (1,)}.items():
+        assert tuple(f[key].shape) == shp, key
+    assert np.abs(f["rigids_t"][0, :, 4:].numpy() - g["inpaint_rigids_t"][0, :, 4:]).max() < 1e-5
+    ds = UnconditionalSampler(to_attr({"min_length": 32, "max_length": 40, "length_step": 8, "samples_per_length": 2}), diffuser, "cpu")
+    assert len(ds) == 4 and list(ds.all_sampling_lengths) == [32, 32, 40, 40]
+    items = [ds[0], ds[1]]
+    for k, (n, i, f) in enumerate(items):
+        assert (n, i) == (32, k)
+        assert f["rigids_t"].shape == (1, 32, 7) and f["res_mask"].shape == (1, 32) and f["torsion_angles_sin_cos"].shape == (1, 32, 7, 2)
+        assert torch.equal(f["seq_idx"][0], torch.arange(1, 33))
+        assert np.abs(f["rigids_t"][0, :, 4:].numpy() - g["denovo_rigids_t"][k, :, 4:]).max() < 1e-5
+    assert len(list(iter(cs))) == 2  # iterable Dataset protocol used by `for ... in self.sampler`
+
+
+def test_pad_feats_matches_reference(golden_dir):
+    """pad_feats / pad_rigid (framedipt/data/utils.py:311-339): the padded mixed-length batch of the fixture was built by the
+    reference's own functions from the same two structures."""
+    from framedipt_b200 import SE3Diffuser, synthetic
+    from framedipt_b200.config import default_conf
+    from framedipt_b200.sampler import pad_feats
+
+    g = np.load(os.path.join(golden_dir, "config_variants.npz"))
+    diffuser = SE3Diffuser(default_conf().diffuser)
+    np.random.seed(123)
+    fa = synthetic.make_features(synthetic.Workload("mixA", 1, (12, 8), ((3, 8),), 6), diffuser, seed=41)
+    fb = synthetic.make_features(synthetic.Workload("mixB", 1, (31,), ((10, 19),), 6), diffuser, seed=42)
+    pa = pad_feats({k: v[0] for k, v in fa.items()}, 31, use_torch=True)
+    pb = pad_feats({k: v[0] for k, v in fb.items()}, 31, use_torch=True)
+    for k in pa:
+        if k == "t":
+            continue
+        ours = torch.stack([pa[k], pb[k]]).numpy()
+        ref = g[f"mixed_in_{k}"]
+        assert ours.shape == ref.shape, k
+        if k == "rigids_t":
+            assert np.abs(ours[..., 4:] - ref[..., 4:]).max() < 1e-5 and rot_angle_between(ours[..., :4], ref[..., :4]).max() < 1e-5
+        else:
+            assert np.array_equal(ours, ref), k
+    with pytest.raises(ValueError):
+        pad_feats({"res_mask": torch.ones(40)}, 31, use_torch=True)
