@@ -33,6 +33,9 @@ FDPT_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
 }
 FDPT_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 FDPT_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// all state spaces: orders this thread's generic-proxy stores to GLOBAL memory (an operand image it has just written) before later
+// async-proxy reads of them (a bulk copy issued after a barrier by another thread of the CTA)
+FDPT_DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 FDPT_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

