@@ -26,6 +26,7 @@
 #include "gemm_tc.cuh"
 #include "lin_tc.cuh"
 #include "node_chain.cuh"
+#include "gemm_img.cuh"
 #include "backbone_tables.inc"
 
 using namespace fdpt;
@@ -73,6 +74,8 @@ struct Workspace {
   float *tors_u;
   // pair side
   float* S;  // [B,H,N,ldS] attention logits / probabilities (IPA and sequence transformer)
+  uint8_t *qimg = nullptr, *kimg = nullptr, *vimg = nullptr, *pimg = nullptr;  // IPA operand images (gemm_img.cuh): Q', K', V' [B*H][JB][5][32 KB]; P [B*H][JB][2JB][32 KB]
+  size_t qkv_img_bytes = 0, p_img_bytes = 0;
   __half *z, *n_img;               // z: fp16 tile images [B][N][JB][32 KB]; n_img: [B][JB][32 KB]
   __half *f_img, *rel_tab;         // edge embedder: f_j k-block images [B][JB][16 KB]; fp16 relative-offset embedding table
   int JB;
@@ -120,6 +123,7 @@ struct fdpt_ctx {
   int use_graph = 1;
   int64_t stat_captures = 0;      // per-timestep graphs captured so far
   int64_t stat_sample_host_us = 0; // host time the last fdpt_sample call spent enqueueing
+  int ipa_img = 1;    // IPA attention GEMMs from operand images (gemm_img.cuh); 0 = fp32 operands split on the fly (gemm_tc.cuh; A/B switch)
   int use_chain = 0;  // node-side layer chains in one persistent kernel per chain (node_chain.cuh); 0 = one launch per layer (A/B switch)
   int et_pair = 0;  // 1: EdgeTransition on CTA pairs (et_fused2.cuh, experimental: slower); 0: single-CTA kernel (et_fused.cuh)
   cudaStream_t own_stream = nullptr;   // the legacy default stream cannot be captured: fdpt_sample then runs on this stream,
@@ -375,6 +379,10 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.z = carve<__half>(p, M * JB * 16384); w.n_img = carve<__half>(p, (size_t)B * JB * 16384);
     w.f_img = carve<__half>(p, (size_t)B * JB * 8192); w.rel_tab = carve<__half>(p, (size_t)R * EMB);
     w.S = carve<float>(p, M * NH * (size_t)((N + 3) & ~3));
+    w.qkv_img_bytes = (size_t)B * NH * JB * IPA_IMG_KB * tc::LT_STAGE_BYTES;
+    w.p_img_bytes = (size_t)B * NH * JB * 2 * JB * tc::LT_STAGE_BYTES;
+    w.qimg = carve<uint8_t>(p, w.qkv_img_bytes); w.kimg = carve<uint8_t>(p, w.qkv_img_bytes); w.vimg = carve<uint8_t>(p, w.qkv_img_bytes);
+    w.pimg = carve<uint8_t>(p, w.p_img_bytes);
     w.pred_rigids = carve<float>(p, M * 7); w.trans_score = carve<float>(p, M * 3); w.psi = carve<float>(p, M * 2);
     w.rig_cur = carve<float>(p, M * 7); w.rig_next = carve<float>(p, M * 7); w.sc_ca = carve<float>(p, M * 3);
     w.t_emb_b = carve<float>(p, (size_t)B * EMB); w.t32_b = carve<float>(p, B); w.bb_tmp = carve<float>(p, M * 15);
@@ -388,7 +396,8 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
   }
   w.capB = B; w.capN = N; w.JB = (N + 127) / 128; w.ldS = (N + 3) & ~3;
   CK(cudaMemset(w.z, 0, sizeof(__half) * M * w.JB * 16384));  // padded rows (j >= N) of the tile images stay zero
-  CK(cudaMemset(w.imgF, 0, 4 * w.img_bytes));                  // rows >= M of the last m-tile of the chained operand images stay zero
+  CK(cudaMemset(w.imgF, 0, 4 * w.img_bytes));
+  CK(cudaMemset(w.qimg, 0, 3 * w.qkv_img_bytes + w.p_img_bytes));  // padding rows / columns of the IPA operand images stay zero                  // rows >= M of the last m-tile of the chained operand images stay zero
   return FDPT_OK;
 }
 
@@ -606,6 +615,39 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
   // q | q_pts, k | k_pts, v | v_pts of every head in one GEMM, then the frames applied in place
   RET(lin(s, C_S, p.Wcat, C_S, p.bcat, w.proj, PROJ_W, M, PROJ_W, C_S, 0, nullptr, 0, nullptr, 0, s_img, nullptr));
   std::unique_ptr<ProfScope> pattn(new ProfScope(ctx, FDPT_PROF_IPA_ATTN, st));  // every kernel that implements the attention itself: prep .. opt
+  const bool img = ctx->ipa_img && ctx->gemm_tc;
+  auto launch_img_gemm = [&](const tc::GemmImgArgs& g) -> int {
+    const long long tiles = (long long)g.m_tiles * g.n_tiles * g.batch;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<long long>(ctx->num_sms, tiles));
+    cfg.blockDim = dim3(tc::GI_THREADS);
+    cfg.dynamicSmemBytes = tc::gemm_img_smem_bytes();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tc::g_use_pdl;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_img_kernel, g);
+    ctx->launches++;
+    if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "gemm_img launch: %s", cudaGetErrorString(e));
+    return FDPT_OK;
+  };
+  if (img) {
+    // Q', K', V' as operand images (frames applied, s_qk and gamma folded into Q'), then S[b,h] = Q'_h K'_h^T + kbias on gemm_img
+    IpaImgArgs ia;
+    ia.M = (int)M; ia.N = N; ia.JB = w.JB; ia.proj = w.proj; ia.quats = quats; ia.trans = trans; ia.head_w = p.head_w; ia.mask = mask;
+    ia.kbias = w.kn; ia.Qimg = w.qimg; ia.Kimg = w.kimg; ia.Vimg = w.vimg;
+    ipa_prep_img_kernel<<<(unsigned)M, 256, 0, st>>>(ia);
+    LAUNCH_CHECK();
+    tc::GemmImgArgs g;
+    memset(&g, 0, sizeof(g));
+    const long long per_bh = (long long)w.JB * IPA_IMG_KB * tc::LT_STAGE_BYTES;
+    g.A = w.qimg; g.sA = per_bh; g.nkbA = IPA_IMG_KB; g.B = w.kimg; g.sB = per_bh; g.nkbB = IPA_IMG_KB; g.b_mn = 0; g.nkb = IPA_IMG_KB;
+    g.M = N; g.N = N; g.m_tiles = w.JB; g.n_tiles = w.JB; g.batch = B * NH; g.batch2 = 1;
+    g.bias = w.kn; g.sBias = N; g.C = w.S; g.ldc = w.ldS; g.sC1 = (long long)N * w.ldS; g.sC2 = 0;
+    RET(launch_img_gemm(g));
+  } else {
   ipa_prep_kernel<<<(unsigned)M, 256, 0, st>>>((int)M, w.proj, quats, trans, p.head_w, mask, N, w.kn);
   LAUNCH_CHECK();
   {  // S[b,h] = s_qk * [q | g q_pts] . [k | k_pts]^T
@@ -618,17 +660,26 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     CK(gemm_dispatch(ctx, g, true, B * NH, st));
     ctx->launches++;
   }
+  }
   {
     const IpaSmemPlan plan = ipa_core_plan(N, ctx->max_smem_optin, ctx->max_smem_sm);
     if (plan.rz < 1) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs more shared memory than available in ipa_core", N);
     IpaCoreArgs a;
     a.B = B; a.N = N; a.JB = w.JB; a.ldS = w.ldS; a.S = w.S; a.z = z; a.Wb_img = p.imgWb; a.bb = p.bb;
-    a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat; a.rz = plan.rz; a.tmem_cols = plan.tmem_cols; a.rows = (int)M; a.mn_swap = ctx->mn_swap; a.dbg = (ctx->dbg_flags & 4) ? ctx->et_dbg : nullptr;
+    a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat; a.rz = plan.rz; a.tmem_cols = plan.tmem_cols; a.rows = (int)M; a.Pg = img ? w.pimg : nullptr; a.mn_swap = ctx->mn_swap; a.dbg = (ctx->dbg_flags & 4) ? ctx->et_dbg : nullptr;
     ProfScope pc(ctx, FDPT_PROF_IPA_CORE, st);
     ipa_core_kernel<<<(unsigned)std::min<long long>((long long)ctx->num_sms * plan.ctas_per_sm, M), 192, plan.bytes, st>>>(a);
     LAUNCH_CHECK();
   }
-  {  // [o | o_pt (global frame)][b,:,h,:] = A_h [V_h | v_pts_h]  -> cat'[:, h*292 : (h+1)*292]
+  if (img) {  // [o | o_pt (global frame)][b,:,h,:] = P_h V'_h  -> cat'[:, h*292 : (h+1)*292]   (V' rows = j: MN-major B)
+    tc::GemmImgArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = w.pimg; g.sA = (long long)w.JB * 2 * w.JB * tc::LT_STAGE_BYTES; g.nkbA = 2 * w.JB;
+    g.B = w.vimg; g.sB = (long long)w.JB * IPA_IMG_KB * tc::LT_STAGE_BYTES; g.nkbB = IPA_IMG_KB; g.b_mn = 1; g.nkb = (N + 63) / 64;
+    g.M = N; g.N = V_W; g.m_tiles = w.JB; g.n_tiles = (V_W + 127) / 128; g.batch = B * NH; g.batch2 = NH;
+    g.bias = nullptr; g.C = w.cat; g.ldc = CAT; g.sC1 = (long long)N * CAT; g.sC2 = V_W;
+    RET(launch_img_gemm(g));
+  } else {  // [o | o_pt (global frame)][b,:,h,:] = A_h [V_h | v_pts_h]  -> cat'[:, h*292 : (h+1)*292]
     GemmArgs g;
     g.A = w.S; g.lda = w.ldS; g.sA1 = (long long)NH * N * w.ldS; g.sA2 = (long long)N * w.ldS;
     g.B = w.proj + PROJ_V; g.ldb = PROJ_W; g.sB1 = (long long)N * PROJ_W; g.sB2 = V_W;
@@ -1013,6 +1064,7 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaFuncSetAttribute(tc::lin_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_img_smem_bytes());
   cudaFuncSetAttribute(tc::node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::node_chain_smem_bytes());
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
   float lower[NBINS];
@@ -1662,6 +1714,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
     case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; tc::g_use_pdl = (value & 16) ? 0 : 1; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
     case FDPT_OPT_ET_PAIR: ctx->et_pair = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
+    case FDPT_OPT_IPA_IMG: ctx->ipa_img = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_CHAIN: ctx->use_chain = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {

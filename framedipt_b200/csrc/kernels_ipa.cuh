@@ -23,6 +23,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include "lin_tc.cuh"
 #include "tc_common.cuh"
 
 namespace fdpt {
@@ -88,6 +89,100 @@ __global__ void __launch_bounds__(256) ipa_prep_kernel(int M, float* __restrict_
   slot[2 * np + p] = gz;
 }
 
+// ---- operand-image form of the prep step (gemm_img.cuh) ---------------------------------------------------------------------
+// Reads the fused projection row of residue m and writes, per head, the three operands of the attention GEMMs as fp16 hi | lo operand
+// images [b, h][128-row tile][5 k-blocks of 64 columns][hi 16 KB | lo 16 KB][128 rows][128 B swizzled]:
+//   Q' = [s_qk q (256) | gamma (R q_pts + t) (24) | 0 (40)]      K' = [k (256) | R k_pts + t (24) | 0]      V' = [v (256) | R v_pts + t (36) | 0]
+// (points planar x | y | z like the projection) and kbias[b, h, j] = -gamma/2 |k_pts_j|^2 + 1e5 (m_j - 1).  Padding rows / columns are
+// never written: the image buffers are zeroed once when the workspace is reserved.
+struct IpaImgArgs {
+  int M, N, JB;
+  const float* proj; const float* quats; const float* trans; const float* head_w; const float* mask;
+  float* kbias;
+  uint8_t* Qimg; uint8_t* Kimg; uint8_t* Vimg;
+};
+constexpr int IPA_IMG_KB = 5;  // 320 columns per head and operand
+
+FDPT_DEVINL void ipa_img_store8(uint8_t* img, int JB, int bh, int i, int c, const float x[8]) {
+  uint4 hi, lo;
+  tc::split8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), hi, lo);
+  uint8_t* d = img + (((size_t)bh * JB + (i >> 7)) * IPA_IMG_KB + (c >> 3)) * tc::LT_STAGE_BYTES + tc::sw128_chunk_off(i & 127, c & 7);
+  *reinterpret_cast<uint4*>(d) = hi;
+  *reinterpret_cast<uint4*>(d + 16384) = lo;
+}
+
+__global__ void __launch_bounds__(256) ipa_prep_img_kernel(IpaImgArgs a) {
+  const int m = blockIdx.x, tid = threadIdx.x;
+  __shared__ float R[9], t[3];
+  if (tid == 0) {
+    float q[4] = {a.quats[m * 4], a.quats[m * 4 + 1], a.quats[m * 4 + 2], a.quats[m * 4 + 3]};
+    quat_to_rot(q, R);
+    t[0] = a.trans[m * 3];
+    t[1] = a.trans[m * 3 + 1];
+    t[2] = a.trans[m * 3 + 2];
+  }
+  __syncthreads();
+  const int b = m / a.N, i = m - b * a.N;
+  const float* row = a.proj + (long long)m * PROJ_W;
+  const float s_qk = sqrtf(1.0f / (3.f * C_HID));
+  // scalar channels: 3 operands x 8 heads x 32 chunks of 8
+  for (int idx = tid; idx < 3 * NH * 32; idx += 256) {
+    const int kind = idx / (NH * 32), h = (idx >> 5) & (NH - 1), c = idx & 31;
+    const float* src = row + (kind == 0 ? PROJ_Q + h * QK_W : kind == 1 ? PROJ_K + h * QK_W : PROJ_V + h * V_W) + 8 * c;
+    const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+    float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    if (kind == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] *= s_qk;
+    }
+    ipa_img_store8(kind == 0 ? a.Qimg : kind == 1 ? a.Kimg : a.Vimg, a.JB, b * NH + h, i, c, x);
+  }
+  // points: one thread per (operand, head)
+  if (tid < 3 * NH) {
+    const int kind = tid / NH, h = tid % NH;
+    const float gamma = log1pf(expf(a.head_w[h])) * sqrtf(1.0f / (3.f * (PQ * 9.0f / 2.f)));  // softplus(w_h) * sqrt(1/108)
+    if (kind < 2) {
+      const float* slot = row + (kind == 0 ? PROJ_Q : PROJ_K) + h * QK_W + C_HID;
+      float gx[PQ], gy[PQ], gz[PQ];
+      float d2 = 0.f;
+#pragma unroll
+      for (int p = 0; p < PQ; ++p) {
+        const float x = slot[p], y = slot[PQ + p], z = slot[2 * PQ + p];
+        gx[p] = R[0] * x + R[1] * y + R[2] * z + t[0];
+        gy[p] = R[3] * x + R[4] * y + R[5] * z + t[1];
+        gz[p] = R[6] * x + R[7] * y + R[8] * z + t[2];
+        d2 += gx[p] * gx[p] + gy[p] * gy[p] + gz[p] * gz[p];
+      }
+      if (kind == 0) {
+#pragma unroll
+        for (int p = 0; p < PQ; ++p) {
+          gx[p] *= gamma; gy[p] *= gamma; gz[p] *= gamma;
+        }
+      } else {
+        a.kbias[((long long)b * NH + h) * a.N + i] = -0.5f * gamma * d2 + 1e5f * (a.mask[m] - 1.f);
+      }
+      uint8_t* img = kind == 0 ? a.Qimg : a.Kimg;
+      ipa_img_store8(img, a.JB, b * NH + h, i, 32, gx);
+      ipa_img_store8(img, a.JB, b * NH + h, i, 33, gy);
+      ipa_img_store8(img, a.JB, b * NH + h, i, 34, gz);
+    } else {
+      const float* slot = row + PROJ_V + h * V_W + C_HID;
+      float g[40];
+#pragma unroll
+      for (int p = 0; p < PV; ++p) {
+        const float x = slot[p], y = slot[PV + p], z = slot[2 * PV + p];
+        g[p] = R[0] * x + R[1] * y + R[2] * z + t[0];
+        g[PV + p] = R[3] * x + R[4] * y + R[5] * z + t[1];
+        g[2 * PV + p] = R[6] * x + R[7] * y + R[8] * z + t[2];
+      }
+#pragma unroll
+      for (int p = 3 * PV; p < 40; ++p) g[p] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) ipa_img_store8(a.Vimg, a.JB, b * NH + h, i, 32 + c, g + 8 * c);
+    }
+  }
+}
+
 // o_pt: global-frame sums -> local frame R_i^T (p - t_i) in place + norms (ipa_pytorch.py:302-316)
 __global__ void __launch_bounds__(96) ipa_opt_kernel(int M, float* __restrict__ cat, const float* __restrict__ quats,
                                                      const float* __restrict__ trans) {
@@ -131,6 +226,8 @@ struct IpaCoreArgs {
   float* cat;            // [B*N, CAT] (cat' order)
   int rz, tmem_cols;     // z ring slots; TMEM columns to allocate (two D1 buffers + D2)
   int rows;              // B*N
+  uint8_t* Pg;           // optional: probabilities as fp16 hi | lo operand images [b, h][i-tile][2 JB k-blocks][32 KB] for the A.V GEMM
+                         // (gemm_img.cuh); S then keeps the logits (the fp32 probabilities are not written)
   int mn_swap;           // bring-up knob: swap LBO / SBO of the MN-major A descriptor
   long long* dbg;        // optional clock64 timeline of CTA 0 ([row iteration][48] stamps), or nullptr
 };
@@ -400,10 +497,20 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
           if (q < JB) {
             const float4 p = make_float4(v[q].x * inv, v[q].y * inv, v[q].z * inv, v[q].w * inv);
             const int j = 4 * (lane + 32 * q);
-            if (j < a.ldS) *reinterpret_cast<float4*>(Sh + j) = p;  // columns in [N, ldS) are zero
+            if (!a.Pg && j < a.ldS) *reinterpret_cast<float4*>(Sh + j) = p;  // columns in [N, ldS) are zero
             const __half2 h01 = __floats2half2_rn(p.x, p.y), h23 = __floats2half2_rn(p.z, p.w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const __half2 l01 = __floats2half2_rn(p.x - f01.x, p.y - f01.y), l23 = __floats2half2_rn(p.z - f23.x, p.w - f23.y);
+            if (a.Pg) {
+              // operand image of the A.V GEMM: row i of tile i >> 7, k-block j >> 6; the low part carries the 2^11 scale of gemm_img's
+              // split (its epilogue divides the cross accumulator by 2048); columns j >= N hold exact zeros (exp(-inf))
+              const __half2 s01 = __floats2half2_rn((p.x - f01.x) * 2048.f, (p.y - f01.y) * 2048.f);
+              const __half2 s23 = __floats2half2_rn((p.z - f23.x) * 2048.f, (p.w - f23.y) * 2048.f);
+              uint8_t* gd = a.Pg + ((((size_t)b * NH + h) * JB + (i >> 7)) * (2 * JB) + (j >> 6)) * (size_t)32768 + (i & 127) * 128 +
+                            (((((j & 63) >> 3)) ^ (i & 7)) << 4) + (j & 7) * 2;
+              *reinterpret_cast<uint2*>(gd) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+              *reinterpret_cast<uint2*>(gd + 16384) = make_uint2(*reinterpret_cast<const uint32_t*>(&s01), *reinterpret_cast<const uint32_t*>(&s23));
+            }
             const int jj = j & 127;
             uint8_t* dst = Pimg + q * IPA_PIMG_TILE + (jj >> 6) * 2048 + h * 128 + ((((jj & 63) >> 3) ^ (h & 7)) << 4) + (jj & 7) * 2;
             *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));

@@ -97,7 +97,7 @@ for sample_length, sample_i, sample_feats in ds:
     path = write_prot_to_pdb(so["prot_traj"][0], %(out)r + f"/sample_{sample_i}.pdb", no_indexing=True)
     out.append({"len": int(sample_length), "i": int(sample_i), "prot": list(so["prot_traj"].shape), "rigid": list(so["rigid_traj"].shape),
                 "finite": bool(np.isfinite(so["prot_traj"]).all()), "trans_ok": bool(np.allclose(rig.get_trans().numpy(), so["prot_traj"][0][:, 1], atol=1e-4)),
-                "pdb": path})
+                "pdb": str(path)})
 print("SEQ " + json.dumps(out))
 ''' % {"shim": os.path.join(ROOT, "shim"), "root": ROOT, "ckpt": str(tmp_path / "denovo.pth"), "out": str(tmp_path)}
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=""), cwd=str(tmp_path), timeout=900)
