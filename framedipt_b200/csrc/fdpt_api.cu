@@ -54,6 +54,9 @@ struct BlockParams {
   // IPA (kernels_ipa.cuh): fused projection weight [6816,256] / bias with per-head contiguous rows, linear_out.weight with columns
   // in cat' order, fp16 hi|lo operand image of linear_b.weight
   float *Wcat = nullptr, *bcat = nullptr, *Wout_perm = nullptr;
+  // projection in operand-image column order (lin_tc.cuh IpaProjEpi): 24 blocks of 320 rows = [operand q|k|v][head][256 scalar | points | 0],
+  // q's scalar rows pre-multiplied by sqrt(1/(3 C))
+  float *Wimgproj = nullptr, *bimgproj = nullptr;
   __half* imgWb = nullptr;
 };
 
@@ -336,6 +339,26 @@ int pack_ipa_params(fdpt_ctx* ctx, BlockParams& p) {
           const __half v = n < 8 ? hi : __float2half_rn(wv - __half2float(hi));
           img[(size_t)kb * 1024 + n * 64 + ((c ^ (n & 7)) << 3) + e] = v;
         }
+  {
+    constexpr int BLK = 320, NPROJ = 3 * NH * BLK;
+    std::vector<float> W2((size_t)NPROJ * C_S, 0.f), b2(NPROJ, 0.f);
+    const float s_qk = sqrtf(1.0f / (3.f * C_HID));
+    for (int kind = 0; kind < 3; ++kind)
+      for (int h = 0; h < NH; ++h) {
+        const int src0 = kind == 0 ? PROJ_Q + h * QK_W : (kind == 1 ? PROJ_K + h * QK_W : PROJ_V + h * V_W);
+        const int width = kind == 2 ? V_W : QK_W;
+        for (int c = 0; c < width; ++c) {
+          const float sc = (kind == 0 && c < C_HID) ? s_qk : 1.f;
+          const size_t dst = (size_t)((kind * NH + h) * BLK + c);
+          for (int k = 0; k < C_S; ++k) W2[dst * C_S + k] = Wcat[(size_t)(src0 + c) * C_S + k] * sc;
+          b2[dst] = bcat[src0 + c] * sc;
+        }
+      }
+    if (!p.Wimgproj) CK(cudaMalloc(&p.Wimgproj, W2.size() * sizeof(float)));
+    if (!p.bimgproj) CK(cudaMalloc(&p.bimgproj, b2.size() * sizeof(float)));
+    CK(cudaMemcpy(p.Wimgproj, W2.data(), W2.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p.bimgproj, b2.data(), b2.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if (!p.Wcat) CK(cudaMalloc(&p.Wcat, Wcat.size() * sizeof(float)));
   if (!p.bcat) CK(cudaMalloc(&p.bcat, bcat.size() * sizeof(float)));
   if (!p.Wout_perm) CK(cudaMalloc(&p.Wout_perm, Wop.size() * sizeof(float)));
@@ -408,7 +431,7 @@ struct Lin {
   // y[M,N] (ldc) = epi(x[M,K] (lda) @ W[N,K]^T (ldb))
   int operator()(const float* x, int lda, const float* W, int ldb, const float* bias, float* y, int ldc, long long M, int N, int K,
                  int relu = 0, const float* residual = nullptr, int ldr = 0, const float* rowmask = nullptr, int accumulate = 0,
-                 const __half* x_img = nullptr, __half* y_img = nullptr) const {
+                 const __half* x_img = nullptr, __half* y_img = nullptr, const tc::IpaProjEpi* ipa = nullptr) const {
     // x_img / y_img: operand-image chaining between consecutive Linear layers (lin_tc.cuh); only valid on the packed lin_tc path
     if (ctx->gemm_tc && !accumulate && M > 0) {
       auto it = ctx->packed.find(std::make_tuple(W, ldb, N, K));
@@ -439,7 +462,11 @@ struct Lin {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cudaError_t e;
-        if (x_img && y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, true>, a);
+        if (ipa) {
+          a.ipa = *ipa;
+          a.dbg = nullptr;
+          e = x_img ? cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, false, true>, a) : cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, false, true>, a);
+        } else if (x_img && y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, true>, a);
         else if (x_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, false>, a);
         else if (y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, true>, a);
         else e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, false>, a);
@@ -448,7 +475,7 @@ struct Lin {
         return FDPT_OK;
       }
     }
-    if (x_img || y_img) return fail(ctx, FDPT_ERR_STATE, "operand-image chaining needs the packed lin_tc path");
+    if (x_img || y_img || ipa) return fail(ctx, FDPT_ERR_STATE, "operand-image chaining needs the packed lin_tc path");
     GemmArgs g;
     g.A = x; g.lda = lda; g.B = W; g.ldb = ldb; g.C = y; g.ldc = ldc; g.M = (int)M; g.N = N; g.K = K;
     g.bias = bias; g.relu = relu; g.residual = residual; g.ldr = ldr; g.rowmask = rowmask; g.accumulate = accumulate;
@@ -613,9 +640,19 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
   Lin lin{ctx, st};
   if (w.JB > IPA_MAX_JB) return fail(ctx, FDPT_ERR_INVALID, "N=%d: the IPA kernel supports N <= %d", N, IPA_MAX_JB * 128);
   // q | q_pts, k | k_pts, v | v_pts of every head in one GEMM, then the frames applied in place
-  RET(lin(s, C_S, p.Wcat, C_S, p.bcat, w.proj, PROJ_W, M, PROJ_W, C_S, 0, nullptr, 0, nullptr, 0, s_img, nullptr));
-  std::unique_ptr<ProfScope> pattn(new ProfScope(ctx, FDPT_PROF_IPA_ATTN, st));  // every kernel that implements the attention itself: prep .. opt
   const bool img = ctx->ipa_img && ctx->gemm_tc;
+  // ipa_img mode 1: the projection GEMM's epilogue applies the frames and writes the Q' / K' / V' operand images itself (IpaProjEpi);
+  //          mode 2: fp32 projection + separate ipa_prep_img kernel (A/B switch)
+  const bool img_fused = img && ctx->ipa_img == 1;
+  if (img_fused) {
+    tc::IpaProjEpi e;
+    e.quats = quats; e.trans = trans; e.head_w = p.head_w; e.mask = mask; e.kbias = w.kn; e.Qimg = w.qimg; e.Kimg = w.kimg; e.Vimg = w.vimg;
+    e.n_res = N; e.JB = w.JB;
+    RET(lin(s, C_S, p.Wimgproj, C_S, p.bimgproj, nullptr, 0, M, 3 * NH * 320, C_S, 0, nullptr, 0, nullptr, 0, s_img, nullptr, &e));
+  } else {
+    RET(lin(s, C_S, p.Wcat, C_S, p.bcat, w.proj, PROJ_W, M, PROJ_W, C_S, 0, nullptr, 0, nullptr, 0, s_img, nullptr));
+  }
+  std::unique_ptr<ProfScope> pattn(new ProfScope(ctx, FDPT_PROF_IPA_ATTN, st));  // every kernel that implements the attention itself: prep .. opt
   auto launch_img_gemm = [&](const tc::GemmImgArgs& g) -> int {
     const long long tiles = (long long)g.m_tiles * g.n_tiles * g.batch;
     cudaLaunchConfig_t cfg = {};
@@ -638,8 +675,10 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     IpaImgArgs ia;
     ia.M = (int)M; ia.N = N; ia.JB = w.JB; ia.proj = w.proj; ia.quats = quats; ia.trans = trans; ia.head_w = p.head_w; ia.mask = mask;
     ia.kbias = w.kn; ia.Qimg = w.qimg; ia.Kimg = w.kimg; ia.Vimg = w.vimg;
-    ipa_prep_img_kernel<<<(unsigned)M, 256, 0, st>>>(ia);
-    LAUNCH_CHECK();
+    if (!img_fused) {
+      ipa_prep_img_kernel<<<(unsigned)M, 256, 0, st>>>(ia);
+      LAUNCH_CHECK();
+    }
     tc::GemmImgArgs g;
     memset(&g, 0, sizeof(g));
     const long long per_bh = (long long)w.JB * IPA_IMG_KB * tc::LT_STAGE_BYTES;
@@ -1064,6 +1103,8 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaFuncSetAttribute(tc::lin_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_img_smem_bytes());
   cudaFuncSetAttribute(tc::node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::node_chain_smem_bytes());
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
@@ -1100,6 +1141,8 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaFree(b.Wcat);
     cudaFree(b.bcat);
     cudaFree(b.Wout_perm);
+    cudaFree(b.Wimgproj);
+    cudaFree(b.bimgproj);
     cudaFree(b.imgWb);
   }
   if (ctx->step_graph.exec) cudaGraphExecDestroy(ctx->step_graph.exec);
@@ -1243,6 +1286,7 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
     for (int b = 0; b < NBLK; ++b) {
       BlockParams& p = ctx->blk[b];
       RET(pack_linear(ctx, p.Wcat, C_S, PROJ_W, C_S)); RET(pack_linear(ctx, p.Wskip, C_S, C_SKIP, C_S));
+      RET(pack_linear(ctx, p.Wimgproj, C_S, 3 * NH * 320, C_S));
       for (int l = 0; l < TF_LAYERS; ++l) {
         auto& L = p.tf[l];
         RET(pack_linear(ctx, L.Win, TF_D, 3 * TF_D, TF_D)); RET(pack_linear(ctx, L.Wo, TF_D, TF_D, TF_D));
@@ -1714,7 +1758,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
     case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; tc::g_use_pdl = (value & 16) ? 0 : 1; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
     case FDPT_OPT_ET_PAIR: ctx->et_pair = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
-    case FDPT_OPT_IPA_IMG: ctx->ipa_img = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
+    case FDPT_OPT_IPA_IMG: ctx->ipa_img = value; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_CHAIN: ctx->use_chain = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {

@@ -25,6 +25,19 @@ constexpr int LT_WORKERS = 256;
 constexpr int LT_THREADS = LT_WORKERS + 64;
 constexpr int LT_MAX_KB = 5;            // K <= 320
 
+// Epilogue of the fused IPA projection (kernels_ipa.cuh): the GEMM's output row of residue m is turned straight into the operand images
+// of the attention GEMMs (gemm_img.cuh) — no fp32 projection buffer, no separate prep kernel.  Output columns are laid out as 24
+// blocks of 320 = [operand (q, k, v)][head][256 scalar channels | points planar x | y | z (24 or 36) | zero padding]; a thread of the
+// epilogue owns one residue (TMEM lane) and 64 consecutive columns, i.e. either 64 scalar channels or the whole point group of one
+// (operand, head), to which it applies the residue's frame (ipa_pytorch.py:214-239, rigid_utils.py:82-106) in registers.
+struct IpaProjEpi {
+  const float* quats; const float* trans;   // [M,4], [M,3] frames (translations in 0.1 A units)
+  const float* head_w; const float* mask;   // [H] head weights (softplus -> gamma), [M] residue mask
+  float* kbias;                             // [B,H,N]  -gamma/2 |k_pts|^2 + 1e5 (m - 1)
+  uint8_t *Qimg, *Kimg, *Vimg;              // [B*H][JB][5 k-blocks][hi|lo][128 rows][128 B]
+  int n_res, JB;
+};
+
 struct LinTcArgs {
   const float* X; int ldx; int M, K, N;
   const __half* Wimg;          // [n_tiles][nkb][2][128][64] fp16 (swizzled rows)
@@ -37,6 +50,7 @@ struct LinTcArgs {
   int x_vec, y_vec;
   int dbg_flags;               // bring-up: bit 0 skip the epilogue stores, bit 1 skip the MMAs
   long long* dbg;              // optional clock64 timeline of CTA (0,0): 16 stamps (tools/lin_timeline.py), or nullptr
+  IpaProjEpi ipa;              // only read by the EPI_IPA instantiation
   // Operand-image chaining between consecutive Linear layers (both optional):
   //   XIMG: X points to the split operand image, i.e. X is already available as the split operand image [m-tile][k-block][hi|lo][128 rows][128 B] written by the previous
   //         layer's epilogue -> the staging phase (fp32 loads + split + swizzled stores by 256 threads) becomes nkb bulk copies;
@@ -53,7 +67,7 @@ struct LinTcArgs {
 
 // YIMG: the epilogue also (or only) writes the operand image of the next layer; a separate instantiation so that the plain kernel keeps
 // its register allocation
-template <bool XIMG, bool YIMG>
+template <bool XIMG, bool YIMG, bool EPI_IPA = false>
 __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -199,6 +213,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
       mbar_wait(&acc_full[as], (t >> 1) & 1);
       tc_fence_after();
       if (tid == 0 && t == 0) LT_TS(9);
+      float pt[EPI_IPA ? 32 : 1];  // EPI_IPA: first half of a point group (columns 256..287 of a block), kept for the second pass
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int cb = c_half + q * 32;
@@ -214,6 +229,79 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         if (n0 + cb >= a.N || (a.dbg_flags & 1)) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
+        if constexpr (EPI_IPA) {
+          const int r = (warp & 3) * 32 + lane;
+          const int m = m0 + r;
+          const int col0 = n0 + cb;                  // multiple of 32
+          const int blk = col0 / 320, within = col0 - blk * 320;
+          const int kind = blk >> 3, h = blk & 7;    // blocks ordered [operand][head]
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + col0 + j);
+          if (m < a.M) {
+            const int bsamp = m / a.ipa.n_res, i = m - bsamp * a.ipa.n_res;
+            uint8_t* img = kind == 0 ? a.ipa.Qimg : (kind == 1 ? a.ipa.Kimg : a.ipa.Vimg);
+            uint8_t* tile = img + ((size_t)(bsamp * 8 + h) * a.ipa.JB + (i >> 7)) * (5 * (size_t)LT_STAGE_BYTES);
+            auto put8 = [&](int c, const float* y) {  // chunk c (8 columns) of this (operand, head) block, row i
+              uint4 hi, lo;
+              split8(make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), hi, lo);
+              uint8_t* d = tile + (size_t)(c >> 3) * LT_STAGE_BYTES + sw128_chunk_off(i & 127, c & 7);
+              *reinterpret_cast<uint4*>(d) = hi;
+              *reinterpret_cast<uint4*>(d + 16384) = lo;
+            };
+            if (within < 256) {
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) put8((within >> 3) + cc, v + 8 * cc);
+            } else if (within == 256) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pt[j] = v[j];
+            } else {  // within == 288: the point group is complete (pt = columns 256..287, v = 288..319)
+              float R[9];
+              {
+                const float qf[4] = {a.ipa.quats[m * 4], a.ipa.quats[m * 4 + 1], a.ipa.quats[m * 4 + 2], a.ipa.quats[m * 4 + 3]};
+                quat_to_rot(qf, R);
+              }
+              const float t0 = a.ipa.trans[m * 3], t1 = a.ipa.trans[m * 3 + 1], t2 = a.ipa.trans[m * 3 + 2];
+              const float gamma = log1pf(expf(__ldg(a.ipa.head_w + h))) * sqrtf(1.0f / 108.f);  // softplus(w_h) * sqrt(1 / (3 * 8 * 9 / 2))
+              if (kind < 2) {  // 8 points: x = pt[0:8], y = pt[8:16], z = pt[16:24]
+                float gx[8], gy[8], gz[8];
+                float d2 = 0.f;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                  const float x = pt[p], y = pt[8 + p], z = pt[16 + p];
+                  gx[p] = R[0] * x + R[1] * y + R[2] * z + t0;
+                  gy[p] = R[3] * x + R[4] * y + R[5] * z + t1;
+                  gz[p] = R[6] * x + R[7] * y + R[8] * z + t2;
+                  d2 += gx[p] * gx[p] + gy[p] * gy[p] + gz[p] * gz[p];
+                }
+                if (kind == 0) {
+#pragma unroll
+                  for (int p = 0; p < 8; ++p) {
+                    gx[p] *= gamma; gy[p] *= gamma; gz[p] *= gamma;
+                  }
+                } else {
+                  a.ipa.kbias[((long long)bsamp * 8 + h) * a.ipa.n_res + i] = -0.5f * gamma * d2 + 1e5f * (__ldg(a.ipa.mask + m) - 1.f);
+                }
+                put8(32, gx);
+                put8(33, gy);
+                put8(34, gz);
+              } else {  // 12 points: x = cols 256..267, y = 268..279, z = 280..291 (z straddles the two passes)
+                float g[40];
+#pragma unroll
+                for (int p = 0; p < 12; ++p) {
+                  const float x = pt[p], y = pt[12 + p], z = (24 + p < 32) ? pt[24 + p] : v[24 + p - 32];
+                  g[p] = R[0] * x + R[1] * y + R[2] * z + t0;
+                  g[12 + p] = R[3] * x + R[4] * y + R[5] * z + t1;
+                  g[24 + p] = R[6] * x + R[7] * y + R[8] * z + t2;
+                }
+#pragma unroll
+                for (int p = 36; p < 40; ++p) g[p] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) put8(32 + c, g + 8 * c);
+              }
+            }
+          }
+          continue;
+        }
         if constexpr (YIMG) {
           // thread = row, 32 consecutive columns in registers = four 16-byte chunks of the next layer's operand image
           const int r = (warp & 3) * 32 + lane;

@@ -33,10 +33,10 @@ def _build(conf, sd, inpainting=True):
     return m.to("cuda").eval(), diffuser
 
 
-def _lookup_mismatch(ours, ref):
+def _lookup_mismatch(ours, ref, tol=1e-5):
     """fraction of entries of a table-look-up score that differ (a float32 omega on a bucket boundary may fall into the neighbour)"""
     scale = np.abs(ref).max(-1, keepdims=True) + 1e-30
-    return float((np.abs(ours - ref) / scale > 1e-5).any(-1).mean())
+    return float((np.abs(ours - ref) / scale > tol).any(-1).mean())
 
 
 def test_cached_score_table_vs_reference(g, golden_dir, state_dict, tmp_path):
@@ -71,7 +71,9 @@ def test_cached_score_table_vs_reference(g, golden_dir, state_dict, tmp_path):
     f1["t"] = torch.tensor([0.37, 0.81]).cuda()
     out = m(f1)
     assert np.abs(out["rigids"].cpu().numpy()[..., 4:] - g["cached_fwd_rigids"][..., 4:]).max() < 1e-4
-    assert _lookup_mismatch(out["rot_score"].cpu().numpy(), g["cached_fwd_rot_score"]) < 0.05
+    # inside a forward the rotation vector itself carries the network's error (1e-5 rad class): the same 2e-3 relative bound as the series
+    # score of the other forward tests, with a few bucket flips of the table index allowed
+    assert _lookup_mismatch(out["rot_score"].cpu().numpy(), g["cached_fwd_rot_score"], 2e-3) < 0.05
     traj = inference_fn(m, diffuser, feats, num_t=6, min_t=0.01, aux_traj=True, noise_scale=0.1, inpainting=True, input_aatype=True,
                         noise=g["cached_noise"])
     r = bb_rmsd(traj["prot_traj"][0][:, :, :5], g["cached_prot_traj"][0])

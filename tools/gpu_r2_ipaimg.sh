@@ -1,10 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python tools/dbg_cached.py 2>&1 | tail -20 > gpurun_out/dbg_cached.log
 timeout 1500 python -m pytest tests -m gpu -q -s -x 2>&1 | grep -v "^$" > gpurun_out/pytest_gpu_full.log
-tail -12 gpurun_out/pytest_gpu_full.log
-for v in 1 0 1 0; do
+tail -6 gpurun_out/pytest_gpu_full.log
+rm -f gpurun_out/ab_ipaimg.log
+for v in 1 2 0 1 2 0; do
   FDPT_OPT_7=$v timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-extra 2>&1 | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('ipa_img=$v', 'ms/step', round(d['ms_per_step'],3), 'launches', d['gpu_launches'], 'ipa_attn ms', round(d['roofline_ipa']['avg_ms'],4), 'frac', round(d['roofline_ipa']['frac'],3), 'core ms', round(d['roofline_ipa_core_kernel']['avg_ms'],4))" | tee -a gpurun_out/ab_ipaimg.log
+d=json.loads(sys.stdin.read()); print('ipa_img=$v', 'ms/step', round(d['ms_per_step'],3), 'launches', d['gpu_launches'], 'ipa_attn ms', round(d['roofline_ipa']['avg_ms'],4), 'frac', round(d['roofline_ipa']['frac'],3), 'ipa_total share', round(d['time_shares_of_forward']['ipa_total'],4))" | tee -a gpurun_out/ab_ipaimg.log
 done
