@@ -421,8 +421,11 @@ def main():
                 extra["cfg4_tcrpmhc800"] = {"global_batch": w4.batch, "batch_per_gpu": b1 - b0, "n_res": w4.n_res, "ms_per_step": ms4,
                                             "value": w4.batch * w4.n_res / (ms4 * 1e-3), "unit": UNIT, "scaling": "strong"}
                 if rank == 0:  # the same global batch on ONE GPU of this box: strong-scaling efficiency measured in the same run
-                    ms4_1 = quick_rate(ctx, model, diffuser, w4, w4.batch, 3, 3, dev, None, 1)
-                    extra["cfg4_tcrpmhc800"].update(ms_per_step_1gpu=ms4_1, strong_scaling_efficiency=ms4_1 / (world * ms4))
+                    try:
+                        ms4_1 = quick_rate(ctx, model, diffuser, w4, w4.batch, 3, 3, dev, None, 1)
+                        extra["cfg4_tcrpmhc800"].update(ms_per_step_1gpu=ms4_1, strong_scaling_efficiency=ms4_1 / (world * ms4))
+                    except Exception as e:  # rank 0 must reach the barrier below whatever happens
+                        extra["cfg4_tcrpmhc800"]["error_1gpu"] = repr(e)[:200]
                 dist.barrier()
             if world == 8:  # cfg5: length sweep, global batch 128 over 8 GPUs = 16 per GPU
                 m5, d5, c5 = build_model(True)
@@ -433,8 +436,11 @@ def main():
                     extra[name] = {"global_batch": w5.batch, "batch_per_gpu": b1 - b0, "n_res": w5.n_res, "ms_per_step": ms5,
                                    "value": w5.batch * w5.n_res / (ms5 * 1e-3), "unit": UNIT, "scaling": "strong"}
                     if rank == 0:
-                        ms5_1 = quick_rate(c5, m5, d5, w5, w5.batch, 3, 3, dev, None, 1)
-                        extra[name].update(ms_per_step_1gpu=ms5_1, strong_scaling_efficiency=ms5_1 / (world * ms5))
+                        try:
+                            ms5_1 = quick_rate(c5, m5, d5, w5, w5.batch, 3, 3, dev, None, 1)
+                            extra[name].update(ms_per_step_1gpu=ms5_1, strong_scaling_efficiency=ms5_1 / (world * ms5))
+                        except Exception as e:
+                            extra[name]["error_1gpu"] = repr(e)[:200]
                     dist.barrier()
         except Exception as e:  # a secondary line must never take the headline down
             extra["error"] = repr(e)[:300]

@@ -20,12 +20,10 @@
 #include "kernels_ipa.cuh"
 #include "kernels_misc.cuh"
 #include "et_fused.cuh"
-#include "et_fused2.cuh"
 #include "edge_embed_fused.cuh"
 #include "tc_linear.cuh"
 #include "gemm_tc.cuh"
 #include "lin_tc.cuh"
-#include "node_chain.cuh"
 #include "gemm_img.cuh"
 #include "backbone_tables.inc"
 
@@ -127,8 +125,6 @@ struct fdpt_ctx {
   int64_t stat_captures = 0;      // per-timestep graphs captured so far
   int64_t stat_sample_host_us = 0; // host time the last fdpt_sample call spent enqueueing
   int ipa_img = 1;    // IPA attention GEMMs from operand images (gemm_img.cuh); 0 = fp32 operands split on the fly (gemm_tc.cuh; A/B switch)
-  int use_chain = 0;  // node-side layer chains in one persistent kernel per chain (node_chain.cuh); 0 = one launch per layer (A/B switch)
-  int et_pair = 0;  // 1: EdgeTransition on CTA pairs (et_fused2.cuh, experimental: slower); 0: single-CTA kernel (et_fused.cuh)
   cudaStream_t own_stream = nullptr;   // the legacy default stream cannot be captured: fdpt_sample then runs on this stream,
   cudaEvent_t fence_in = nullptr, fence_out = nullptr;  // fenced against the caller's stream with these events
   long long* et_dbg = nullptr;  // optional clock64 timeline buffer of the EdgeTransition kernel (FDPT_OPT_ET_TIMELINE)
@@ -492,67 +488,6 @@ struct Lin {
     if (r__ != FDPT_OK) return r__; \
   } while (0)
 
-// Program of one node_chain_kernel launch (node_chain.cuh): a sequence of row-local Linear / LayerNorm ops on 128-row tiles.
-struct Chain {
-  fdpt_ctx* ctx;
-  long long M;
-  tc::ChainArgs a;
-  bool bad = false;
-  Chain(fdpt_ctx* c, long long M_) : ctx(c), M(M_) {
-    memset(&a, 0, sizeof(a));
-    a.M = (int)M_;
-  }
-  tc::ChainOp* next() {
-    if (a.nops >= tc::CH_MAX_OPS) {
-      bad = true;
-      return &a.ops[tc::CH_MAX_OPS - 1];
-    }
-    return &a.ops[a.nops++];
-  }
-  // Y / Yimg = epi(X @ W[N,K]^T (row stride ldw) + bias); X = fp32 rows (x, ldx) or the operand image x_img
-  void linear(const float* x, int ldx, const __half* x_img, const float* W, int ldw, int N, int K, const float* bias, int relu,
-              const float* rowmask, const float* residual, int ldr, float* y, int ldy, __half* y_img, int epi = tc::CH_EPI_PLAIN,
-              float* y2 = nullptr) {
-    auto it = ctx->packed.find(std::make_tuple(W, ldw, N, K));
-    if (it == ctx->packed.end()) {
-      bad = true;
-      return;
-    }
-    tc::ChainOp& o = *next();
-    o.kind = tc::CH_LINEAR;
-    o.X = x; o.ldx = ldx; o.Ximg = x_img; o.K = K; o.N = N; o.nkb = it->second.nkb; o.n_tiles = it->second.n_tiles; o.Wimg = it->second.img;
-    o.bias = bias; o.relu = relu; o.rowmask = rowmask; o.residual = residual; o.ldr = ldr; o.Y = y; o.ldy = ldy; o.Yimg = y_img; o.epi = epi;
-    o.Y2 = y2;
-  }
-  // y (, y2, y_img) = LN_C((sum_k x[k * pstride] + pre_bias) * pre_mask + pre_res) * gamma + beta (* rowmask)
-  void ln(int C, const float* x, int ldx, const float* gamma, const float* beta, const float* rowmask, float* y, int ldy, float* y2, int ldy2,
-          __half* y_img, int nparts = 1, long long pstride = 0, const float* pre_bias = nullptr, const float* pre_mask = nullptr,
-          const float* pre_res = nullptr) {
-    tc::ChainOp& o = *next();
-    o.kind = tc::CH_LN;
-    o.C = C; o.X = x; o.ldx = ldx; o.gamma = gamma; o.beta = beta; o.rowmask = rowmask; o.Y = y; o.ldy = ldy; o.Y2 = y2; o.ldy2 = ldy2; o.Yimg = y_img;
-    o.nparts = nparts; o.pstride = pstride; o.pre_bias = pre_bias; o.pre_mask = pre_mask; o.pre_res = pre_res;
-  }
-  int launch(cudaStream_t st) {
-    if (bad) return fail(ctx, FDPT_ERR_STATE, "node chain: too many ops or a weight that was not pre-split");
-    if (a.nops == 0 || M <= 0) return FDPT_OK;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((M + 127) / 128));
-    cfg.blockDim = dim3(tc::LT_THREADS);
-    cfg.dynamicSmemBytes = tc::node_chain_smem_bytes();
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = tc::g_use_pdl;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, tc::node_chain_kernel, a);
-    ctx->launches++;
-    if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "node_chain launch: %s", cudaGetErrorString(e));
-    return FDPT_OK;
-  }
-};
-
 template <int C>
 int layernorm(fdpt_ctx* ctx, cudaStream_t st, const float* x, float* y, const float* g, const float* b, long long rows,
               const float* rowmask, const float* pairmask = nullptr, int nres = 0, long long row0 = 0) {
@@ -577,18 +512,7 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
     LAUNCH_CHECK();
   }
   auto& T = ctx->top;
-  const bool chain_mode = ctx->gemm_tc && ctx->use_chain;
-  if (chain_mode) {
-    // node MLP (3 Linear layers, hidden activations as operand images) + LayerNorm + mask, and the per-residue part of the edge
-    // embedder's first layer, as one chain; `node_copy` receives a second copy of the embedding (the trunk's running node state)
-    Chain ch(ctx, M);
-    ch.linear(w.node_feat, FN, nullptr, T.nW0, FN, C_S, FN, T.nb0, 1, nullptr, nullptr, 0, nullptr, 0, w.imgT1);
-    ch.linear(nullptr, 0, w.imgT1, T.nW2, C_S, C_S, C_S, T.nb2, 1, nullptr, nullptr, 0, nullptr, 0, w.imgT2);
-    ch.linear(nullptr, 0, w.imgT2, T.nW4, C_S, C_S, C_S, T.nb4, 0, nullptr, nullptr, 0, w.tmpA, C_S, nullptr);
-    ch.ln(C_S, w.tmpA, C_S, T.nln_g, T.nln_b, in->res_mask, node_out, C_S, node_copy, C_S, nullptr);
-    ch.linear(w.feat1d, F1, nullptr, T.eW0, EIN, C_Z, F1, T.eb0, 0, nullptr, nullptr, 0, w.PA, C_Z, nullptr);
-    RET(ch.launch(st));
-  } else if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {  // hidden activations as operand images (lin_tc Ximg / Yimg)
+  if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {  // hidden activations as operand images (lin_tc Ximg / Yimg)
     RET(lin(w.node_feat, FN, T.nW0, FN, T.nb0, nullptr, C_S, M, C_S, FN, 1, nullptr, 0, nullptr, 0, nullptr, w.imgT1));
     RET(lin(nullptr, C_S, T.nW2, C_S, T.nb2, nullptr, C_S, M, C_S, C_S, 1, nullptr, 0, nullptr, 0, w.imgT1, w.imgT2));
     RET(lin(nullptr, C_S, T.nW4, C_S, T.nb4, w.tmpA, C_S, M, C_S, C_S, 0, nullptr, 0, nullptr, 0, w.imgT2, nullptr));
@@ -597,13 +521,11 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
     RET(lin(w.tmpA, C_S, T.nW2, C_S, T.nb2, w.tmpB, C_S, M, C_S, C_S, 1));
     RET(lin(w.tmpB, C_S, T.nW4, C_S, T.nb4, w.tmpA, C_S, M, C_S, C_S, 0));
   }
-  if (!chain_mode) {
-    RET(layernorm<C_S>(ctx, st, w.tmpA, node_out, T.nln_g, T.nln_b, M, in->res_mask));
-    if (node_copy) CK(cudaMemcpyAsync(node_copy, node_out, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
-    // edge embedder (edge_embed_fused.cuh): W0 = [A (F1) | B (F1) | C (32) | D (22)];  PA_i = A f_i + b0 per residue (fp32 class),
-    // everything pair-sized inside one fused tcgen05 kernel
-    RET(lin(w.feat1d, F1, T.eW0, EIN, T.eb0, w.PA, C_Z, M, C_Z, F1, 0));
-  }
+  RET(layernorm<C_S>(ctx, st, w.tmpA, node_out, T.nln_g, T.nln_b, M, in->res_mask));
+  if (node_copy) CK(cudaMemcpyAsync(node_copy, node_out, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
+  // edge embedder (edge_embed_fused.cuh): W0 = [A (F1) | B (F1) | C (32) | D (22)];  PA_i = A f_i + b0 per residue (fp32 class),
+  // everything pair-sized inside one fused tcgen05 kernel
+  RET(lin(w.feat1d, F1, T.eW0, EIN, T.eb0, w.PA, C_Z, M, C_Z, F1, 0));
   {
     const long long chunks = (long long)B * w.JB * 128 * 8;
     tc::f_to_image_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(B, N, w.JB, F1, w.feat1d, w.f_img);
@@ -628,11 +550,8 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
 // ---- IPA (kernels_ipa.cuh) ------------------------------------------------------------------------------------
 int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* z, const float* quats, const float* trans,
             const float* mask, float* out, int ldo, const float* residual, const float* outmask, cudaStream_t st,
-            const float* ln_g = nullptr, const float* ln_b = nullptr, float* ln_out = nullptr, const __half* s_img = nullptr,
-            bool defer_sumk = false) {
-  // s_img: operand image of s (written by the previous block's chain): the projection GEMM skips its staging phase.
-  // defer_sumk: stop after the split-K linear_out GEMM; the caller's node chain sums the parts, adds bias / mask / residual and applies
-  //             the LayerNorm (tmpA / tmpB / tmpC hold the partial products)
+            const float* ln_g = nullptr, const float* ln_b = nullptr, float* ln_out = nullptr, const __half* s_img = nullptr) {
+  // s_img: optional operand image of s: the projection GEMM then skips its staging phase
   ProfScope ps(ctx, FDPT_PROF_IPA_TOTAL, st);
   Workspace& w = ctx->ws;
   const BlockParams& p = ctx->blk[blk];
@@ -739,7 +658,6 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     g.C = w.tmpA; g.ldc = C_S; g.sC1 = w.tmpB - w.tmpA; g.M = (int)M; g.N = C_S; g.K = CAT / OUT_SPLIT;
     CK(gemm_dispatch(ctx, g, true, OUT_SPLIT, st));
     ctx->launches++;
-    if (defer_sumk) return FDPT_OK;
     sumk_layernorm_kernel<C_S><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(w.tmpA, w.tmpB - w.tmpA, OUT_SPLIT, p.bout, residual, outmask, ln_out, ln_g,
                                                                         ln_b, M);
     LAUNCH_CHECK();
@@ -753,16 +671,14 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
 
 // ---- edge transition (fused tcgen05 kernel, et_fused.cuh) ------------------------------------------------------
 int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const __half* z_in, const float* mask, __half* z_out,
-                        cudaStream_t st, bool prologue_done = false) {
+                        cudaStream_t st) {
   ProfScope ps(ctx, FDPT_PROF_EDGE_TRANSITION, st);
   Workspace& w = ctx->ws;
   const BlockParams& p = ctx->blk[blk];
   const long long M = (long long)B * N;
   Lin lin{ctx, st};
   // per-residue parts: n = initial_embed(node); U_i = W1[:,128:256] n_i + b1; Pf_i = Wf[:,128:256] n_i + bf
-  if (prologue_done) {
-    // computed by the block's node chain (n_emb, U, Pf already in the workspace)
-  } else if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {  // n is written as fp32 (for the n_j images) AND as the operand image of the two GEMMs below
+  if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {  // n is written as fp32 (for the n_j images) AND as the operand image of the two GEMMs below
     RET(lin(node, C_S, p.Wie, C_S, p.bie, w.n_emb, C_Z, M, C_Z, C_S, 0, nullptr, 0, nullptr, 0, nullptr, w.imgN));
     RET(lin(nullptr, C_Z, p.We1 + C_Z, ET_HID, p.be1, w.U, ET_HID, M, ET_HID, C_Z, 0, nullptr, 0, nullptr, 0, w.imgN, nullptr));
     RET(lin(nullptr, C_Z, p.Wef + C_Z, ET_HID, p.bef, w.Pf, C_Z, M, C_Z, C_Z, 0, nullptr, 0, nullptr, 0, w.imgN, nullptr));
@@ -782,20 +698,7 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   a.tiles = M * w.JB;
   if (a.tiles >= (1LL << 31)) return fail(ctx, FDPT_ERR_INVALID, "B*N*ceil(N/128) = %lld tiles: the pair kernels index tiles with 32 bits", a.tiles);
   a.dbg = (ctx->dbg_flags & 4) ? nullptr : ctx->et_dbg;
-  if (ctx->et_pair && a.tiles >= 2) {
-    const long long pairs = (a.tiles + 1) / 2;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(ctx->num_sms / 2, pairs));
-    cfg.blockDim = dim3(tc::ET_THREADS);
-    cfg.dynamicSmemBytes = tc::et2_smem_bytes();
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const int et_flags = (ctx->dbg_flags >> 5) & 7;  // debug flag bits 32 / 64 / 128: profiling experiments of the pair kernel
-    CK(cudaLaunchKernelEx(&cfg, tc::et_fused2_kernel, a, et_flags));
-  } else {
+  {
     const int grid = (int)std::min<long long>(ctx->num_sms, a.tiles);
     tc::et_fused_kernel<<<grid, tc::ET_THREADS, tc::et_smem_bytes(), st>>>(a);
   }
@@ -865,74 +768,6 @@ int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaSt
   return FDPT_OK;
 }
 
-// ---- node side of a trunk block as three node chains around the two attention calls (node_chain.cuh) -------------------------
-//   chain 1: node = LN(node + mask * (sum of the split-K parts of linear_out + bias)) (ipa_pytorch.py:531-532);
-//            x = [node | skip_embed(node0)] (533-536); qkv = in_proj_0(x)
-//   chain 2: encoder layer 0 after its attention (out_proj + residual, norm1, FFN + residual, norm2), qkv = in_proj_1(x)
-//   chain 3: encoder layer 1 after its attention, node += post_tfmr(x) (539), node transition + LN + mask (540-541), backbone update
-//            composed into the frames (542-547), and either the per-residue prologue of the EdgeTransition that follows
-//            (initial_embed, U_i, Pf_i: 84-91) or, in the last block, the torsion head's MLP (347-360)
-// unit_mode (fdpt_seq_tfmr): only the sequence-transformer sub-block: w.node / w.node0 are given, chain 1 starts at skip_embed and
-// chain 3 stops after post_tfmr.
-int run_node_chains(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, int nparts, cudaStream_t st, bool unit_mode = false) {
-  ProfScope ps(ctx, FDPT_PROF_SEQ_TFMR, st);
-  Workspace& w = ctx->ws;
-  const BlockParams& p = ctx->blk[blk];
-  const long long M = (long long)B * N;
-  {
-    Chain ch(ctx, M);
-    if (unit_mode) {
-      copy_cols_kernel<<<(unsigned)((M * C_S + 255) / 256), 256, 0, st>>>(M, C_S, w.node, C_S, w.tf_x, TF_D, 0, nullptr);
-      LAUNCH_CHECK();
-    } else {
-      ch.ln(C_S, w.tmpA, C_S, p.ln_g, p.ln_b, nullptr, w.node, C_S, w.tf_x, TF_D, nullptr, nparts, w.tmpB - w.tmpA, p.bout, mask, w.node);
-    }
-    ch.linear(w.node0, C_S, nullptr, p.Wskip, C_S, C_SKIP, C_S, p.bskip, 0, nullptr, nullptr, 0, w.tf_x + C_S, TF_D, nullptr);
-    ch.linear(w.tf_x, TF_D, nullptr, p.tf[0].Win, TF_D, 3 * TF_D, TF_D, p.tf[0].bin, 0, nullptr, nullptr, 0, w.qkv, 3 * TF_D, nullptr);
-    RET(ch.launch(st));
-  }
-  for (int l = 0; l < TF_LAYERS; ++l) {
-    const auto& L = p.tf[l];
-    RET(seq_attention(ctx, B, N, mask, st));
-    Chain ch(ctx, M);
-    ch.linear(w.att_o, TF_D, nullptr, L.Wo, TF_D, TF_D, TF_D, L.bo, 0, nullptr, w.tf_x, TF_D, w.tmpA, TF_D, nullptr);
-    ch.ln(TF_D, w.tmpA, TF_D, L.n1g, L.n1b, nullptr, w.tf_x, TF_D, nullptr, 0, w.imgF);
-    ch.linear(nullptr, 0, w.imgF, L.W1, TF_D, TF_D, TF_D, L.b1, 1, nullptr, nullptr, 0, nullptr, 0, w.imgT1);
-    ch.linear(nullptr, 0, w.imgT1, L.W2, TF_D, TF_D, TF_D, L.b2, 0, nullptr, w.tf_x, TF_D, w.tmpB, TF_D, nullptr);
-    if (l + 1 < TF_LAYERS) {
-      ch.ln(TF_D, w.tmpB, TF_D, L.n2g, L.n2b, nullptr, w.tf_x, TF_D, nullptr, 0, w.imgF);
-      ch.linear(nullptr, 0, w.imgF, p.tf[l + 1].Win, TF_D, 3 * TF_D, TF_D, p.tf[l + 1].bin, 0, nullptr, nullptr, 0, w.qkv, 3 * TF_D, nullptr);
-      RET(ch.launch(st));
-      continue;
-    }
-    ch.ln(TF_D, w.tmpB, TF_D, L.n2g, L.n2b, nullptr, w.tf_x, TF_D, nullptr, 0, w.imgF);
-    // node = node + post_tfmr(x); its image feeds the node transition
-    ch.linear(nullptr, 0, w.imgF, p.Wpost, TF_D, C_S, TF_D, p.bpost, 0, nullptr, w.node, C_S, w.node, C_S, w.imgT1);
-    if (unit_mode) {
-      RET(ch.launch(st));
-      break;
-    }
-    ch.linear(nullptr, 0, w.imgT1, p.Wt1, C_S, C_S, C_S, p.bt1, 1, nullptr, nullptr, 0, nullptr, 0, w.imgT2);
-    ch.linear(nullptr, 0, w.imgT2, p.Wt2, C_S, C_S, C_S, p.bt2, 1, nullptr, nullptr, 0, nullptr, 0, w.imgT1);
-    ch.linear(nullptr, 0, w.imgT1, p.Wt3, C_S, C_S, C_S, p.bt3, 0, nullptr, w.node, C_S, w.tmpA, C_S, nullptr);
-    ch.ln(C_S, w.tmpA, C_S, p.tln_g, p.tln_b, mask, w.node, C_S, nullptr, 0, w.imgF);
-    // backbone update: u = Linear(node) (rows with diffuse mask 0 are not updated, so the mask commutes), composed in the epilogue
-    ch.linear(nullptr, 0, w.imgF, p.Wbb, C_S, 6, C_S, p.bbb, 0, w.dmask, nullptr, 0, w.quats, 4, nullptr, tc::CH_EPI_COMPOSE, w.trans);
-    if (blk < NBLK - 1) {
-      ch.linear(nullptr, 0, w.imgF, p.Wie, C_S, C_Z, C_S, p.bie, 0, nullptr, nullptr, 0, w.n_emb, C_Z, w.imgN);
-      ch.linear(nullptr, 0, w.imgN, p.We1 + C_Z, ET_HID, ET_HID, C_Z, p.be1, 0, nullptr, nullptr, 0, w.U, ET_HID, nullptr);
-      ch.linear(nullptr, 0, w.imgN, p.Wef + C_Z, ET_HID, C_Z, C_Z, p.bef, 0, nullptr, nullptr, 0, w.Pf, C_Z, nullptr);
-    } else {
-      auto& T = ctx->top;
-      ch.linear(nullptr, 0, w.imgF, T.tW1, C_S, C_S, C_S, T.tb1, 1, nullptr, nullptr, 0, nullptr, 0, w.imgT1);
-      ch.linear(nullptr, 0, w.imgT1, T.tW2, C_S, C_S, C_S, T.tb2, 0, nullptr, w.node, C_S, nullptr, 0, w.imgT2);
-      ch.linear(nullptr, 0, w.imgT2, T.tWf, C_S, 2, C_S, T.tbf, 0, nullptr, nullptr, 0, w.tors_u, 2, nullptr);
-    }
-    RET(ch.launch(st));
-  }
-  return FDPT_OK;
-}
-
 // ---- full forward -------------------------------------------------------------------------------------------------
 int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_out* out, cudaStream_t st) {
   if (!ctx->finalized) return fail(ctx, FDPT_ERR_STATE, "parameters not finalised");
@@ -944,22 +779,11 @@ int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_o
   Lin lin{ctx, st};
   const float cs = ctx->cfg.coordinate_scaling;
   RET(run_embed(ctx, B, N, in, w.node0, w.z, st, w.node));
-  // node chains need the split-K form of linear_out (three equally spaced part buffers)
-  const int out_split = (ctx->dbg_flags & 16384) ? 2 : 3;
-  const bool chain_mode = ctx->gemm_tc && ctx->use_chain && !(ctx->dbg_flags & 256) && (CAT / 64) % out_split == 0 && w.tmpB - w.tmpA == w.tmpC - w.tmpB;
   init_frames_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>((int)M, in->rigids_t, cs, in->res_mask, in->fixed_mask, w.quats, w.trans,
                                                                   w.dmask);
   LAUNCH_CHECK();
   for (int b = 0; b < NBLK; ++b) {
     const BlockParams& p = ctx->blk[b];
-    if (chain_mode) {
-      // after block b-1's chain imgF holds the operand image of `node`
-      RET(run_ipa(ctx, b, B, N, w.node, w.z, w.quats, w.trans, in->res_mask, w.tmpC, C_S, w.node, in->res_mask, st, p.ln_g, p.ln_b, w.node,
-                  b > 0 ? w.imgF : nullptr, true));
-      RET(run_node_chains(ctx, b, B, N, in->res_mask, out_split, st));
-      if (b < NBLK - 1) RET(run_edge_transition(ctx, b, B, N, w.node, w.z, in->res_mask, w.z, st, true));
-      continue;
-    }
     // node = LN(node + ipa(node) * mask)
     RET(run_ipa(ctx, b, B, N, w.node, w.z, w.quats, w.trans, in->res_mask, w.tmpC, C_S, w.node, in->res_mask, st, p.ln_g, p.ln_b, w.node));
     RET(run_seq_tfmr(ctx, b, B, N, in->res_mask, st));
@@ -997,9 +821,7 @@ int forward_impl(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, const fdpt_o
   LAUNCH_CHECK();
   // torsion head (ipa_pytorch.py:347-363)
   auto& T = ctx->top;
-  if (chain_mode) {
-    // the torsion MLP ran at the end of the last block's node chain (tors_u holds linear_final's output)
-  } else if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {
+  if (ctx->gemm_tc && !(ctx->dbg_flags & 32768)) {
     RET(lin(w.node, C_S, T.tW1, C_S, T.tb1, nullptr, C_S, M, C_S, C_S, 1, nullptr, 0, nullptr, 0, nullptr, w.imgT1));
     RET(lin(nullptr, C_S, T.tW2, C_S, T.tb2, nullptr, C_S, M, C_S, C_S, 0, w.node, C_S, nullptr, 0, w.imgT1, w.imgT2));
     RET(lin(nullptr, C_S, T.tWf, C_S, T.tbf, w.tors_u, 2, M, 2, C_S, 0, nullptr, 0, nullptr, 0, w.imgT2, nullptr));
@@ -1095,7 +917,6 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaDeviceGetAttribute(&ctx->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
   cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::et_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et_smem_bytes());
-  cudaFuncSetAttribute(tc::et_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et2_smem_bytes());
   cudaFuncSetAttribute(tc::ee_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ee_smem_bytes());
   cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::tc_linear_smem_bytes(512));
   cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_tc_smem_bytes(128));
@@ -1106,7 +927,6 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaFuncSetAttribute(tc::lin_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_img_smem_bytes());
-  cudaFuncSetAttribute(tc::node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::node_chain_smem_bytes());
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
   float lower[NBINS];
   {
@@ -1671,8 +1491,7 @@ int fdpt_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* node, const
   const size_t M = (size_t)B * N;
   CK(cudaMemcpyAsync(w.node, node, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(w.node0, node0, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
-  if (ctx->gemm_tc && ctx->use_chain) RET(run_node_chains(ctx, blk, B, N, mask, 0, st, true));
-  else RET(run_seq_tfmr(ctx, blk, B, N, mask, st));
+  RET(run_seq_tfmr(ctx, blk, B, N, mask, st));
   if (tfmr_out) CK(cudaMemcpyAsync(tfmr_out, w.tf_x, sizeof(float) * M * TF_D, cudaMemcpyDeviceToDevice, st));
   if (node_out) CK(cudaMemcpyAsync(node_out, w.node, sizeof(float) * M * C_S, cudaMemcpyDeviceToDevice, st));
   return FDPT_OK;
@@ -1757,9 +1576,8 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
     case FDPT_OPT_MN_SWAP: ctx->mn_swap = value != 0; return FDPT_OK;
     case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; tc::g_use_pdl = (value & 16) ? 0 : 1; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
-    case FDPT_OPT_ET_PAIR: ctx->et_pair = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
+    case FDPT_OPT_ET_PAIR: return fail(ctx, FDPT_ERR_INVALID, "the CTA-pair EdgeTransition variant was removed (slower than the single-CTA kernel, DESIGN.md)");
     case FDPT_OPT_IPA_IMG: ctx->ipa_img = value; ctx->step_graph.key.clear(); return FDPT_OK;
-    case FDPT_OPT_CHAIN: ctx->use_chain = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {
         // host-mapped so that the stamps (and the barrier-timeout records of tc::mbar_wait) survive a device-side trap

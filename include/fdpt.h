@@ -235,19 +235,16 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *      1  lin_tc: skip the epilogue stores            2  lin_tc: skip the MMAs
  *      4  route the clock64 timeline buffer to the IPA core kernel instead of EdgeTransition
  *      8  gemm_tc: 128-column tiles whenever N > 128  16  launch the GEMM kernels without programmatic dependent launch
- *     32 / 64 / 128  CTA-pair EdgeTransition experiments: no weight waits / no MMAs / every MMA twice (results are garbage)
  *    256  IPA linear_out as one GEMM instead of split-K + fused reduce
  *    512  lin_tc: write the clock64 timeline of CTA (0,0)   1024  lin_tc: 32-column epilogue staging passes
  *   8192  edge embedder: write the clock64 timeline of worker thread 0 of CTA 0
  *  16384  IPA linear_out: 2-way instead of 3-way split-K
  *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition) */
 enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
-       FDPT_OPT_ET_PAIR = 5 /* 1: EdgeTransition kernel on CTA pairs (cta_group::2; experimental, slower); 0 (default): single-CTA kernel */,
+       FDPT_OPT_ET_PAIR = 5 /* retired: the cta_group::2 EdgeTransition variant of round 1 was slower (1.3 vs 1.0 ms) and has been removed */,
        FDPT_OPT_IPA_IMG = 7 /* 1 (default): the two batched attention GEMMs of the IPA multiply ready operand images (gemm_img.cuh)
                                written by the projection GEMM's own epilogue; 2: same, images written by a separate prep kernel;
-                               0: fp32 operands split on the fly (gemm_tc.cuh).  A/B switch */,
-       FDPT_OPT_CHAIN = 6 /* 1 (default): the row-local node-side layers of a block run as three persistent chain kernels
-                             (node_chain.cuh); 0: one launch per layer (A/B switch) */ };
+                               0: fp32 operands split on the fly (gemm_tc.cuh).  A/B switch */ };
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
 /* clock64 timeline of CTA 0 of the last EdgeTransition kernel ([tile][48] stamps; profiling aid, needs FDPT_OPT_ET_TIMELINE) */
 int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n);

@@ -318,25 +318,6 @@ def test_tiny_and_oversized_inputs(model):
         m({k: v.to("cuda") for k, v in feats.items()})
 
 
-def test_edge_transition_cta_pair_variant_is_bit_identical(ctx):
-    """The experimental cta_group::2 EdgeTransition kernel (et_fused2.cuh, FDPT_OPT_ET_PAIR) runs the same MMAs in the same order on
-    CTA pairs: its output must equal the default kernel's bit for bit, including odd tile counts (the peer CTA repeats the last tile)
-    and pairs that straddle a (sample, j-block) boundary."""
-    g = torch.Generator(device="cuda").manual_seed(5)
-    try:
-        for (B, N) in [(1, 37), (1, 131), (2, 129), (3, 200)]:
-            node = torch.randn(B, N, 256, device="cuda", generator=g)
-            z = torch.randn(B, N, N, 128, device="cuda", generator=g)
-            mask = (torch.rand(B, N, device="cuda", generator=g) > 0.1).float()
-            ctx.set_option(5, 0)
-            ref = ctx.edge_transition(0, node, z, mask)
-            ctx.set_option(5, 1)
-            out = ctx.edge_transition(0, node, z, mask)
-            assert torch.equal(ref, out), (B, N, (ref - out).abs().max().item())
-    finally:
-        ctx.set_option(5, 0)
-
-
 @pytest.mark.parametrize("tag", ["s6", "s12"])
 def test_logp_confidence_score_vs_reference(golden_dir, model, tag):
     """EigenFold confidence score (experiments/utils.py:752-869) with the synthetic network: forward-noise the sample with the
@@ -442,3 +423,32 @@ def test_trajectory_option_variants_vs_reference(golden_dir, state_dict, tag):
     r = bb_rmsd(out["prot_traj"][0][:, :, :5], g[f"{tag}_prot_traj"][0])
     print(f"variant {tag}: per-residue RMSD vs reference max {r.max():.3e}")
     assert r.max() < 1e-3
+
+
+def test_ipa_operand_image_modes_agree(model):
+    """The three ways the IPA attention GEMMs get their operands (FDPT_OPT_IPA_IMG): 1 = operand images written by the projection GEMM's
+    epilogue (default), 2 = images written by a separate prep kernel, 0 = fp32 operands split on the fly — same arithmetic class
+    (2-term fp16 split), so a forward at N=300 (three j-tiles per row, ragged last tile, two chains) must agree to fp32 noise."""
+    from framedipt_b200 import synthetic
+
+    m, diffuser = model
+    ctx = m.context(torch.device("cuda", 0))
+    wl = synthetic.Workload("img300", 2, (140, 160), ((60, 72), (200, 212)), 10)
+    np.random.seed(4)
+    feats = synthetic.make_features(wl, diffuser, seed=4)
+    feats["t"] = 0.5 * torch.ones(wl.batch)
+    feats["res_mask"][1, -5:] = 0.0
+    feats = {k: v.to("cuda") for k, v in feats.items()}
+    outs = {}
+    try:
+        for mode in (1, 2, 0):
+            ctx.set_option(7, mode)
+            outs[mode] = {k: v.cpu().numpy() for k, v in m(feats).items()}
+    finally:
+        ctx.set_option(7, 1)
+    valid = feats["res_mask"].cpu().numpy().astype(bool)
+    for mode in (2, 0):
+        d = np.abs(outs[mode]["rigids"][..., 4:] - outs[1]["rigids"][..., 4:])[valid].max()
+        da = rot_angle_between(outs[mode]["rigids"][..., :4], outs[1]["rigids"][..., :4])[valid].max()
+        print(f"IPA image mode {mode} vs 1: |dtrans| {d:.2e} A, rot {da:.2e} rad")
+        assert d < 2e-5 and da < 2e-5
