@@ -41,6 +41,7 @@ struct BlockParams {
   const float *ln_g, *ln_b, *Wskip, *bskip;
   struct TfLayer {
     const float *Win, *bin, *Wo, *bo, *W1, *b1, *W2, *b2, *n1g, *n1b, *n2g, *n2b;
+    float *Win_s = nullptr, *bin_s = nullptr;  // in_proj with the q rows pre-multiplied by 1/sqrt(d_head) (operand-image attention path)
   } tf[TF_LAYERS];
   const float *Wpost, *bpost;
   const float *Wt1, *bt1, *Wt2, *bt2, *Wt3, *bt3, *tln_g, *tln_b;
@@ -77,6 +78,8 @@ struct Workspace {
   float* S;  // [B,H,N,ldS] attention logits / probabilities (IPA and sequence transformer)
   uint8_t *qimg = nullptr, *kimg = nullptr, *vimg = nullptr, *pimg = nullptr;  // IPA operand images (gemm_img.cuh): Q', K', V' [B*H][JB][5][32 KB]; P [B*H][JB][2JB][32 KB]
   size_t qkv_img_bytes = 0, p_img_bytes = 0;
+  uint8_t *tf_qimg = nullptr, *tf_kimg = nullptr, *tf_vimg = nullptr, *tf_pimg = nullptr;  // same for the sequence transformer: [B*4][JB][2][32 KB], P [B*4][JB][2JB][32 KB]
+  size_t tf_qkv_img_bytes = 0, tf_p_img_bytes = 0;
   __half *z, *n_img;               // z: fp16 tile images [B][N][JB][32 KB]; n_img: [B][JB][32 KB]
   __half *f_img, *rel_tab;         // edge embedder: f_j k-block images [B][JB][16 KB]; fp16 relative-offset embedding table
   int JB;
@@ -124,6 +127,7 @@ struct fdpt_ctx {
   int use_graph = 1;
   int64_t stat_captures = 0;      // per-timestep graphs captured so far
   int64_t stat_sample_host_us = 0; // host time the last fdpt_sample call spent enqueueing
+  int tf_img = 1;     // sequence-transformer attention GEMMs from operand images (in_proj epilogue -> gemm_img); 0 = gemm_tc path (A/B switch)
   int ipa_img = 1;    // IPA attention GEMMs from operand images (gemm_img.cuh); 0 = fp32 operands split on the fly (gemm_tc.cuh; A/B switch)
   cudaStream_t own_stream = nullptr;   // the legacy default stream cannot be captured: fdpt_sample then runs on this stream,
   cudaEvent_t fence_in = nullptr, fence_out = nullptr;  // fenced against the caller's stream with these events
@@ -402,6 +406,10 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.p_img_bytes = (size_t)B * NH * JB * 2 * JB * tc::LT_STAGE_BYTES;
     w.qimg = carve<uint8_t>(p, w.qkv_img_bytes); w.kimg = carve<uint8_t>(p, w.qkv_img_bytes); w.vimg = carve<uint8_t>(p, w.qkv_img_bytes);
     w.pimg = carve<uint8_t>(p, w.p_img_bytes);
+    w.tf_qkv_img_bytes = (size_t)B * TF_H * JB * 2 * tc::LT_STAGE_BYTES;
+    w.tf_p_img_bytes = (size_t)B * TF_H * JB * 2 * JB * tc::LT_STAGE_BYTES;
+    w.tf_qimg = carve<uint8_t>(p, w.tf_qkv_img_bytes); w.tf_kimg = carve<uint8_t>(p, w.tf_qkv_img_bytes); w.tf_vimg = carve<uint8_t>(p, w.tf_qkv_img_bytes);
+    w.tf_pimg = carve<uint8_t>(p, w.tf_p_img_bytes);
     w.pred_rigids = carve<float>(p, M * 7); w.trans_score = carve<float>(p, M * 3); w.psi = carve<float>(p, M * 2);
     w.rig_cur = carve<float>(p, M * 7); w.rig_next = carve<float>(p, M * 7); w.sc_ca = carve<float>(p, M * 3);
     w.t_emb_b = carve<float>(p, (size_t)B * EMB); w.t32_b = carve<float>(p, B); w.bb_tmp = carve<float>(p, M * 15);
@@ -416,6 +424,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
   w.capB = B; w.capN = N; w.JB = (N + 127) / 128; w.ldS = (N + 3) & ~3;
   CK(cudaMemset(w.z, 0, sizeof(__half) * M * w.JB * 16384));  // padded rows (j >= N) of the tile images stay zero
   CK(cudaMemset(w.imgF, 0, 4 * w.img_bytes));
+  CK(cudaMemset(w.tf_qimg, 0, 3 * w.tf_qkv_img_bytes + w.tf_p_img_bytes));
   CK(cudaMemset(w.qimg, 0, 3 * w.qkv_img_bytes + w.p_img_bytes));  // padding rows / columns of the IPA operand images stay zero                  // rows >= M of the last m-tile of the chained operand images stay zero
   return FDPT_OK;
 }
@@ -427,7 +436,7 @@ struct Lin {
   // y[M,N] (ldc) = epi(x[M,K] (lda) @ W[N,K]^T (ldb))
   int operator()(const float* x, int lda, const float* W, int ldb, const float* bias, float* y, int ldc, long long M, int N, int K,
                  int relu = 0, const float* residual = nullptr, int ldr = 0, const float* rowmask = nullptr, int accumulate = 0,
-                 const __half* x_img = nullptr, __half* y_img = nullptr, const tc::IpaProjEpi* ipa = nullptr) const {
+                 const __half* x_img = nullptr, __half* y_img = nullptr, const tc::IpaProjEpi* ipa = nullptr, int epi = 1) const {
     // x_img / y_img: operand-image chaining between consecutive Linear layers (lin_tc.cuh); only valid on the packed lin_tc path
     if (ctx->gemm_tc && !accumulate && M > 0) {
       auto it = ctx->packed.find(std::make_tuple(W, ldb, N, K));
@@ -436,7 +445,21 @@ struct Lin {
         tc::LinTcArgs a;
         a.X = x; a.ldx = lda; a.M = (int)M; a.K = K; a.N = N; a.Wimg = pw.img; a.nkb = pw.nkb; a.n_tiles = pw.n_tiles;
         const int m_tiles = (int)((M + 127) / 128);
-        a.tiles_per_cta = std::min(pw.n_tiles, std::max(1, (m_tiles * pw.n_tiles + ctx->num_sms - 1) / ctx->num_sms));
+        {
+          // n-tiles per CTA: minimise waves x (tiles per CTA + fixed per-CTA cost in tile units).  The plain "spread over the SMs" rule
+          // left the 60-tile IPA projection with 154 CTAs on 148 SMs: a second wave of six CTAs doubled its time
+          int best = 1;
+          long long best_cost = -1;
+          for (int tpc = 1; tpc <= pw.n_tiles; ++tpc) {
+            const long long ctas = (long long)m_tiles * ((pw.n_tiles + tpc - 1) / tpc);
+            const long long cost = ((ctas + ctx->num_sms - 1) / ctx->num_sms) * (tpc + 2);
+            if (best_cost < 0 || cost < best_cost) {
+              best_cost = cost;
+              best = tpc;
+            }
+          }
+          a.tiles_per_cta = best;
+        }
         a.stg_cols = (ctx->dbg_flags & 1024) ? 32 : 16;  // 16-column staging patches: measured faster than 32 for every layer shape (profiles/r01_bench_lin_ablation.txt)
         a.units = std::min(8, (int)((ctx->max_smem_optin - tc::lin_tc_fixed_bytes(pw.nkb, a.stg_cols)) / tc::LT_UNIT_BYTES));
         a.bias = bias; a.relu = relu; a.rowmask = rowmask; a.residual = residual; a.ldr = ldr; a.Y = y; a.ldy = ldc;
@@ -461,7 +484,8 @@ struct Lin {
         if (ipa) {
           a.ipa = *ipa;
           a.dbg = nullptr;
-          e = x_img ? cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, false, true>, a) : cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, false, true>, a);
+          if (epi == 2) e = x_img ? cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, false, 2>, a) : cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, false, 2>, a);
+          else e = x_img ? cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, false, 1>, a) : cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, false, 1>, a);
         } else if (x_img && y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, true>, a);
         else if (x_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, false>, a);
         else if (y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, true>, a);
@@ -547,6 +571,25 @@ int run_embed(fdpt_ctx* ctx, int B, int N, const fdpt_feats* in, float* node_out
   return FDPT_OK;
 }
 
+int launch_img_gemm(fdpt_ctx* ctx, const tc::GemmImgArgs& g, cudaStream_t st) {
+  const long long tiles = (long long)g.m_tiles * g.n_tiles * g.batch;
+  if (tiles <= 0) return FDPT_OK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::min<long long>(ctx->num_sms, tiles));
+  cfg.blockDim = dim3(tc::GI_THREADS);
+  cfg.dynamicSmemBytes = tc::gemm_img_smem_bytes();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = tc::g_use_pdl;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_img_kernel, g);
+  ctx->launches++;
+  if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "gemm_img launch: %s", cudaGetErrorString(e));
+  return FDPT_OK;
+}
+
 // ---- IPA (kernels_ipa.cuh) ------------------------------------------------------------------------------------
 int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* z, const float* quats, const float* trans,
             const float* mask, float* out, int ldo, const float* residual, const float* outmask, cudaStream_t st,
@@ -572,23 +615,6 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     RET(lin(s, C_S, p.Wcat, C_S, p.bcat, w.proj, PROJ_W, M, PROJ_W, C_S, 0, nullptr, 0, nullptr, 0, s_img, nullptr));
   }
   std::unique_ptr<ProfScope> pattn(new ProfScope(ctx, FDPT_PROF_IPA_ATTN, st));  // every kernel that implements the attention itself: prep .. opt
-  auto launch_img_gemm = [&](const tc::GemmImgArgs& g) -> int {
-    const long long tiles = (long long)g.m_tiles * g.n_tiles * g.batch;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)std::min<long long>(ctx->num_sms, tiles));
-    cfg.blockDim = dim3(tc::GI_THREADS);
-    cfg.dynamicSmemBytes = tc::gemm_img_smem_bytes();
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = tc::g_use_pdl;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, tc::gemm_img_kernel, g);
-    ctx->launches++;
-    if (e != cudaSuccess) return fail(ctx, FDPT_ERR_CUDA, "gemm_img launch: %s", cudaGetErrorString(e));
-    return FDPT_OK;
-  };
   if (img) {
     // Q', K', V' as operand images (frames applied, s_qk and gamma folded into Q'), then S[b,h] = Q'_h K'_h^T + kbias on gemm_img
     IpaImgArgs ia;
@@ -604,7 +630,7 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     g.A = w.qimg; g.sA = per_bh; g.nkbA = IPA_IMG_KB; g.B = w.kimg; g.sB = per_bh; g.nkbB = IPA_IMG_KB; g.b_mn = 0; g.nkb = IPA_IMG_KB;
     g.M = N; g.N = N; g.m_tiles = w.JB; g.n_tiles = w.JB; g.batch = B * NH; g.batch2 = 1;
     g.bias = w.kn; g.sBias = N; g.C = w.S; g.ldc = w.ldS; g.sC1 = (long long)N * w.ldS; g.sC2 = 0;
-    RET(launch_img_gemm(g));
+    RET(launch_img_gemm(ctx, g, st));
   } else {
   ipa_prep_kernel<<<(unsigned)M, 256, 0, st>>>((int)M, w.proj, quats, trans, p.head_w, mask, N, w.kn);
   LAUNCH_CHECK();
@@ -636,7 +662,7 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     g.B = w.vimg; g.sB = (long long)w.JB * IPA_IMG_KB * tc::LT_STAGE_BYTES; g.nkbB = IPA_IMG_KB; g.b_mn = 1; g.nkb = (N + 63) / 64;
     g.M = N; g.N = V_W; g.m_tiles = w.JB; g.n_tiles = (V_W + 127) / 128; g.batch = B * NH; g.batch2 = NH;
     g.bias = nullptr; g.C = w.cat; g.ldc = CAT; g.sC1 = (long long)N * CAT; g.sC2 = V_W;
-    RET(launch_img_gemm(g));
+    RET(launch_img_gemm(ctx, g, st));
   } else {  // [o | o_pt (global frame)][b,:,h,:] = A_h [V_h | v_pts_h]  -> cat'[:, h*292 : (h+1)*292]
     GemmArgs g;
     g.A = w.S; g.lda = w.ldS; g.sA1 = (long long)NH * N * w.ldS; g.sA2 = (long long)N * w.ldS;
@@ -708,8 +734,28 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
 
 // 4-head attention of one encoder layer on qkv [M, 960] -> att_o [M, 320] (torch.nn.MultiheadAttention inside TransformerEncoderLayer,
 // ipa_pytorch.py:433-443; boolean key-padding semantics)
-int seq_attention(fdpt_ctx* ctx, int B, int N, const float* mask, cudaStream_t st) {
+int seq_attention(fdpt_ctx* ctx, int B, int N, const float* mask, cudaStream_t st, bool img = false) {
   Workspace& w = ctx->ws;
+  if (img) {
+    // the in_proj epilogue wrote Q (pre-scaled by 1/sqrt(d_head)), K, V as operand images: S = Q K^T, softmax -> P image, O = P V on gemm_img
+    const long long per_bh = (long long)w.JB * 2 * tc::LT_STAGE_BYTES;
+    tc::GemmImgArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = w.tf_qimg; g.sA = per_bh; g.nkbA = 2; g.B = w.tf_kimg; g.sB = per_bh; g.nkbB = 2; g.b_mn = 0; g.nkb = 2;
+    g.M = N; g.N = N; g.m_tiles = w.JB; g.n_tiles = w.JB; g.batch = B * TF_H; g.batch2 = 1;
+    g.bias = nullptr; g.C = w.S; g.ldc = w.ldS; g.sC1 = (long long)N * w.ldS; g.sC2 = 0;
+    RET(launch_img_gemm(ctx, g, st));
+    const long long rows = (long long)B * TF_H * N;
+    softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(w.S, rows, N, w.ldS, TF_H * N, 1.0f, mask, w.tf_pimg, w.JB);
+    LAUNCH_CHECK();
+    memset(&g, 0, sizeof(g));
+    g.A = w.tf_pimg; g.sA = (long long)w.JB * 2 * w.JB * tc::LT_STAGE_BYTES; g.nkbA = 2 * w.JB;
+    g.B = w.tf_vimg; g.sB = per_bh; g.nkbB = 2; g.b_mn = 1; g.nkb = (N + 63) / 64;
+    g.M = N; g.N = TF_DH; g.m_tiles = w.JB; g.n_tiles = 1; g.batch = B * TF_H; g.batch2 = TF_H;
+    g.bias = nullptr; g.C = w.att_o; g.ldc = TF_D; g.sC1 = (long long)N * TF_D; g.sC2 = TF_DH;
+    RET(launch_img_gemm(ctx, g, st));
+    return FDPT_OK;
+  }
     {
     GemmArgs g;  // S[b,h] = Q K^T  (rows padded to ldS floats: 16-byte aligned rows for the softmax and the P V operand loads)
     g.A = w.qkv; g.lda = 3 * TF_D; g.sA1 = (long long)N * 3 * TF_D; g.sA2 = TF_DH;
@@ -750,8 +796,16 @@ int run_seq_tfmr(fdpt_ctx* ctx, int blk, int B, int N, const float* mask, cudaSt
   RET(lin(w.node0, C_S, p.Wskip, C_S, p.bskip, w.tf_x + C_S, TF_D, M, C_SKIP, C_S));
   for (int l = 0; l < TF_LAYERS; ++l) {
     const auto& L = p.tf[l];
-    RET(lin(w.tf_x, TF_D, L.Win, TF_D, L.bin, w.qkv, 3 * TF_D, M, 3 * TF_D, TF_D));
-    RET(seq_attention(ctx, B, N, mask, st));
+    const bool img = ctx->gemm_tc && ctx->tf_img && L.Win_s;
+    if (img) {
+      tc::IpaProjEpi e;
+      memset(&e, 0, sizeof(e));
+      e.Qimg = w.tf_qimg; e.Kimg = w.tf_kimg; e.Vimg = w.tf_vimg; e.n_res = N; e.JB = w.JB;
+      RET(lin(w.tf_x, TF_D, L.Win_s, TF_D, L.bin_s, nullptr, 0, M, 3 * TF_D, TF_D, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, &e, 2));
+    } else {
+      RET(lin(w.tf_x, TF_D, L.Win, TF_D, L.bin, w.qkv, 3 * TF_D, M, 3 * TF_D, TF_D));
+    }
+    RET(seq_attention(ctx, B, N, mask, st, img));
     RET(lin(w.att_o, TF_D, L.Wo, TF_D, L.bo, w.tmpA, TF_D, M, TF_D, TF_D, 0, w.tf_x, TF_D));
     RET(layernorm<TF_D>(ctx, st, w.tmpA, w.tf_x, L.n1g, L.n1b, M, nullptr));
     if (chain) {  // linear1 hands its ReLU output to linear2 as a ready operand image (no fp32 round trip, no re-split)
@@ -924,8 +978,10 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaFuncSetAttribute(tc::lin_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
-  cudaFuncSetAttribute(tc::lin_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
-  cudaFuncSetAttribute(tc::lin_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tc_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::gemm_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::gemm_img_smem_bytes());
   // distogram bin edges: torch.linspace(min_bin, max_bin, num_bins) in float32 (framedipt/data/utils.py:546)
   float lower[NBINS];
@@ -961,6 +1017,10 @@ int fdpt_destroy(fdpt_ctx* ctx) {
     cudaFree(b.Wcat);
     cudaFree(b.bcat);
     cudaFree(b.Wout_perm);
+    for (auto& L : b.tf) {
+      cudaFree(L.Win_s);
+      cudaFree(L.bin_s);
+    }
     cudaFree(b.Wimgproj);
     cudaFree(b.bimgproj);
     cudaFree(b.imgWb);
@@ -1068,6 +1128,20 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
       L.Wo = P(q + ".self_attn.out_proj.weight"); L.bo = P(q + ".self_attn.out_proj.bias");
       L.W1 = P(q + ".linear1.weight"); L.b1 = P(q + ".linear1.bias"); L.W2 = P(q + ".linear2.weight"); L.b2 = P(q + ".linear2.bias");
       L.n1g = P(q + ".norm1.weight"); L.n1b = P(q + ".norm1.bias"); L.n2g = P(q + ".norm2.weight"); L.n2b = P(q + ".norm2.bias");
+      {  // in_proj with the 1/sqrt(d_head) of the attention logits folded into the q rows (rows 0 .. d_model-1)
+        std::vector<float> Wh((size_t)3 * TF_D * TF_D), bh(3 * TF_D);
+        CK(cudaMemcpy(Wh.data(), L.Win, Wh.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(bh.data(), L.bin, bh.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        const float sc = 1.0f / sqrtf((float)TF_DH);
+        for (int r = 0; r < TF_D; ++r) {
+          for (int k = 0; k < TF_D; ++k) Wh[(size_t)r * TF_D + k] *= sc;
+          bh[r] *= sc;
+        }
+        if (!L.Win_s) CK(cudaMalloc(&L.Win_s, Wh.size() * sizeof(float)));
+        if (!L.bin_s) CK(cudaMalloc(&L.bin_s, bh.size() * sizeof(float)));
+        CK(cudaMemcpy(L.Win_s, Wh.data(), Wh.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.bin_s, bh.data(), bh.size() * sizeof(float), cudaMemcpyHostToDevice));
+      }
     }
     p.Wpost = P(t + "post_tfmr_" + bs + ".weight"); p.bpost = P(t + "post_tfmr_" + bs + ".bias");
     const std::string nt = t + "node_transition_" + bs;
@@ -1110,6 +1184,7 @@ int fdpt_finalize_params(fdpt_ctx* ctx) {
       for (int l = 0; l < TF_LAYERS; ++l) {
         auto& L = p.tf[l];
         RET(pack_linear(ctx, L.Win, TF_D, 3 * TF_D, TF_D)); RET(pack_linear(ctx, L.Wo, TF_D, TF_D, TF_D));
+        RET(pack_linear(ctx, L.Win_s, TF_D, 3 * TF_D, TF_D));
         RET(pack_linear(ctx, L.W1, TF_D, TF_D, TF_D)); RET(pack_linear(ctx, L.W2, TF_D, TF_D, TF_D));
       }
       RET(pack_linear(ctx, p.Wpost, TF_D, C_S, TF_D));
@@ -1577,6 +1652,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
     case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; tc::g_use_pdl = (value & 16) ? 0 : 1; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
     case FDPT_OPT_ET_PAIR: return fail(ctx, FDPT_ERR_INVALID, "the CTA-pair EdgeTransition variant was removed (slower than the single-CTA kernel, DESIGN.md)");
+    case FDPT_OPT_TF_IMG: ctx->tf_img = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_IPA_IMG: ctx->ipa_img = value; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:
       if (value && !ctx->et_dbg) {

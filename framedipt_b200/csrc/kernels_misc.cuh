@@ -213,8 +213,11 @@ __global__ void compose_update_kernel(int M, const float* __restrict__ upd, cons
 // S[rows, N]: row = ((b*H + h)*N + i).  One warp per row, in place.
 // ------------------------------------------------------------------------------------------------
 // Rows have stride ld (multiple of 4, >= N, <= 1024); the row lives in registers between the single read and the single write.
+// Pimg != nullptr: the probabilities are written as the fp16 hi | lo operand image of the P.V GEMM (gemm_img.cuh) instead of in place:
+// [row / N = (b, h)][i-tile][2 JB k-blocks of 64 keys][hi 16 KB | lo 16 KB][128 rows][128 B]; the low part carries gemm_img's 2^11 scale.
+// Columns beyond ld are never written (the buffer is zeroed when the workspace is reserved).
 __global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long rows, int N, int ld, int rows_per_batch,
-                                                           float scale, const float* __restrict__ keymask) {
+                                                           float scale, const float* __restrict__ keymask, uint8_t* Pimg = nullptr, int JB = 0) {
   // key mask of the CTA's sample, staged once in shared memory (16-byte reads, no bank conflicts): read per element from global
   // memory it cost four L1 wavefronts per instruction, four times the traffic of the logits themselves.  The 8 rows of a CTA share
   // one sample whenever rows_per_batch is a multiple of 8; otherwise (odd N) the rows read the mask from global memory.
@@ -274,7 +277,22 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* S, long long r
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int c = lane + 32 * q;
-    if (c < nch) s4[c] = make_float4(v[q].x * inv, v[q].y * inv, v[q].z * inv, v[q].w * inv);
+    if (c >= nch) continue;
+    const float4 p = make_float4(v[q].x * inv, v[q].y * inv, v[q].z * inv, v[q].w * inv);
+    if (!Pimg) {
+      s4[c] = p;
+      continue;
+    }
+    const long long bh = row / N;
+    const int i = (int)(row - bh * N), j = 4 * c;
+    const __half2 h01 = __floats2half2_rn(p.x, p.y), h23 = __floats2half2_rn(p.z, p.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((p.x - f01.x) * 2048.f, (p.y - f01.y) * 2048.f);
+    const __half2 l23 = __floats2half2_rn((p.z - f23.x) * 2048.f, (p.w - f23.y) * 2048.f);
+    uint8_t* d = Pimg + (((size_t)bh * JB + (i >> 7)) * (2 * JB) + (j >> 6)) * (size_t)32768 + (i & 127) * 128 + (((((j & 63) >> 3)) ^ (i & 7)) << 4) +
+                 (j & 7) * 2;
+    *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    *reinterpret_cast<uint2*>(d + 16384) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   }
 }
 

@@ -67,8 +67,12 @@ struct LinTcArgs {
 
 // YIMG: the epilogue also (or only) writes the operand image of the next layer; a separate instantiation so that the plain kernel keeps
 // its register allocation
-template <bool XIMG, bool YIMG, bool EPI_IPA = false>
+// EPI: 0 plain epilogue; 1 fused IPA projection (IpaProjEpi above); 2 in_proj of a sequence-transformer layer: the 960 output columns
+// [q | k | v] x [4 heads x 80] are written as the per-(sample, head) Q / K / V operand images [b*4 + h][JB][2 k-blocks][32 KB] of the
+// attention GEMMs (gemm_img.cuh); 80 = 10 chunks of 8 columns, so every 16-byte chunk belongs to exactly one head
+template <bool XIMG, bool YIMG, int EPI = 0>
 __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
+  constexpr bool EPI_IPA = EPI == 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Aimg = smem;                                        // nkb x [hi 16 KB | lo 16 KB]
@@ -229,6 +233,30 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
         if (n0 + cb >= a.N || (a.dbg_flags & 1)) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
+        if constexpr (EPI == 2) {
+          const int r = (warp & 3) * 32 + lane;
+          const int m = m0 + r;
+          const int col0 = n0 + cb;
+          if (m < a.M) {
+            const int bsamp = m / a.ipa.n_res, i = m - bsamp * a.ipa.n_res;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const int cg = (col0 >> 3) + cc;          // 8-column chunk index, 0..119
+              if (cg >= 120) break;
+              const int kind = cg / 40, within = cg - kind * 40, h = within / 10, c = within - h * 10;
+              float y[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = v[8 * cc + e] + __ldg(a.bias + col0 + 8 * cc + e);
+              uint4 hi, lo;
+              split8(make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), hi, lo);
+              uint8_t* img = kind == 0 ? a.ipa.Qimg : (kind == 1 ? a.ipa.Kimg : a.ipa.Vimg);
+              uint8_t* d = img + (((size_t)(bsamp * 4 + h) * a.ipa.JB + (i >> 7)) * 2 + (c >> 3)) * (size_t)LT_STAGE_BYTES + sw128_chunk_off(i & 127, c & 7);
+              *reinterpret_cast<uint4*>(d) = hi;
+              *reinterpret_cast<uint4*>(d + 16384) = lo;
+            }
+          }
+          continue;
+        }
         if constexpr (EPI_IPA) {
           const int r = (warp & 3) * 32 + lane;
           const int m = m0 + r;

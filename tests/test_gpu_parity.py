@@ -444,10 +444,14 @@ def test_ipa_operand_image_modes_agree(model):
         for mode in (1, 2, 0):
             ctx.set_option(7, mode)
             outs[mode] = {k: v.cpu().numpy() for k, v in m(feats).items()}
+        ctx.set_option(7, 1)
+        ctx.set_option(8, 0)  # sequence-transformer attention on the fp32-operand GEMM path (FDPT_OPT_TF_IMG = 0)
+        outs["tf0"] = {k: v.cpu().numpy() for k, v in m(feats).items()}
     finally:
         ctx.set_option(7, 1)
+        ctx.set_option(8, 1)
     valid = feats["res_mask"].cpu().numpy().astype(bool)
-    for mode in (2, 0):
+    for mode in (2, 0, "tf0"):
         d = np.abs(outs[mode]["rigids"][..., 4:] - outs[1]["rigids"][..., 4:])[valid].max()
         da = rot_angle_between(outs[mode]["rigids"][..., :4], outs[1]["rigids"][..., :4])[valid].max()
         print(f"IPA image mode {mode} vs 1: |dtrans| {d:.2e} A, rot {da:.2e} rad")

@@ -71,9 +71,13 @@ def test_cached_score_table_vs_reference(g, golden_dir, state_dict, tmp_path):
     f1["t"] = torch.tensor([0.37, 0.81]).cuda()
     out = m(f1)
     assert np.abs(out["rigids"].cpu().numpy()[..., 4:] - g["cached_fwd_rigids"][..., 4:]).max() < 1e-4
-    # inside a forward the rotation vector itself carries the network's error (1e-5 rad class): the same 2e-3 relative bound as the series
-    # score of the other forward tests, with a few bucket flips of the table index allowed
-    assert _lookup_mismatch(out["rot_score"].cpu().numpy(), g["cached_fwd_rot_score"], 2e-3) < 0.05
+    # inside a forward the rotation vector carries the network's error (1e-5 rad class) and most residues are fixed (omega ~ 1e-6: the
+    # direction v / omega is rounding noise there): same criterion as the series score of the other forward tests -- error relative to the
+    # largest score of the tensor -- with a few bucket flips of the table index allowed
+    rs, rs_ref = out["rot_score"].cpu().numpy(), g["cached_fwd_rot_score"]
+    frac_bad = float((np.abs(rs - rs_ref).max(-1) > 2e-3 * np.abs(rs_ref).max()).mean())
+    print(f"use_cached_score forward: {frac_bad:.2%} of the residues off by more than 2e-3 of max|score|")
+    assert frac_bad < 0.05
     traj = inference_fn(m, diffuser, feats, num_t=6, min_t=0.01, aux_traj=True, noise_scale=0.1, inpainting=True, input_aatype=True,
                         noise=g["cached_noise"])
     r = bb_rmsd(traj["prot_traj"][0][:, :, :5], g["cached_prot_traj"][0])
