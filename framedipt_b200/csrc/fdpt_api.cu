@@ -56,6 +56,7 @@ struct BlockParams {
   // projection in operand-image column order (lin_tc.cuh IpaProjEpi): 24 blocks of 320 rows = [operand q|k|v][head][256 scalar | points | 0],
   // q's scalar rows pre-multiplied by sqrt(1/(3 C))
   float *Wimgproj = nullptr, *bimgproj = nullptr;
+  __half* imgWout = nullptr;  // linear_out.weight (cat' column order) as split operand image [2 n-tiles][42 k-blocks][hi|lo][128][128 B]
   __half* imgWb = nullptr;
 };
 
@@ -78,6 +79,8 @@ struct Workspace {
   float* S;  // [B,H,N,ldS] attention logits / probabilities (IPA and sequence transformer)
   uint8_t *qimg = nullptr, *kimg = nullptr, *vimg = nullptr, *pimg = nullptr;  // IPA operand images (gemm_img.cuh): Q', K', V' [B*H][JB][5][32 KB]; P [B*H][JB][2JB][32 KB]
   size_t qkv_img_bytes = 0, p_img_bytes = 0;
+  uint8_t* cat_img = nullptr;  // concat row of the IPA as operand image [m-tile][42 k-blocks][32 KB] (A operand of linear_out on gemm_img)
+  size_t cat_img_bytes = 0;
   uint8_t *tf_qimg = nullptr, *tf_kimg = nullptr, *tf_vimg = nullptr, *tf_pimg = nullptr;  // same for the sequence transformer: [B*4][JB][2][32 KB], P [B*4][JB][2JB][32 KB]
   size_t tf_qkv_img_bytes = 0, tf_p_img_bytes = 0;
   __half *z, *n_img;               // z: fp16 tile images [B][N][JB][32 KB]; n_img: [B][JB][32 KB]
@@ -359,6 +362,15 @@ int pack_ipa_params(fdpt_ctx* ctx, BlockParams& p) {
     CK(cudaMemcpy(p.Wimgproj, W2.data(), W2.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p.bimgproj, b2.data(), b2.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
+  {
+    constexpr int NKB = CAT / 64, NT = (C_S + 127) / 128;
+    if (!p.Wout_perm) CK(cudaMalloc(&p.Wout_perm, Wop.size() * sizeof(float)));
+    CK(cudaMemcpy(p.Wout_perm, Wop.data(), Wop.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (!p.imgWout) CK(cudaMalloc(&p.imgWout, (size_t)NT * NKB * tc::LT_STAGE_BYTES));
+    const long long chunks = (long long)NT * NKB * 128 * 8;
+    tc::pack_weight_split_kernel<<<(unsigned)((chunks + 255) / 256), 256>>>(p.Wout_perm, CAT, C_S, CAT, NKB, NT, p.imgWout);
+    CK(cudaGetLastError());
+  }
   if (!p.Wcat) CK(cudaMalloc(&p.Wcat, Wcat.size() * sizeof(float)));
   if (!p.bcat) CK(cudaMalloc(&p.bcat, bcat.size() * sizeof(float)));
   if (!p.Wout_perm) CK(cudaMalloc(&p.Wout_perm, Wop.size() * sizeof(float)));
@@ -406,6 +418,8 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
     w.p_img_bytes = (size_t)B * NH * JB * 2 * JB * tc::LT_STAGE_BYTES;
     w.qimg = carve<uint8_t>(p, w.qkv_img_bytes); w.kimg = carve<uint8_t>(p, w.qkv_img_bytes); w.vimg = carve<uint8_t>(p, w.qkv_img_bytes);
     w.pimg = carve<uint8_t>(p, w.p_img_bytes);
+    w.cat_img_bytes = ((M + 127) / 128) * (size_t)(CAT / 64) * tc::LT_STAGE_BYTES;
+    w.cat_img = carve<uint8_t>(p, w.cat_img_bytes);
     w.tf_qkv_img_bytes = (size_t)B * TF_H * JB * 2 * tc::LT_STAGE_BYTES;
     w.tf_p_img_bytes = (size_t)B * TF_H * JB * 2 * JB * tc::LT_STAGE_BYTES;
     w.tf_qimg = carve<uint8_t>(p, w.tf_qkv_img_bytes); w.tf_kimg = carve<uint8_t>(p, w.tf_qkv_img_bytes); w.tf_vimg = carve<uint8_t>(p, w.tf_qkv_img_bytes);
@@ -424,6 +438,7 @@ int reserve_ws(fdpt_ctx* ctx, int B, int N) {
   w.capB = B; w.capN = N; w.JB = (N + 127) / 128; w.ldS = (N + 3) & ~3;
   CK(cudaMemset(w.z, 0, sizeof(__half) * M * w.JB * 16384));  // padded rows (j >= N) of the tile images stay zero
   CK(cudaMemset(w.imgF, 0, 4 * w.img_bytes));
+  CK(cudaMemset(w.cat_img, 0, w.cat_img_bytes));  // rows >= M of the last tile stay zero
   CK(cudaMemset(w.tf_qimg, 0, 3 * w.tf_qkv_img_bytes + w.tf_p_img_bytes));
   CK(cudaMemset(w.qimg, 0, 3 * w.qkv_img_bytes + w.p_img_bytes));  // padding rows / columns of the IPA operand images stay zero                  // rows >= M of the last m-tile of the chained operand images stay zero
   return FDPT_OK;
@@ -672,10 +687,30 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     CK(gemm_dispatch(ctx, g, false, B * NH, st));
     ctx->launches++;
   }
+  const int OUT_SPLIT = (ctx->dbg_flags & 16384) ? 2 : 3;  // K = 2688 = 42 k-blocks = 3 x 14 (debug flag 16384: 2 x 21)
+  const bool split_ok = ln_out && ctx->gemm_tc && !(ctx->dbg_flags & 256) && (CAT / 64) % OUT_SPLIT == 0 && w.tmpB - w.tmpA == w.tmpC - w.tmpB;
+  if (img && split_ok && ctx->ipa_img != 3) {
+    // inverse frames + norms AND the operand image of the concat row in one pass; linear_out then multiplies two ready images
+    // (3-way split-K over the 42 k-blocks), the reduce is folded into the LayerNorm kernel as before
+    ipa_opt_img_kernel<<<(unsigned)M, 256, 0, st>>>((int)M, w.cat, quats, trans, w.cat_img);
+    LAUNCH_CHECK();
+    pattn.reset();
+    tc::GemmImgArgs g;
+    memset(&g, 0, sizeof(g));
+    const int nkb_all = CAT / 64, nkb = nkb_all / OUT_SPLIT;
+    g.A = w.cat_img; g.sA = (long long)nkb * tc::LT_STAGE_BYTES; g.nkbA = nkb_all;
+    g.B = reinterpret_cast<const uint8_t*>(p.imgWout); g.sB = (long long)nkb * tc::LT_STAGE_BYTES; g.nkbB = nkb_all; g.b_mn = 0; g.nkb = nkb;
+    g.M = (int)M; g.N = C_S; g.m_tiles = (int)((M + 127) / 128); g.n_tiles = (C_S + 127) / 128; g.batch = OUT_SPLIT; g.batch2 = 1;
+    g.bias = nullptr; g.C = w.tmpA; g.ldc = C_S; g.sC1 = w.tmpB - w.tmpA; g.sC2 = 0;
+    RET(launch_img_gemm(ctx, g, st));
+    sumk_layernorm_kernel<C_S><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(w.tmpA, w.tmpB - w.tmpA, OUT_SPLIT, p.bout, residual, outmask, ln_out, ln_g,
+                                                                        ln_b, M);
+    LAUNCH_CHECK();
+    return FDPT_OK;
+  }
   ipa_opt_kernel<<<(unsigned)M, NH * PV, 0, st>>>((int)M, w.cat, quats, trans);
   LAUNCH_CHECK();
   pattn.reset();
-  const int OUT_SPLIT = (ctx->dbg_flags & 16384) ? 2 : 3;  // K = 2688 = 42 k-blocks = 3 x 14 (debug flag 16384: 2 x 21)
   if (ln_out && ctx->gemm_tc && !(ctx->dbg_flags & 256) && (CAT / 64) % OUT_SPLIT == 0 && w.tmpB - w.tmpA == w.tmpC - w.tmpB) {
     // linear_out as a 3-way split-K GEMM (one long serial k-loop per CTA otherwise: 88 CTAs x 42 k-blocks; split: 264 CTAs x 14); the
     // partial products are summed, biased, masked and added to the residual inside the LayerNorm kernel that follows
@@ -1021,6 +1056,7 @@ int fdpt_destroy(fdpt_ctx* ctx) {
       cudaFree(L.Win_s);
       cudaFree(L.bin_s);
     }
+    cudaFree(b.imgWout);
     cudaFree(b.Wimgproj);
     cudaFree(b.bimgproj);
     cudaFree(b.imgWb);

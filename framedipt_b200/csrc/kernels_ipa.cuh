@@ -208,6 +208,50 @@ __global__ void __launch_bounds__(96) ipa_opt_kernel(int M, float* __restrict__ 
   cat[(long long)m * CAT + CATP_NRM + h * PV + p] = sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f);
 }
 
+// ipa_opt + operand image of the concat row in one pass (gemm_img.cuh consumes it as the A operand of linear_out, K = 2688 = 42 k-blocks):
+// the row of residue m is staged in shared memory, the point outputs are moved to the local frame and their norms written exactly as
+// ipa_opt_kernel does, then the whole row is split into fp16 hi | lo 16-byte chunks of the image
+// [128-row tile of the flattened residue index][42 k-blocks][hi 16 KB | lo 16 KB][128 rows][128 B swizzled].
+__global__ void __launch_bounds__(256) ipa_opt_img_kernel(int M, const float* __restrict__ cat, const float* __restrict__ quats,
+                                                          const float* __restrict__ trans, uint8_t* __restrict__ img) {
+  const int m = blockIdx.x, tid = threadIdx.x;
+  __shared__ __align__(16) float row[CAT];
+  __shared__ float R[9], t[3];
+  const float4* src = reinterpret_cast<const float4*>(cat + (long long)m * CAT);
+  for (int k = tid; k < CAT / 4; k += 256) reinterpret_cast<float4*>(row)[k] = src[k];
+  if (tid == 0) {
+    float q[4] = {quats[m * 4], quats[m * 4 + 1], quats[m * 4 + 2], quats[m * 4 + 3]};
+    quat_to_rot(q, R);
+    t[0] = trans[m * 3];
+    t[1] = trans[m * 3 + 1];
+    t[2] = trans[m * 3 + 2];
+  }
+  __syncthreads();
+  if (tid < NH * PV) {
+    const int h = tid / PV, p = tid % PV;
+    float* slot = row + h * V_W + C_HID;
+    const float x = slot[p] - t[0], y = slot[PV + p] - t[1], z = slot[2 * PV + p] - t[2];
+    const float lx = R[0] * x + R[3] * y + R[6] * z;
+    const float ly = R[1] * x + R[4] * y + R[7] * z;
+    const float lz = R[2] * x + R[5] * y + R[8] * z;
+    slot[p] = lx;
+    slot[PV + p] = ly;
+    slot[2 * PV + p] = lz;
+    row[CATP_NRM + h * PV + p] = sqrtf(lx * lx + ly * ly + lz * lz + 1e-8f);
+  }
+  __syncthreads();
+  uint8_t* tile = img + (size_t)(m >> 7) * (CAT / 64) * tc::LT_STAGE_BYTES;
+  const int r = m & 127;
+  for (int c = tid; c < CAT / 8; c += 256) {
+    const float4 x0 = reinterpret_cast<const float4*>(row)[2 * c], x1 = reinterpret_cast<const float4*>(row)[2 * c + 1];
+    uint4 hi, lo;
+    tc::split8(x0, x1, hi, lo);
+    uint8_t* d = tile + (size_t)(c >> 3) * tc::LT_STAGE_BYTES + tc::sw128_chunk_off(r, c & 7);
+    *reinterpret_cast<uint4*>(d) = hi;
+    *reinterpret_cast<uint4*>(d + 16384) = lo;
+  }
+}
+
 // 2^x for x <= 0 with the SFU instruction (2 ulp; results below the normal range flush to zero, which is what a softmax wants)
 FDPT_DEVINL float ex2_approx(float x) {
   float y;

@@ -245,7 +245,8 @@ enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDP
        FDPT_OPT_TF_IMG = 8 /* 1 (default): the sequence transformer's attention GEMMs multiply operand images written by the in_proj
                               epilogue / the row softmax (gemm_img.cuh); 0: fp32 operands split on the fly (gemm_tc.cuh).  A/B switch */,
        FDPT_OPT_IPA_IMG = 7 /* 1 (default): the two batched attention GEMMs of the IPA multiply ready operand images (gemm_img.cuh)
-                               written by the projection GEMM's own epilogue; 2: same, images written by a separate prep kernel;
+                               written by the projection GEMM's own epilogue, and linear_out multiplies the concat row as an image
+                               (ipa_opt_img_kernel); 3: same without the linear_out part; 2: images written by a separate prep kernel;
                                0: fp32 operands split on the fly (gemm_tc.cuh).  A/B switch */ };
 int fdpt_set_option(fdpt_ctx* ctx, int option, int value);
 /* clock64 timeline of CTA 0 of the last EdgeTransition kernel ([tile][48] stamps; profiling aid, needs FDPT_OPT_ET_TIMELINE) */
