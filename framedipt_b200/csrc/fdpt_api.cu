@@ -25,6 +25,7 @@
 #include "gemm_tc.cuh"
 #include "lin_tc.cuh"
 #include "gemm_img.cuh"
+#include "lin_tcw.cuh"
 #include "backbone_tables.inc"
 
 using namespace fdpt;
@@ -130,6 +131,7 @@ struct fdpt_ctx {
   int use_graph = 1;
   int64_t stat_captures = 0;      // per-timestep graphs captured so far
   int64_t stat_sample_host_us = 0; // host time the last fdpt_sample call spent enqueueing
+  int lin_wres = 1;   // Linear layers whose CTAs own one n-tile keep the whole weight panel resident and stream the activation (lin_tcw.cuh); 0 = lin_tc
   int tf_img = 1;     // sequence-transformer attention GEMMs from operand images (in_proj epilogue -> gemm_img); 0 = gemm_tc path (A/B switch)
   int ipa_img = 1;    // IPA attention GEMMs from operand images (gemm_img.cuh); 0 = fp32 operands split on the fly (gemm_tc.cuh; A/B switch)
   cudaStream_t own_stream = nullptr;   // the legacy default stream cannot be captured: fdpt_sample then runs on this stream,
@@ -496,7 +498,14 @@ struct Lin {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cudaError_t e;
-        if (ipa) {
+        if (!ipa && ctx->lin_wres && a.tiles_per_cta == 1 && !(ctx->dbg_flags & (1 | 2 | 512))) {
+          // one n-tile per CTA: weight-resident variant (the whole panel is prefetched under the predecessor kernel's tail)
+          cfg.dynamicSmemBytes = tc::lin_tcw_smem_bytes(pw.nkb);
+          if (x_img && y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tcw_kernel<true, true>, a);
+          else if (x_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tcw_kernel<true, false>, a);
+          else if (y_img) e = cudaLaunchKernelEx(&cfg, tc::lin_tcw_kernel<false, true>, a);
+          else e = cudaLaunchKernelEx(&cfg, tc::lin_tcw_kernel<false, false>, a);
+        } else if (ipa) {
           a.ipa = *ipa;
           a.dbg = nullptr;
           if (epi == 2) e = x_img ? cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<true, false, 2>, a) : cudaLaunchKernelEx(&cfg, tc::lin_tc_kernel<false, false, 2>, a);
@@ -1013,6 +1022,10 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaFuncSetAttribute(tc::lin_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tcw_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tcw_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tcw_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(tc::lin_tcw_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::lin_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
@@ -1688,6 +1701,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
     case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; tc::g_use_pdl = (value & 16) ? 0 : 1; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
     case FDPT_OPT_ET_PAIR: return fail(ctx, FDPT_ERR_INVALID, "the CTA-pair EdgeTransition variant was removed (slower than the single-CTA kernel, DESIGN.md)");
+    case FDPT_OPT_LIN_WRES: ctx->lin_wres = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_TF_IMG: ctx->tf_img = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_IPA_IMG: ctx->ipa_img = value; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_ET_TIMELINE:

@@ -242,6 +242,8 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition) */
 enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
        FDPT_OPT_ET_PAIR = 5 /* retired: the cta_group::2 EdgeTransition variant of round 1 was slower (1.3 vs 1.0 ms) and has been removed */,
+       FDPT_OPT_LIN_WRES = 9 /* 1 (default): Linear layers whose CTAs own a single n-tile run the weight-resident kernel (lin_tcw.cuh: whole
+                                weight panel prefetched under the predecessor's tail, activation streamed); 0: lin_tc.  A/B switch */,
        FDPT_OPT_TF_IMG = 8 /* 1 (default): the sequence transformer's attention GEMMs multiply operand images written by the in_proj
                               epilogue / the row softmax (gemm_img.cuh); 0: fp32 operands split on the fly (gemm_tc.cuh).  A/B switch */,
        FDPT_OPT_IPA_IMG = 7 /* 1 (default): the two batched attention GEMMs of the IPA multiply ready operand images (gemm_img.cuh)

