@@ -187,6 +187,48 @@ def cpu_port_rate(wl, steps: int, warmup: int, threads: int):
     return n * steps / el, el / steps
 
 
+def eager_gpu_rate(wl, B: int, steps: int, warmup: int, dev):
+    """Secondary baseline (recommended): what a user of the reference gets on this box with `use_gpu: true` -- the same
+    eager PyTorch modules on the B200 (fp32, TF32 off), state round-tripping to the host every step for the numpy reverse step
+    (experiments/utils.py:292-412).  The reference checkout does not exist on the GPU box, so its restatement (oracle port: the same
+    torch ops in the same order) is what runs; factory calls inside it are routed to the GPU with torch.device(...)."""
+    import torch
+    from framedipt_b200 import SE3Diffuser, synthetic
+    from framedipt_b200.config import default_conf
+    from framedipt_b200.params import synthetic_state_dict
+    from oracle import framedipt_oracle as orc
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    diffuser = SE3Diffuser(default_conf().diffuser)
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict(0, with_aatype=not wl.de_novo).items()}
+    np.random.seed(123)
+    feats = {k: v.to(dev) for k, v in synthetic.make_features(wl, diffuser, seed=0, batch=B).items()}
+    n = wl.n_res
+    sched_t = np.linspace(wl.min_t, 1.0, wl.num_t)[::-1]
+    dt = 1 / wl.num_t
+    noise = np.random.normal(size=(warmup + steps, 2, B, n, 3))
+    dm = ((1 - feats["fixed_mask"]) * feats["res_mask"]).cpu().numpy().astype(np.float64)
+    t_start = None
+    with torch.no_grad(), torch.device(dev):
+        for s in range(warmup + steps):
+            if s == warmup:
+                torch.cuda.synchronize(dev)
+                t_start = time.perf_counter()
+            t = float(sched_t[s])
+            feats["t"] = t * torch.ones(B)
+            out = orc.score_network_forward(sd, feats, inpainting=not wl.de_novo, input_aatype=not wl.de_novo)
+            rig = out["rigids"].float()
+            feats["sc_ca_t"] = rig[..., 4:]
+            R1, T1 = orc.reverse_step(feats["rigids_t"].float().cpu().numpy(), out["rot_score"].cpu().numpy().astype(np.float64),
+                                      out["trans_score"].float().cpu().numpy(), dm, t, dt, noise[s, 0], noise[s, 1], noise_scale=wl.noise_scale)
+            q1 = orc.rot_to_quat_np(R1.astype(np.float64)).astype(np.float32)
+            feats["rigids_t"] = torch.tensor(np.concatenate([q1, T1], -1))
+        torch.cuda.synchronize(dev)
+    el = time.perf_counter() - t_start
+    return B * n * steps / el, el / steps
+
+
 DTYPE = "mixed: fp16-operand/fp32-accumulate tcgen05 on the pair side (z stored fp16), 2-term fp16 split (fp32-class) on the node side, fp32 SIMT elsewhere, fp64 SDE step"
 
 
@@ -503,6 +545,17 @@ def main():
         if extra:
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
+            try:  # secondary baseline: eager PyTorch on this GPU (the reference's `use_gpu: true` path), B = 1 like the reference and the full batch
+                line["eager_gpu_baseline"] = {}
+                del st, pf, noise_dev
+                torch.cuda.empty_cache()
+                for bb in (1, B):
+                    r_e, s_e = eager_gpu_rate(wl, bb, 3, 1, dev)
+                    line["eager_gpu_baseline"][f"B={bb}"] = {"value": r_e, "unit": UNIT, "ms_per_step": s_e * 1e3}
+                line["eager_gpu_baseline"]["what"] = ("oracle port (the reference's torch ops, eager, fp32 with TF32 off) on the same B200, host numpy "
+                                                       "reverse step every timestep like experiments/utils.py:292-412; 3 timesteps after 1 warm-up")
+            except Exception as e:
+                line["eager_gpu_baseline"] = {"error": repr(e)[:300]}
             rate, sps = cpu_port_rate(wl, args.cpu_steps, 1, cores)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"oracle port, B=1 of the batch, N_res={N}, {args.cpu_steps} timesteps after 1 warm-up ({sps:.2f} s/step)"}
