@@ -10,8 +10,9 @@
 //   GEMM1  D1[128 x 384] = [z | n_j] (K=256) . W1cat^T          W1cat = [W1[:, 0:128] | W1[:, 256:384]]
 //   E1     h1 = relu(D1 + U_i)                      -> fp16, 128-column chunks in shared memory
 //   GEMM2  D2[128 x 384] += h1_chunk(c) . W2[:, chunk c]^T       (accumulated over the three K chunks as they appear)
-//   E2     r2 = relu(D2 + b2)                       -> fp16 chunks
-//   GEMM3  D3[128 x 128] = [z | n_j] . W3cat[:, 384:640]^T + sum_c r2_chunk(c) . W3cat[:, chunk c]^T
+//   E2     r2 = relu(D2 + b2)                       -> fp16, written back IN PLACE into D2's tensor-memory columns (tcgen05.st: two
+//                                                      K elements per 32-bit column) = the A operand of GEMM3's partial products
+//   GEMM3  D3[128 x 128] = [z | n_j] . W3cat[:, 384:640]^T + sum_c r2_chunk(c) . W3cat[:, chunk c]^T      (A from tensor memory)
 //                                                     W3cat = [Wf | Wf[:, 0:128] | Wf[:, 256:384]]
 //   E3     z' = LN(D3 + Pf_i) * mask                -> fp16 tile image, bulk store
 //
@@ -24,6 +25,7 @@
 // All operands fp16 (10-bit mantissa = TF32 precision, which the pair side tolerates: SURVEY §7 hard part 1), fp32 accumulate.
 #pragma once
 #include "tc_common.cuh"
+#include "tmem_a_test.cuh"
 
 namespace fdpt {
 namespace tc {
@@ -46,6 +48,7 @@ struct EtArgs {
   const __half* W2;             // image [6 kb][384][128 B]
   const __half* W3cat;          // image [10 kb][128][128 B]
   long long tiles;              // B*N*JB
+  int r2_tmem;                  // 1: r2 is handed to GEMM3 through tensor memory (A operand from TMEM); 0: through the shared-memory chunk buffers
   long long* dbg;               // optional clock64 timeline of CTA 0 (bring-up / profiling aid): [tile][48] stamps, or nullptr
 };
 
@@ -83,7 +86,8 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   uint64_t* vec_full = d2_empty + 1;         // [2]
   uint64_t* vec_free = vec_full + 2;         // [2]
   uint64_t* stg_full = vec_free + 2;         // [1] all workers have written their part of the output tile into BUF[1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_full + 1);
+  uint64_t* r2_full = stg_full + 1;          // [3] chunk c of r2 is in tensor memory (fp16, A operand of GEMM3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r2_full + 3);
   float* Ui_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][384]
   float* Pf_s = Ui_s + 2 * 384;                            // [2][128]
   float* b2_s = Pf_s + 2 * 128;                            // [384]
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, ET_WORKERS);
     mbar_init(stg_full, ET_WORKERS);
+    for (int c = 0; c < 3; ++c) mbar_init(&r2_full[c], ET_WORKERS);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&vec_full[s], 32);
       mbar_init(&vec_free[s], ET_WORKERS);
@@ -276,14 +281,33 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
         umma_commit(&az_empty[zs]);
         ET_TS(7);
+        // G3 partial products: A = r2 chunk c straight from tensor memory (the workers wrote it in place over D2: worker group g's 64
+        // K-elements of the chunk sit packed in the 32 columns D2 + 128 c + 64 g), B = W3cat k-block 2c + g from the weight ring
         for (int c = 0; c < 3; ++c) {
-          const int b = c & 1;
-          mbar_wait(&buf_full[b], bf[b] & 1);
-          ++bf[b];
+          if (!a.r2_tmem) {
+            const int b = c & 1;
+            mbar_wait(&buf_full[b], bf[b] & 1);
+            ++bf[b];
+            tc_fence_after();
+            ET_TS(11 + c);
+            for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, DS, false);
+            if (c != 1) umma_commit(&buf_free[b]);  // BUF[1] becomes the output staging buffer: released by worker thread 0
+            ET_TS(8 + c);
+            continue;
+          }
+          mbar_wait(&r2_full[c], (uint32_t)(t - t_begin) & 1);
           tc_fence_after();
           ET_TS(11 + c);
-          for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, DS, false);
-          if (c != 1) umma_commit(&buf_free[b]);  // BUF[1] becomes the output staging buffer: released by worker thread 0
+          for (int kb = 0; kb < 2; ++kb) {
+            const int s = wit % ET_WSTAGES;
+            mbar_wait(&w_full[s], (wit / ET_WSTAGES) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(WST + s * ET_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ts(DS, D2 + c * 128 + kb * 64 + 8 * k, make_sw128_desc(b_addr + k * 32), idesc, 1u);
+            umma_commit(&w_empty[s]);
+            ++wit;
+          }
           ET_TS(8 + c);
         }
         umma_commit(ds_full);
@@ -356,16 +380,30 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       if (threadIdx.x == 0) ET_TS(26);
       for (int c = 0; c < 3; ++c) {
         load_half(D2 + c * 128, v);
-        if (c == 2) {
-          tc_fence_before();
-          mbar_arrive(d2_empty);
-        }
+        if (!a.r2_tmem) {
+          if (c == 2) {
+            tc_fence_before();
+            mbar_arrive(d2_empty);
+          }
 #pragma unroll
-        for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + b2_s[c * 128 + cg + n], 0.f);
-        wait_free(c & 1);
-        store_half(BUF + (c & 1) * ET_TILE_BYTES, v);
-        fence_proxy_async();
-        mbar_arrive(&buf_full[c & 1]);
+          for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + b2_s[c * 128 + cg + n], 0.f);
+          wait_free(c & 1);
+          store_half(BUF + (c & 1) * ET_TILE_BYTES, v);
+          fence_proxy_async();
+          mbar_arrive(&buf_full[c & 1]);
+          if (threadIdx.x == 0) ET_TS(27 + c);
+          continue;
+        }
+        uint32_t pk[32];
+#pragma unroll
+        for (int n = 0; n < 32; ++n)
+          pk[n] = pack_half2(fmaxf(v[2 * n] + b2_s[c * 128 + cg + 2 * n], 0.f), fmaxf(v[2 * n + 1] + b2_s[c * 128 + cg + 2 * n + 1], 0.f));
+        // in place: this thread's own 64 fp32 columns of the chunk become 32 packed fp16 columns (the other group's range is disjoint)
+        tmem_st32(D2 + lane_base + c * 128 + cg, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&r2_full[c]);
+        if (c == 2) mbar_arrive(d2_empty);
         if (threadIdx.x == 0) ET_TS(27 + c);
       }
       // ---- E3: LayerNorm + mask -> fp16 tile image -> bulk store staged in BUF[1] (free: its last reader, G3 partial 1, completed
@@ -414,6 +452,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       for (int n = 0; n < 64; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
       mbar_arrive(&vec_free[vbuf]);
       if (threadIdx.x == 0) ET_TS(31);
+      if (a.r2_tmem) wait_free(1);  // BUF[1]'s last reader was G2(1) (h1 chunk 1); its release is consumed here (already complete: D3 is)
       store_half(BUF + ET_TILE_BYTES, v);
       fence_proxy_async();
       mbar_arrive(stg_full);
@@ -434,7 +473,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
 }
 
 inline size_t et_smem_bytes() {
-  return 1024 + 5 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 40 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 512) * 4 + 64 + 32;
+  return 1024 + 5 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 44 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 512) * 4 + 64 + 32;
 }
 
 // ---- layout helpers --------------------------------------------------------------------------------------------------

@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         L.fdpt_rot_score_idx.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
         L.fdpt_sample_ref.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.fdpt_tmem_a_selftest.argtypes = [C.c_void_p] * 5
         L.fdpt_seq_tfmr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
         L.fdpt_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_void_p]
@@ -447,6 +448,12 @@ class Context:
                                        _ptr(draws), int(philox_seed) & 0xFFFFFFFFFFFFFFFF, int(diffuse_rot), int(diffuse_trans), _ptr(out),
                                        self.stream))
         return out
+
+    def tmem_a_selftest(self, a, b):
+        """d = fp16(a[128,64]) @ fp16(b[128,64])^T through tcgen05.mma with A in tensor memory (bring-up unit)."""
+        d = torch.empty(128, 128, device=self.device)
+        self._ck(lib().fdpt_tmem_a_selftest(self._h, _ptr(a), _ptr(b), _ptr(d), self.stream))
+        return d
 
     def seq_tfmr(self, blk, node, node0, mask):
         """(encoder output [B,N,320], node + post_tfmr(...) [B,N,256]) of block `blk`'s sequence-transformer sub-block."""

@@ -242,6 +242,8 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition) */
 enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
        FDPT_OPT_ET_PAIR = 5 /* retired: the cta_group::2 EdgeTransition variant of round 1 was slower (1.3 vs 1.0 ms) and has been removed */,
+       FDPT_OPT_ET_R2_TMEM = 10 /* 1 (default): the fused EdgeTransition kernel hands r2 to its third GEMM through tensor memory
+                                   (tcgen05.st in place over D2, tcgen05.mma with the A operand in TMEM); 0: through shared memory */,
        FDPT_OPT_LIN_WRES = 9 /* 1 (default): Linear layers whose CTAs own a single n-tile run the weight-resident kernel (lin_tcw.cuh: whole
                                 weight panel prefetched under the predecessor's tail, activation streamed); 0: lin_tc.  A/B switch */,
        FDPT_OPT_TF_IMG = 8 /* 1 (default): the sequence transformer's attention GEMMs multiply operand images written by the in_proj
@@ -257,6 +259,9 @@ int fdpt_debug_read(fdpt_ctx* ctx, int64_t* out, int n);
  * Bring-up / unit entry of the building blocks the fused pair-side kernels use. */
 int fdpt_tc_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const float* w, const float* bias, int act,
                    float* y, void* stream);
+/* bring-up unit of tcgen05.mma with the A operand in tensor memory (written by tcgen05.st): d[128,128] = fp16(a[128,64]) . fp16(b[128,64])^T,
+ * fp32 accumulate; device pointers.  Pins the TMEM operand layout the fused EdgeTransition kernel uses for its GEMM3 partial products. */
+int fdpt_tmem_a_selftest(fdpt_ctx* ctx, const float* a, const float* b, float* d, void* stream);
 /* InvariantPointAttention.forward (ipa_pytorch.py:170-329) of block `blk` on given s [B,N,c_s], z [B,N,N,c_z],
  * frames (quats [B,N,4], trans in 0.1 A units [B,N,3]), mask [B,N] -> out [B,N,c_s] (linear_out applied, not masked) */
 int fdpt_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const float* z, const float* quats,

@@ -491,3 +491,15 @@ def test_forward_with_lecun_scale_final_layers_vs_oracle():
     print(f"LeCun-scale final layers: frames move by up to {move:.1f} A in one forward; |dtrans| {dt:.2e} A, rot {da:.2e} rad")
     # TF32-class pair side: the forward-level deviation scales with the size of the update (5e-4 A at 1 A of motion)
     assert da < 5e-3 and dt < 1e-3 * max(move, 1.0)
+
+
+def test_tcgen05_mma_with_a_operand_in_tmem(ctx):
+    """tcgen05.mma kind::f16 with A read from tensor memory (lane = row, two fp16 K-elements per 32-bit column, written by tcgen05.st):
+    the operand form the fused EdgeTransition kernel uses to feed r2 into its third GEMM without a shared-memory round trip."""
+    g = torch.Generator().manual_seed(9)
+    a, b = torch.randn(128, 64, generator=g).cuda(), torch.randn(128, 64, generator=g).cuda()
+    d = ctx.tmem_a_selftest(a.contiguous(), b.contiguous()).cpu()
+    ref = a.cpu().half().double() @ b.cpu().half().double().T
+    err = (d.double() - ref).abs().max().item()
+    print(f"TMEM-A MMA: max abs err {err:.3e} (|ref| max {ref.abs().max():.1f})")
+    assert err < 2e-5 * ref.abs().max().item()

@@ -7,7 +7,7 @@ from framedipt_b200.params import synthetic_state_dict
 ctx = runtime.Context()
 ctx.load_state_dict(synthetic_state_dict(0))
 ctx.set_option(2, 1)
-ctx.set_option(5, int(os.environ.get("ET_PAIR", "1")))
+ctx.set_option(10, int(os.environ.get("R2_TMEM", "1")))
 ctx.set_option(3, int(os.environ.get("DBG_FLAGS", "0")))
 B, N = 8, 350
 node = torch.randn(B, N, 256, device="cuda"); z = torch.randn(B, N, N, 128, device="cuda"); mask = torch.ones(B, N, device="cuda")
