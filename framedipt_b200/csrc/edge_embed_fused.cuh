@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
 
   if (warp == 9) {
     // ============================ loader ============================
-    if (lane == 0 && t_begin < t_end) {
+    if (elect_one() && t_begin < t_end) {
       mbar_arrive_expect_tx(w_full, 3 * EE_W_BYTES);
       bulk_g2s(W0s, a.W0img, EE_W_BYTES, w_full);
       bulk_g2s(W2s, a.W2img, EE_W_BYTES, w_full);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
     }
   } else if (warp == 8) {
     // ============================ MMA issuer ============================
-    if (lane == 0 && t_begin < t_end) {
+    if (elect_one() && t_begin < t_end) {
       const uint32_t idesc = make_idesc_f16(128, 128);
       mbar_wait(w_full, 0);
       tc_fence_after();

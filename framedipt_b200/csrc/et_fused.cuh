@@ -49,6 +49,7 @@ struct EtArgs {
   const __half* W3cat;          // image [10 kb][128][128 B]
   long long tiles;              // B*N*JB
   int r2_tmem;                  // 1: r2 is handed to GEMM3 through tensor memory (A operand from TMEM); 0: through the shared-memory chunk buffers
+  int exp;                      // timing experiments only (results wrong): 1 no weight copies, 2 MMAs shrunk to N=16, 4 no shared-memory stores in E1/E3, 8 no z load/store
   long long* dbg;               // optional clock64 timeline of CTA 0 (bring-up / profiling aid): [tile][48] stamps, or nullptr
 };
 
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
 
   if (warp == 9) {
     // ============================ loader ============================
-    if (lane == 0 && t_begin < t_end) {
+    if (elect_one() && t_begin < t_end) {
       uint32_t wit = 0;      // weight stage counter
       auto load_z = [&](long long t) {
         const int s = (int)((t - t_begin) & 1);
@@ -172,9 +173,13 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       auto stage = [&](const __half* img, int rows_total, int row0, int kb) {
         const int s = wit % ET_WSTAGES;
         mbar_wait(&w_empty[s], ((wit / ET_WSTAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&w_full[s], ET_STAGE_BYTES);
-        bulk_g2s(WST + s * ET_STAGE_BYTES, reinterpret_cast<const uint8_t*>(img) + ((size_t)kb * rows_total + row0) * 128, ET_STAGE_BYTES,
-                 &w_full[s]);
+        if (a.exp & 1) {
+          mbar_arrive(&w_full[s]);
+        } else {
+          mbar_arrive_expect_tx(&w_full[s], ET_STAGE_BYTES);
+          bulk_g2s(WST + s * ET_STAGE_BYTES, reinterpret_cast<const uint8_t*>(img) + ((size_t)kb * rows_total + row0) * 128, ET_STAGE_BYTES,
+                   &w_full[s]);
+        }
         ++wit;
       };
       load_z(t_begin);
@@ -212,8 +217,8 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     }
   } else if (warp == 8) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, 128);
+    if (elect_one()) {
+      const uint32_t idesc = (a.exp & 2) ? make_idesc_f16(128, 16) : make_idesc_f16(128, 128);
       uint32_t wit = 0, ds_e = 0, bf[2] = {0, 0}, d2_e = 0, an_f = 0;
       auto gemm_kb = [&](uint32_t a_addr, uint32_t d_col, bool first_acc) {
         // one k-block: wait the weight stage, 4 x (128x128x16) MMAs, release the stage
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + Ui_t[c * 128 + cg + n], 0.f);
         if (threadIdx.x == 0) ET_TS(18 + 3 * c);
         wait_free(c & 1);
-        store_half(BUF + (c & 1) * ET_TILE_BYTES, v);
+        if (!(a.exp & 4)) store_half(BUF + (c & 1) * ET_TILE_BYTES, v);
         fence_proxy_async();
         mbar_arrive(&buf_full[c & 1]);
         if (threadIdx.x == 0) ET_TS(19 + 3 * c);
@@ -453,7 +458,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       mbar_arrive(&vec_free[vbuf]);
       if (threadIdx.x == 0) ET_TS(31);
       if (a.r2_tmem) wait_free(1);  // BUF[1]'s last reader was G2(1) (h1 chunk 1); its release is consumed here (already complete: D3 is)
-      store_half(BUF + ET_TILE_BYTES, v);
+      if (!(a.exp & 4)) store_half(BUF + ET_TILE_BYTES, v);
       fence_proxy_async();
       mbar_arrive(stg_full);
       if (threadIdx.x == 0) {

@@ -769,6 +769,7 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   a.ln_g = p.eln_g; a.ln_b = p.eln_b; a.mask = mask; a.W1cat = p.imgW1cat; a.W2 = p.imgW2; a.W3cat = p.imgW3cat;
   a.tiles = M * w.JB;
   a.r2_tmem = ctx->et_r2_tmem;
+  a.exp = (ctx->dbg_flags >> 20) & 15;
   if (a.tiles >= (1LL << 31)) return fail(ctx, FDPT_ERR_INVALID, "B*N*ceil(N/128) = %lld tiles: the pair kernels index tiles with 32 bits", a.tiles);
   a.dbg = (ctx->dbg_flags & 4) ? nullptr : ctx->et_dbg;
   {

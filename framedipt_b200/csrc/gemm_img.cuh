@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) gemm_img_kernel(const __grid_co
 
   if (warp == 9) {
     // ============================ loader ============================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         int mt, nt, z;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) gemm_img_kernel(const __grid_co
     }
   } else if (warp == 8) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0, tl = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
         int mt, nt, z;

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(GemmTcArgs a) {
 
   if (warp == GT_PRODUCERS / 32) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(GT_BM, BN) | (a.b_kmajor ? 0u : (1u << 16));
       const uint32_t acc_main = tmem_base, acc_x = tmem_base + (uint32_t)BN;
       for (int kb = 0; kb < nkb; ++kb) {

@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
 
   if (warp == 5) {
     // ============================ loader ============================
-    if (lane == 0 && nrows > 0) {
+    if (elect_one() && nrows > 0) {
       mbar_arrive_expect_tx(wb_full, 4096);
       bulk_g2s(Wbs, a.Wb_img, 4096, wb_full);
       uint32_t cnt = 0;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
     }
   } else if (warp == 4) {
     // ============================ MMA issuer ============================
-    if (lane == 0 && nrows > 0) {
+    if (elect_one() && nrows > 0) {
       mbar_wait(wb_full, 0);
       tc_fence_after();
       const uint32_t idesc_b = make_idesc_f16(128, 16);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
 
   if (warp == 9) {
     // ============================ weight loader (weights are static: no need to wait for the predecessor kernel) ============================
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;  // ring unit counter: 2 per k-block (hi, lo)
       for (int nt = nt_begin; nt < nt_end; ++nt)
         for (int kb = 0; kb < a.nkb; ++kb)
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
     }
   } else if (warp == 8) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(128, 128);
       int it = 0;
       for (int t = 0; t < ntiles; ++t) {

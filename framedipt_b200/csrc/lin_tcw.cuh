@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
 
   if (warp == 9) {
     // ============================ weight loader: the whole panel, before the predecessor kernel has finished ============================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int kb = 0; kb < a.nkb; ++kb) {
         mbar_arrive_expect_tx(&w_full[kb], LT_STAGE_BYTES);
         bulk_g2s(Wst + (size_t)kb * LT_STAGE_BYTES, reinterpret_cast<const uint8_t*>(a.Wimg) + ((size_t)nt * a.nkb + kb) * LT_STAGE_BYTES,
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
     }
   } else if (warp == 8) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(128, 128);
       const uint32_t acc_main = tmem_base, acc_x = tmem_base + 128;
       for (int kb = 0; kb < a.nkb; ++kb) {

@@ -27,6 +27,18 @@ FDPT_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_t
 FDPT_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 FDPT_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// one lane of a converged warp (elect.sync): unlike `lane == 0`, ptxas knows that exactly one thread is active in the guarded region,
+// so the warp-level tcgen05 / bulk-copy instructions in it are emitted once instead of inside a per-active-thread ELECT loop
+FDPT_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------
 FDPT_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
