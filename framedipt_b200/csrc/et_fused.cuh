@@ -31,7 +31,7 @@ namespace fdpt {
 namespace tc {
 
 constexpr int ET_TILE_BYTES = 32768;    // 128 rows x 128 halfs (two k-blocks)
-constexpr int ET_WSTAGES = 3;
+constexpr int ET_WSTAGES = 5;
 constexpr int ET_STAGE_BYTES = 16384;   // 128 weight rows x one k-block
 
 struct EtArgs {
@@ -68,8 +68,8 @@ constexpr int ET_THREADS = ET_WORKERS + 96;  // + MMA warp, weight loader warp, 
 __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* A0z = smem;                                 // 2 x 32 KB
-  uint8_t* A0n = A0z + 2 * ET_TILE_BYTES;              // 32 KB
+  uint8_t* A0z = smem;                                 // 32 KB (single buffer: the next tile's z is fetched under G3's partial products + E3)
+  uint8_t* A0n = A0z + ET_TILE_BYTES;                  // 32 KB
   uint8_t* BUF = A0n + ET_TILE_BYTES;                  // 2 x 32 KB
   uint8_t* WST = BUF + 2 * ET_TILE_BYTES;              // ET_WSTAGES x 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(WST + ET_WSTAGES * ET_STAGE_BYTES);
@@ -157,14 +157,10 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     if (elect_one() && t_begin < t_end) {
       uint32_t wit = 0;      // weight stage counter
       auto load_z = [&](long long t) {
-        const int s = (int)((t - t_begin) & 1);
-        const uint32_t use = (uint32_t)((t - t_begin) >> 1);
-        mbar_wait(&az_empty[s], (use & 1) ^ 1);
-        mbar_arrive_expect_tx(&az_full[s], ET_TILE_BYTES);
+        mbar_arrive_expect_tx(&az_full[0], ET_TILE_BYTES);
         int jb;
         const long long m = tile_m(t, jb);
-        bulk_g2s(A0z + s * ET_TILE_BYTES, reinterpret_cast<const uint8_t*>(a.z_in) + ((m * a.JB + jb) * (long long)ET_TILE_BYTES), ET_TILE_BYTES,
-                 &az_full[s]);
+        bulk_g2s(A0z, reinterpret_cast<const uint8_t*>(a.z_in) + ((m * a.JB + jb) * (long long)ET_TILE_BYTES), ET_TILE_BYTES, &az_full[0]);
       };
       auto load_n = [&](long long t) {
         mbar_arrive_expect_tx(an_full, ET_TILE_BYTES);
@@ -188,19 +184,17 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         // weight stream in the exact order the MMA warp consumes it
         for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 0, kb);                                   // G1(0)
         for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 128, kb);                                 // G1(1)
-        if (t + 1 < t_end) load_z(t + 1);                                                            // prefetch next z tile
         for (int n = 0; n < 3; ++n) for (int kb = 0; kb < 2; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(0)
         for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 256, kb);                                 // G1(2)
         for (int n = 0; n < 3; ++n) for (int kb = 2; kb < 4; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(1)
         for (int n = 0; n < 3; ++n) for (int kb = 4; kb < 6; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(2)
         for (int kb = 6; kb < 10; ++kb) stage(a.W3cat, 128, 0, kb);                                  // G3 static ([z | n_j])
         for (int kb = 0; kb < 6; ++kb) stage(a.W3cat, 128, 0, kb);                                   // G3 partials
-        if (t + 1 < t_end && tile_bjb(t + 1) != tile_bjb(t)) {
-          // the n_j image changes: wait until tile t's last reader (G3 static) has completed
-          const int s = (int)((t - t_begin) & 1);
-          const uint32_t use = (uint32_t)((t - t_begin) >> 1);
-          mbar_wait(&az_empty[s], use & 1);
-          load_n(t + 1);
+        if (t + 1 < t_end) {
+          // tile t's last reader of z and n_j (G3 static) has completed: fetch the next tile's z (and the n_j image if it changes)
+          mbar_wait(&az_empty[0], (uint32_t)(t - t_begin) & 1);
+          load_z(t + 1);
+          if (tile_bjb(t + 1) != tile_bjb(t)) load_n(t + 1);
         }
       }
     }
@@ -233,16 +227,14 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         ++wit;
       };
       for (long long t = t_begin; t < t_end; ++t) {
-        const int zs = (int)((t - t_begin) & 1);
-        const uint32_t zuse = (uint32_t)((t - t_begin) >> 1);
-        mbar_wait(&az_full[zs], zuse & 1);
+        mbar_wait(&az_full[0], (uint32_t)(t - t_begin) & 1);
         if (t == t_begin || tile_bjb(t) != tile_bjb(t - 1)) {
           mbar_wait(an_full, an_f & 1);
           ++an_f;
         }
         tc_fence_after();
         ET_TS(0);
-        const uint32_t az = smem_u32(A0z + zs * ET_TILE_BYTES), an = smem_u32(A0n);
+        const uint32_t az = smem_u32(A0z), an = smem_u32(A0n);
         const uint32_t bufa[2] = {smem_u32(BUF), smem_u32(BUF + ET_TILE_BYTES)};
         auto a0_kb = [&](int kb) { return kb < 2 ? az + kb * 16384 : an + (kb - 2) * 16384; };
         auto G1 = [&](int c) {
@@ -284,7 +276,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         ++ds_e;
         tc_fence_after();
         for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
-        umma_commit(&az_empty[zs]);
+        umma_commit(&az_empty[0]);
         ET_TS(7);
         // G3 partial products: A = r2 chunk c straight from tensor memory (the workers wrote it in place over D2: worker group g's 64
         // K-elements of the chunk sit packed in the 32 columns D2 + 128 c + 64 g), B = W3cat k-block 2c + g from the weight ring
@@ -412,47 +404,37 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         if (threadIdx.x == 0) ET_TS(27 + c);
       }
       // ---- E3: LayerNorm + mask -> fp16 tile image -> bulk store staged in BUF[1] (free: its last reader, G3 partial 1, completed
-      //      before D3 did).  Every thread computes the statistics of its whole row -- the other group's 64 columns are re-read from
-      //      TMEM once, with the own-half mean as shift for the single-pass variance -- so the two groups never synchronise.
+      //      before D3 did).  DS is released as soon as each thread holds its 64 columns; the row statistics of the two halves are
+      //      combined through shared memory (one named barrier among the 256 workers).
       mbar_wait(ds_full, ds_f & 1);
       ++ds_f;
       tc_fence_after();
       if (threadIdx.x == 0) ET_TS(30);
       load_half(DS, v);
+      tc_fence_before();
+      mbar_arrive(ds_empty);  // D3 is in registers: the next tile's first GEMM may overwrite DS while the LayerNorm runs
       float s0 = 0.f;
 #pragma unroll
       for (int n = 0; n < 64; ++n) {
         v[n] += Pf_t[cg + n];
         s0 += v[n];
       }
-      const float shift = s0 * (1.f / 64.f);
-      float sd = 0.f, sq = 0.f;
+      const float mh = s0 * (1.f / 64.f);
+      float m2 = 0.f;
 #pragma unroll
       for (int n = 0; n < 64; ++n) {
-        const float d = v[n] - shift;
-        sd += d;
-        sq += d * d;
+        const float d = v[n] - mh;
+        m2 += d * d;
       }
-      const int og = 64 - cg;  // first column of the other group's half
-      {
-        float w[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          tmem_ld32(DS + lane_base + og + 32 * h, w);
-          tmem_ld_wait();
-#pragma unroll
-          for (int n = 0; n < 32; ++n) {
-            const float d = w[n] + Pf_t[og + 32 * h + n] - shift;
-            sd += d;
-            sq += d * d;
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(ds_empty);
-      const float dm = sd * (1.f / 128.f);
-      const float mean = shift + dm;
-      const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - dm * dm, 0.f) + 1e-5f);
+      // the two groups own one half of every row each: exchange (mean, sum of squared deviations) of the halves through shared
+      // memory and combine them with the pairwise update (Chan et al.), exact for equal counts
+      red_s[wg * 128 + row] = mh;
+      red_q[wg * 128 + row] = m2;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mo = red_s[(wg ^ 1) * 128 + row], m2o = red_q[(wg ^ 1) * 128 + row];
+      const float mean = 0.5f * (mh + mo);
+      const float dmo = mh - mo;
+      const float rstd = rsqrtf((m2 + m2o + 32.f * dmo * dmo) * (1.f / 128.f) + 1e-5f);
 #pragma unroll
       for (int n = 0; n < 64; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
       mbar_arrive(&vec_free[vbuf]);
@@ -478,7 +460,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
 }
 
 inline size_t et_smem_bytes() {
-  return 1024 + 5 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 44 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 512) * 4 + 64 + 32;
+  return 1024 + 4 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 44 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 512) * 4 + 64 + 32;
 }
 
 // ---- layout helpers --------------------------------------------------------------------------------------------------
