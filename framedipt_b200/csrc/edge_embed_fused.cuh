@@ -52,7 +52,7 @@ constexpr int EE_THREADS = EE_WORKERS + 64;
 
 __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   uint8_t* W0s = smem;                      // 32 KB
   uint8_t* W2s = W0s + EE_W_BYTES;          // 32 KB
   uint8_t* W4s = W2s + EE_W_BYTES;          // 32 KB

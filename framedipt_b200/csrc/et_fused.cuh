@@ -16,12 +16,13 @@
 //                                                     W3cat = [Wf | Wf[:, 0:128] | Wf[:, 256:384]]
 //   E3     z' = LN(D3 + Pf_i) * mask                -> fp16 tile image, bulk store
 //
-// TMEM: columns [0,384) = D2, [384,512) = D1 chunk stage / D3.   Shared memory (224 KB): A0z x2 (64 KB, bulk-copied,
-// double buffered across tiles), A0n (32 KB), two 32 KB chunk buffers (h1 / r2 / output staging), 4-stage weight ring.
-// Warps 0-7: epilogue workers in two groups of 128 (thread <-> tile row <-> TMEM lane; group g owns columns [64g, 64g+64) of every
-// 128-column chunk = k-block g of the chunk it writes, which halves the latency of each epilogue step); warp 8: MMA issuer + TMEM
-// owner; warp 9: weight / z / n_j loader; warp 10: prefetches the per-tile epilogue vectors (U_i, Pf_i) of the next tile into a
-// double-buffered shared-memory slot so that the workers never wait on a global load between tiles.
+// TMEM: columns [0,384) = D2 (then r2, packed fp16, in place), [384,512) = D1 chunk stage / D3.   Shared memory (216 KB): A0z (32 KB,
+// bulk-copied; the next tile's z is fetched while G3's partial products and E3 run), A0n (32 KB), two 32 KB chunk buffers (h1 / output
+// staging), 5-stage weight ring (80 KB: the ring depth, not the tensor pipe, paced this kernel with 3 stages).
+// Warps 0-15: epilogue workers in four groups of 128 (thread <-> tile row <-> TMEM lane; group g owns columns [32g, 32g+32) of every
+// 128-column chunk: four warps per scheduler hide the TMEM-load / shared-memory latencies of each other); warp 16: MMA issuer (one
+// elect.sync lane) + TMEM owner; warp 17: weight / z / n_j loader; warp 18: prefetches the per-tile epilogue vectors (U_i, Pf_i) of
+// the next tile into a double-buffered shared-memory slot so that the workers never wait on a global load between tiles.
 // All operands fp16 (10-bit mantissa = TF32 precision, which the pair side tolerates: SURVEY §7 hard part 1), fp32 accumulate.
 #pragma once
 #include "tc_common.cuh"
@@ -48,26 +49,29 @@ struct EtArgs {
   const __half* W2;             // image [6 kb][384][128 B]
   const __half* W3cat;          // image [10 kb][128][128 B]
   long long tiles;              // B*N*JB
-  int r2_tmem;                  // 1: r2 is handed to GEMM3 through tensor memory (A operand from TMEM); 0: through the shared-memory chunk buffers
   int exp;                      // timing experiments only (results wrong): 1 no weight copies, 2 MMAs shrunk to N=16, 4 no shared-memory stores in E1/E3, 8 no z load/store
   long long* dbg;               // optional clock64 timeline of CTA 0 (bring-up / profiling aid): [tile][48] stamps, or nullptr
 };
 
 #define ET_TS(id)                                                                                  \
   do {                                                                                             \
-    if (a.dbg && blockIdx.x == 0 && (t - t_begin) < 8) a.dbg[(t - t_begin) * 48 + (id)] = clock64(); \
+    if (a.dbg && blockIdx.x == ((a.exp & 8) ? 77 : 0) && (t - t_begin) >= ((a.exp & 8) ? 40 : 0) && (t - t_begin) < ((a.exp & 8) ? 48 : 8)) \
+      a.dbg[((t - t_begin) & 7) * 48 + (id)] = clock64();                                            \
   } while (0)
 
 struct EtPhase {  // phase counters of one role
   uint32_t w = 0, az[2] = {0, 0}, an = 0, ds_full = 0, ds_empty = 0, buf_full[2] = {0, 0}, buf_free[2] = {0, 0}, d2_full = 0, d2_empty = 0;
 };
 
-constexpr int ET_WORKERS = 256;
+constexpr int ET_GROUPS = 4;                      // epilogue worker groups (128 threads each)
+constexpr int ET_GC = 128 / ET_GROUPS;            // columns of a 128-column chunk owned by one group
+constexpr int ET_WORKERS = 128 * ET_GROUPS;
+constexpr int ET_WW = ET_WORKERS / 32;            // worker warps; then: MMA warp, loader warp, epilogue-vector warp
 constexpr int ET_THREADS = ET_WORKERS + 96;  // + MMA warp, weight loader warp, epilogue-vector prefetch warp
 
 __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   uint8_t* A0z = smem;                                 // 32 KB (single buffer: the next tile's z is fetched under G3's partial products + E3)
   uint8_t* A0n = A0z + ET_TILE_BYTES;                  // 32 KB
   uint8_t* BUF = A0n + ET_TILE_BYTES;                  // 2 x 32 KB
@@ -94,8 +98,8 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   float* b2_s = Pf_s + 2 * 128;                            // [384]
   float* g_s = b2_s + 384;                                 // [128]
   float* be_s = g_s + 128;                                 // [128]
-  float* red_s = be_s + 128;                               // [2][128] LayerNorm partial sums of the two worker groups
-  float* red_q = red_s + 256;                              // [2][128]
+  float* red_s = be_s + 128;                               // [ET_GROUPS][128] LayerNorm partial means of the worker groups
+  float* red_q = red_s + ET_GROUPS * 128;                  // [ET_GROUPS][128] partial sums of squared deviations
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long per = (a.tiles + gridDim.x - 1) / gridDim.x;
@@ -117,7 +121,6 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     mbar_init(ds_full, 1);
     mbar_init(ds_empty, ET_WORKERS);
     mbar_init(d2_full, 1);
-    mbar_init(d2_empty, ET_WORKERS);
     mbar_init(stg_full, ET_WORKERS);
     for (int c = 0; c < 3; ++c) mbar_init(&r2_full[c], ET_WORKERS);
     for (int s = 0; s < 2; ++s) {
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     g_s[k] = a.ln_g[k];
     be_s[k] = a.ln_b[k];
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == ET_WW) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     return tile_mb(t, jb, b);
   };
 
-  if (warp == 9) {
+  if (warp == ET_WW + 1) {
     // ============================ loader ============================
     if (elect_one() && t_begin < t_end) {
       uint32_t wit = 0;      // weight stage counter
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == ET_WW + 2) {
     // ============================ epilogue-vector prefetcher ============================
     for (long long t = t_begin; t < t_end; ++t) {
       const uint32_t n = (uint32_t)(t - t_begin), buf = n & 1;
@@ -209,11 +212,11 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       for (int k = lane; k < 128; k += 32) Pf_s[buf * 128 + k] = a.Pf[m * 128 + k];
       mbar_arrive(&vec_full[buf]);
     }
-  } else if (warp == 8) {
+  } else if (warp == ET_WW) {
     // ============================ MMA issuer ============================
     if (elect_one()) {
       const uint32_t idesc = (a.exp & 2) ? make_idesc_f16(128, 16) : make_idesc_f16(128, 128);
-      uint32_t wit = 0, ds_e = 0, bf[2] = {0, 0}, d2_e = 0, an_f = 0;
+      uint32_t wit = 0, ds_e = 0, bf[2] = {0, 0}, an_f = 0;
       auto gemm_kb = [&](uint32_t a_addr, uint32_t d_col, bool first_acc) {
         // one k-block: wait the weight stage, 4 x (128x128x16) MMAs, release the stage
         const int s = wit % ET_WSTAGES;
@@ -249,10 +252,6 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
           const int b = c & 1;
           mbar_wait(&buf_full[b], bf[b] & 1);
           ++bf[b];
-          if (c == 0) {
-            mbar_wait(d2_empty, (d2_e & 1) ^ 1);
-            ++d2_e;
-          }
           tc_fence_after();
           for (int n = 0; n < 3; ++n)
             for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, D2 + n * 128, c == 0 && kb == 0);
@@ -278,20 +277,10 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
         umma_commit(&az_empty[0]);
         ET_TS(7);
-        // G3 partial products: A = r2 chunk c straight from tensor memory (the workers wrote it in place over D2: worker group g's 64
-        // K-elements of the chunk sit packed in the 32 columns D2 + 128 c + 64 g), B = W3cat k-block 2c + g from the weight ring
+        // G3 partial products: A = r2 chunk c straight from tensor memory (the workers wrote it in place over D2: the 16 K-elements of
+        // k-step j of the chunk sit packed in the 8 columns D2 + 128 c + ET_GC (16 j / ET_GC) + (16 j % ET_GC) / 2), B = W3cat k-block
+        // 2c + kb from the weight ring
         for (int c = 0; c < 3; ++c) {
-          if (!a.r2_tmem) {
-            const int b = c & 1;
-            mbar_wait(&buf_full[b], bf[b] & 1);
-            ++bf[b];
-            tc_fence_after();
-            ET_TS(11 + c);
-            for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, DS, false);
-            if (c != 1) umma_commit(&buf_free[b]);  // BUF[1] becomes the output staging buffer: released by worker thread 0
-            ET_TS(8 + c);
-            continue;
-          }
           mbar_wait(&r2_full[c], (uint32_t)(t - t_begin) & 1);
           tc_fence_after();
           ET_TS(11 + c);
@@ -301,7 +290,10 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
             tc_fence_after();
             const uint32_t b_addr = smem_u32(WST + s * ET_STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ts(DS, D2 + c * 128 + kb * 64 + 8 * k, make_sw128_desc(b_addr + k * 32), idesc, 1u);
+            for (int k = 0; k < 4; ++k) {
+              const int kk = 64 * kb + 16 * k;  // first K element of the step within the chunk
+              umma_f16_ts(DS, D2 + c * 128 + ET_GC * (kk / ET_GC) + (kk % ET_GC) / 2, make_sw128_desc(b_addr + k * 32), idesc, 1u);
+            }
             umma_commit(&w_empty[s]);
             ++wit;
           }
@@ -311,42 +303,42 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       }
     }
   } else {
-    // ============================ epilogue workers (2 groups x 128 threads) ============================
-    const int wg = warp >> 2;                         // column half owned by this group
+    // ============================ epilogue workers (ET_GROUPS groups x 128 threads) ============================
+    // thread <-> tile row <-> TMEM lane; group g owns columns [ET_GC g, ET_GC g + ET_GC) of every 128-column chunk
+    const int wg = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
-    const int cg = wg * 64;
+    const int cg = wg * ET_GC;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ds_f = 0, fr[2] = {0, 0}, d2_f = 0;
     auto wait_free = [&](int b) {
       mbar_wait(&buf_free[b], (fr[b] & 1) ^ 1);
       ++fr[b];
     };
-    // 64 values -> fp16 -> k-block `wg` of a swizzled chunk buffer, row `row` (8 chunks of 16 bytes)
-    auto store_half = [&](uint8_t* buf, const float* v /*[64]*/) {
+    // 32 values -> fp16 -> columns [cg, cg + 32) of row `row` of a swizzled chunk buffer (k-block cg / 64, four 16-byte chunks)
+    auto store_part = [&](uint8_t* buf, const float* v /*[32]*/) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const float* p = v + c * 8;
         const uint4 u = make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
-        *reinterpret_cast<uint4*>(buf + wg * 16384 + sw128_chunk_off(row, c)) = u;
+        *reinterpret_cast<uint4*>(buf + (wg >> 1) * 16384 + sw128_chunk_off(row, (wg & 1) * 4 + c)) = u;
       }
     };
-    auto load_half = [&](uint32_t taddr, float* v /*[64]*/) {
+    auto load_part = [&](uint32_t taddr, float* v /*[32]*/) {
       tmem_ld32(taddr + lane_base + cg, v);
-      tmem_ld32(taddr + lane_base + cg + 32, v + 32);
       tmem_ld_wait();
     };
     for (long long t = t_begin; t < t_end; ++t) {
       int jb, bsamp;
       const long long m = tile_mb(t, jb, bsamp);
       const int j = jb * 128 + row;
-      // per-tile epilogue vectors (same i for the whole tile), prefetched by warp 10
+      // per-tile epilogue vectors (same i for the whole tile), prefetched by the vector warp
       const uint32_t vn = (uint32_t)(t - t_begin), vbuf = vn & 1;
       const float* Ui_t = Ui_s + vbuf * 384;
       const float* Pf_t = Pf_s + vbuf * 128;
       float mk = 0.f;
       if (j < a.N) mk = a.mask[m] * a.mask[(long long)bsamp * a.N + j];
       mbar_wait(&vec_full[vbuf], (vn >> 1) & 1);
-      float v[64];
+      float v[ET_GC];
       if (threadIdx.x == 0) ET_TS(16);
       // ---- E1: three chunks of h1
       for (int c = 0; c < 3; ++c) {
@@ -358,89 +350,84 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         ++ds_f;
         tc_fence_after();
         if (threadIdx.x == 0) ET_TS(17 + 3 * c);
-        load_half(DS, v);
+        load_part(DS, v);
         tc_fence_before();
         mbar_arrive(ds_empty);
 #pragma unroll
-        for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + Ui_t[c * 128 + cg + n], 0.f);
+        for (int n = 0; n < ET_GC; ++n) v[n] = fmaxf(v[n] + Ui_t[c * 128 + cg + n], 0.f);
         if (threadIdx.x == 0) ET_TS(18 + 3 * c);
         wait_free(c & 1);
-        if (!(a.exp & 4)) store_half(BUF + (c & 1) * ET_TILE_BYTES, v);
+        if (!(a.exp & 4)) store_part(BUF + (c & 1) * ET_TILE_BYTES, v);
         fence_proxy_async();
         mbar_arrive(&buf_full[c & 1]);
         if (threadIdx.x == 0) ET_TS(19 + 3 * c);
       }
-      // ---- E2: three chunks of r2
+      // ---- E2: three chunks of r2, written back in place (this thread's 32 fp32 columns become 16 packed fp16 columns)
       mbar_wait(d2_full, d2_f & 1);
       ++d2_f;
       tc_fence_after();
       if (threadIdx.x == 0) ET_TS(26);
       for (int c = 0; c < 3; ++c) {
-        load_half(D2 + c * 128, v);
-        if (!a.r2_tmem) {
-          if (c == 2) {
-            tc_fence_before();
-            mbar_arrive(d2_empty);
-          }
+        load_part(D2 + c * 128, v);
+        uint32_t pk[ET_GC / 2];
 #pragma unroll
-          for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + b2_s[c * 128 + cg + n], 0.f);
-          wait_free(c & 1);
-          store_half(BUF + (c & 1) * ET_TILE_BYTES, v);
-          fence_proxy_async();
-          mbar_arrive(&buf_full[c & 1]);
-          if (threadIdx.x == 0) ET_TS(27 + c);
-          continue;
-        }
-        uint32_t pk[32];
-#pragma unroll
-        for (int n = 0; n < 32; ++n)
+        for (int n = 0; n < ET_GC / 2; ++n)
           pk[n] = pack_half2(fmaxf(v[2 * n] + b2_s[c * 128 + cg + 2 * n], 0.f), fmaxf(v[2 * n + 1] + b2_s[c * 128 + cg + 2 * n + 1], 0.f));
-        // in place: this thread's own 64 fp32 columns of the chunk become 32 packed fp16 columns (the other group's range is disjoint)
-        tmem_st32(D2 + lane_base + c * 128 + cg, pk);
+        tmem_st16(D2 + lane_base + c * 128 + cg, pk);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&r2_full[c]);
-        if (c == 2) mbar_arrive(d2_empty);
         if (threadIdx.x == 0) ET_TS(27 + c);
       }
-      // ---- E3: LayerNorm + mask -> fp16 tile image -> bulk store staged in BUF[1] (free: its last reader, G3 partial 1, completed
-      //      before D3 did).  DS is released as soon as each thread holds its 64 columns; the row statistics of the two halves are
-      //      combined through shared memory (one named barrier among the 256 workers).
+      // ---- E3: LayerNorm + mask -> fp16 tile image -> bulk store staged in BUF[1] (free: its last reader, G2(1), completed long
+      //      ago).  DS is released as soon as each thread holds its columns; the row statistics of the groups are combined through
+      //      shared memory (one named barrier among the workers).
       mbar_wait(ds_full, ds_f & 1);
       ++ds_f;
       tc_fence_after();
       if (threadIdx.x == 0) ET_TS(30);
-      load_half(DS, v);
+      load_part(DS, v);
       tc_fence_before();
       mbar_arrive(ds_empty);  // D3 is in registers: the next tile's first GEMM may overwrite DS while the LayerNorm runs
-      float s0 = 0.f;
+      if (threadIdx.x == 0) ET_TS(33);
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int n = 0; n < 64; ++n) {
+      for (int n = 0; n < ET_GC; n += 2) {
         v[n] += Pf_t[cg + n];
+        v[n + 1] += Pf_t[cg + n + 1];
         s0 += v[n];
+        s1 += v[n + 1];
       }
-      const float mh = s0 * (1.f / 64.f);
-      float m2 = 0.f;
+      const float mh = (s0 + s1) * (1.f / ET_GC);
+      float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int n = 0; n < 64; ++n) {
-        const float d = v[n] - mh;
-        m2 += d * d;
+      for (int n = 0; n < ET_GC; n += 2) {
+        const float d0 = v[n] - mh, d1 = v[n + 1] - mh;
+        q0 += d0 * d0;
+        q1 += d1 * d1;
       }
-      // the two groups own one half of every row each: exchange (mean, sum of squared deviations) of the halves through shared
-      // memory and combine them with the pairwise update (Chan et al.), exact for equal counts
+      // exchange (mean, sum of squared deviations) of the row parts and combine them with the pairwise update (Chan et al.)
       red_s[wg * 128 + row] = mh;
-      red_q[wg * 128 + row] = m2;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mo = red_s[(wg ^ 1) * 128 + row], m2o = red_q[(wg ^ 1) * 128 + row];
-      const float mean = 0.5f * (mh + mo);
-      const float dmo = mh - mo;
-      const float rstd = rsqrtf((m2 + m2o + 32.f * dmo * dmo) * (1.f / 128.f) + 1e-5f);
+      red_q[wg * 128 + row] = q0 + q1;
+      if (threadIdx.x == 0) ET_TS(34);
+      asm volatile("bar.sync 1, %0;" ::"n"(ET_WORKERS) : "memory");
+      if (threadIdx.x == 0) ET_TS(35);
+      float mean = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
+      for (int g = 0; g < ET_GROUPS; ++g) mean += red_s[g * 128 + row];
+      mean *= (1.f / ET_GROUPS);
+#pragma unroll
+      for (int g = 0; g < ET_GROUPS; ++g) {
+        const float dg = red_s[g * 128 + row] - mean;
+        m2 += red_q[g * 128 + row] + (float)ET_GC * dg * dg;
+      }
+      const float rstd = rsqrtf(m2 * (1.f / 128.f) + 1e-5f);
+#pragma unroll
+      for (int n = 0; n < ET_GC; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
       mbar_arrive(&vec_free[vbuf]);
       if (threadIdx.x == 0) ET_TS(31);
-      if (a.r2_tmem) wait_free(1);  // BUF[1]'s last reader was G2(1) (h1 chunk 1); its release is consumed here (already complete: D3 is)
-      if (!(a.exp & 4)) store_half(BUF + ET_TILE_BYTES, v);
+      wait_free(1);  // BUF[1]'s last reader was G2(1) (h1 chunk 1); its release is consumed here (already complete: D3 is)
+      if (!(a.exp & 4)) store_part(BUF + ET_TILE_BYTES, v);
       fence_proxy_async();
       mbar_arrive(stg_full);
       if (threadIdx.x == 0) {
@@ -456,11 +443,11 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == ET_WW) tmem_dealloc(tmem_base, 512);
 }
 
 inline size_t et_smem_bytes() {
-  return 1024 + 4 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 44 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 512) * 4 + 64 + 32;
+  return 1024 + 4 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 44 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 2 * ET_GROUPS * 128) * 4 + 64 + 32;
 }
 
 // ---- layout helpers --------------------------------------------------------------------------------------------------

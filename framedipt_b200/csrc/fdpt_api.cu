@@ -132,7 +132,6 @@ struct fdpt_ctx {
   int use_graph = 1;
   int64_t stat_captures = 0;      // per-timestep graphs captured so far
   int64_t stat_sample_host_us = 0; // host time the last fdpt_sample call spent enqueueing
-  int et_r2_tmem = 1; // EdgeTransition: r2 handed to GEMM3 through tensor memory (A operand from TMEM); 0 = through shared memory (A/B switch)
   int lin_wres = 1;   // Linear layers whose CTAs own one n-tile keep the whole weight panel resident and stream the activation (lin_tcw.cuh); 0 = lin_tc
   int tf_img = 1;     // sequence-transformer attention GEMMs from operand images (in_proj epilogue -> gemm_img); 0 = gemm_tc path (A/B switch)
   int ipa_img = 1;    // IPA attention GEMMs from operand images (gemm_img.cuh); 0 = fp32 operands split on the fly (gemm_tc.cuh; A/B switch)
@@ -768,7 +767,6 @@ int run_edge_transition(fdpt_ctx* ctx, int blk, int B, int N, const float* node,
   a.B = B; a.N = N; a.JB = w.JB; a.z_in = z_in; a.z_out = z_out; a.n_img = w.n_img; a.Ui = w.U; a.Pf = w.Pf; a.b2 = p.be2;
   a.ln_g = p.eln_g; a.ln_b = p.eln_b; a.mask = mask; a.W1cat = p.imgW1cat; a.W2 = p.imgW2; a.W3cat = p.imgW3cat;
   a.tiles = M * w.JB;
-  a.r2_tmem = ctx->et_r2_tmem;
   a.exp = (ctx->dbg_flags >> 20) & 15;
   if (a.tiles >= (1LL << 31)) return fail(ctx, FDPT_ERR_INVALID, "B*N*ceil(N/128) = %lld tiles: the pair kernels index tiles with 32 bits", a.tiles);
   a.dbg = (ctx->dbg_flags & 4) ? nullptr : ctx->et_dbg;
@@ -1705,7 +1703,7 @@ int fdpt_set_option(fdpt_ctx* ctx, int option, int value) {
     case FDPT_OPT_DEBUG_FLAGS: ctx->dbg_flags = value; ctx->step_graph.key.clear(); tc::g_force_bn = (value & 8) ? 128 : 0; tc::g_use_pdl = (value & 16) ? 0 : 1; return FDPT_OK;
     case FDPT_OPT_GRAPH: ctx->use_graph = value != 0; return FDPT_OK;
     case FDPT_OPT_ET_PAIR: return fail(ctx, FDPT_ERR_INVALID, "the CTA-pair EdgeTransition variant was removed (slower than the single-CTA kernel, DESIGN.md)");
-    case FDPT_OPT_ET_R2_TMEM: ctx->et_r2_tmem = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
+    case FDPT_OPT_ET_R2_TMEM: return value ? FDPT_OK : fail(ctx, FDPT_ERR_INVALID, "the shared-memory hand-over of r2 was removed: the EdgeTransition kernel always feeds GEMM3 from tensor memory");
     case FDPT_OPT_LIN_WRES: ctx->lin_wres = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_TF_IMG: ctx->tf_img = value != 0; ctx->step_graph.key.clear(); return FDPT_OK;
     case FDPT_OPT_IPA_IMG: ctx->ipa_img = value; ctx->step_graph.key.clear(); return FDPT_OK;

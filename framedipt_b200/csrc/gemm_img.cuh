@@ -37,7 +37,7 @@ struct GemmImgArgs {
 
 __global__ void __launch_bounds__(GI_THREADS, 1) gemm_img_kernel(const __grid_constant__ GemmImgArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   uint8_t* ring = smem;                                                     // GI_STAGES x 64 KB
   float* Stg = reinterpret_cast<float*>(ring + (size_t)GI_STAGES * GI_STAGE_BYTES);  // 8 warps x 32 rows x 17 floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(Stg + 8 * 32 * 17);

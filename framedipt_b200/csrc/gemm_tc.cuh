@@ -177,7 +177,7 @@ FDPT_DEVINL void store_tile(const ChunkPlan& p, uint8_t* stage, const RegTile& t
 
 __global__ void __launch_bounds__(GT_THREADS, 2) gemm_tc_kernel(GemmTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   const GemmArgs& g = a.g;
   const int BN = a.bn;
   const uint32_t a_bytes = GT_BM * 128, b_bytes = (uint32_t)BN * 128;

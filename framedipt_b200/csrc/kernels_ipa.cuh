@@ -324,7 +324,7 @@ inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
 __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   const int N = a.N, JB = a.JB, ldL = JB * 128;
   uint8_t* ring = smem;                                      // rz x 32 KB z tiles
   uint8_t* Pimg = ring + (size_t)a.rz * IPA_TILE_BYTES;      // JB x 4 KB probability images (B operand of GEMM-o)

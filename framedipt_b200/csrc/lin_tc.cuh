@@ -74,7 +74,7 @@ template <bool XIMG, bool YIMG, int EPI = 0>
 __global__ void __launch_bounds__(LT_THREADS, 1) lin_tc_kernel(LinTcArgs a) {
   constexpr bool EPI_IPA = EPI == 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   uint8_t* Aimg = smem;                                        // nkb x [hi 16 KB | lo 16 KB]
   uint8_t* Wst = Aimg + (size_t)a.nkb * LT_STAGE_BYTES;        // units x 16 KB
   float* Stg = reinterpret_cast<float*>(Wst + (size_t)a.units * LT_UNIT_BYTES);  // 8 warps x 32 rows x (stg_cols + 1) floats

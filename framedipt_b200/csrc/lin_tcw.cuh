@@ -18,7 +18,7 @@ namespace tc {
 template <bool XIMG, bool YIMG>
 __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   uint8_t* Aring = smem;                                          // 2 x [hi 16 KB | lo 16 KB]; later the epilogue's transposition patches
   uint8_t* Wst = Aring + 2 * (size_t)LT_STAGE_BYTES;              // nkb x [hi 16 KB | lo 16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Wst + (size_t)a.nkb * LT_STAGE_BYTES);

@@ -19,6 +19,10 @@ namespace tc {
 
 FDPT_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// bytes to skip so that the dynamic shared-memory window starts 1024-byte aligned (swizzle atoms).  Rounding the POINTER up through
+// uintptr_t loses the address space: every later access becomes a generic LD / ST (long-scoreboard latency) instead of LDS / STS.
+FDPT_DEVINL uint32_t smem_align_pad(const void* smem_raw) { return (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u; }
+
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is still
 // running (as soon as every predecessor CTA has called launch_dependents or exited); it must call pdl_wait() before it touches

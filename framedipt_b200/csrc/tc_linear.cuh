@@ -23,7 +23,7 @@ struct TcLinearArgs {
 __global__ void __launch_bounds__(192, 1) tc_linear_kernel(TcLinearArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A image: K/64 x 16 KB][weight stages: LIN_STAGES x 16 KB][barriers]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   const int nkb = a.K / KB;
   uint8_t* Aimg = smem;
   uint8_t* Wst = Aimg + (size_t)nkb * 16384;

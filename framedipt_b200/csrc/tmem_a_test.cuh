@@ -18,6 +18,13 @@ FDPT_DEVINL void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
         "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+FDPT_DEVINL void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               :
+               : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+                 "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+               : "memory");
+}
 FDPT_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] . B[smem desc]^T
 FDPT_DEVINL void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -33,7 +40,7 @@ FDPT_DEVINL void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, 
 // one CTA of 128 threads: A [128, 64] fp32, B [128, 64] fp32 (row-major) -> D [128, 128] fp32
 __global__ void __launch_bounds__(128) tmem_a_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   uint8_t* Bimg = smem;  // 128 rows x 128 B, swizzled
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);

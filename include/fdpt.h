@@ -242,8 +242,8 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition) */
 enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
        FDPT_OPT_ET_PAIR = 5 /* retired: the cta_group::2 EdgeTransition variant of round 1 was slower (1.3 vs 1.0 ms) and has been removed */,
-       FDPT_OPT_ET_R2_TMEM = 10 /* 1 (default): the fused EdgeTransition kernel hands r2 to its third GEMM through tensor memory
-                                   (tcgen05.st in place over D2, tcgen05.mma with the A operand in TMEM); 0: through shared memory */,
+       FDPT_OPT_ET_R2_TMEM = 10 /* retired switch: the fused EdgeTransition kernel always hands r2 to its third GEMM through tensor memory
+                                   (tcgen05.st in place over D2, tcgen05.mma with the A operand in TMEM); 0 is rejected */,
        FDPT_OPT_LIN_WRES = 9 /* 1 (default): Linear layers whose CTAs own a single n-tile run the weight-resident kernel (lin_tcw.cuh: whole
                                 weight panel prefetched under the predecessor's tail, activation streamed); 0: lin_tc.  A/B switch */,
        FDPT_OPT_TF_IMG = 8 /* 1 (default): the sequence transformer's attention GEMMs multiply operand images written by the in_proj

@@ -14,7 +14,7 @@ node = torch.randn(B, N, 256, device="cuda"); z = torch.randn(B, N, N, 128, devi
 for _ in range(2):
     ctx.edge_transition(0, node, z, mask)
 ts = ctx.debug_read().reshape(8, 48)
-names = {0: "M tile start", 42: "M G1(0) kb0 local landed", 43: "M G1(0) kb0 peer landed", 44: "M G1(0) kb1 local landed", 45: "M G1(0) kb1 peer landed", 46: "M G1(0) kb2 local landed", 47: "M G1(0) kb2 peer landed", 33: "L G1(0) kb0 TMA issued", 34: "L G1(0) kb1 TMA issued", 35: "L G1(0) kb2 TMA issued", 36: "L G1(0) kb3 TMA issued", 37: "M G1(0) kb1 issued", 38: "M G1(0) kb2 issued", 39: "M G1(0) kb3 issued", 14: "M G1(0) ds_empty ok", 15: "M G1(0) kb0 issued", 1: "M G1(0) issued", 2: "M G1(1) issued", 3: "M G2(0) issued", 4: "M G1(2) issued", 5: "M G2(1) issued", 6: "M G2(2) issued",
+names = {0: "M tile start", 42: "M G1(0) kb0 local landed", 43: "M G1(0) kb0 peer landed", 44: "M G1(0) kb1 local landed", 45: "M G1(0) kb1 peer landed", 46: "M G1(0) kb2 local landed", 47: "M G1(0) kb2 peer landed", 33: "W E3 D3 loaded", 34: "W E3 partial stats done", 35: "W E3 barrier passed", 36: "L G1(0) kb3 TMA issued", 37: "M G1(0) kb1 issued", 38: "M G1(0) kb2 issued", 39: "M G1(0) kb3 issued", 14: "M G1(0) ds_empty ok", 15: "M G1(0) kb0 issued", 1: "M G1(0) issued", 2: "M G1(1) issued", 3: "M G2(0) issued", 4: "M G1(2) issued", 5: "M G2(1) issued", 6: "M G2(2) issued",
          7: "M G3s issued", 11: "M G3p0 bufwait done", 8: "M G3p(0) issued", 9: "M G3p(1) issued", 10: "M G3p(2) issued",
          16: "W tile start", 17: "W E1(0) ds_full", 18: "W E1(0) math done", 19: "W E1(0) stored", 20: "W E1(1) ds_full", 21: "W E1(1) math done",
          22: "W E1(1) stored", 23: "W E1(2) ds_full", 24: "W E1(2) math done", 25: "W E1(2) stored", 26: "W E2 d2_full", 27: "W E2(0) stored",
