@@ -87,8 +87,10 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   uint64_t* buf_full = ds_empty + 1;         // [2]
   uint64_t* buf_free = buf_full + 2;         // [2]
   uint64_t* d2_full = buf_free + 2;          // [1]
-  uint64_t* d2_empty = d2_full + 1;          // [1]
-  uint64_t* vec_full = d2_empty + 1;         // [2]
+  uint64_t* sb_full = d2_full + 1;           // [1] G1(1)'s output is in the second staging buffer (D2's idle columns [256,384))
+  uint64_t* sb_empty = sb_full + 1;          // [1] ... and the workers have drained it
+  uint64_t* an_empty = sb_empty + 1;         // [1] the tile's last reader of the n_j image has completed
+  uint64_t* vec_full = an_empty + 1;         // [2]
   uint64_t* vec_free = vec_full + 2;         // [2]
   uint64_t* stg_full = vec_free + 2;         // [1] all workers have written their part of the output tile into BUF[1]
   uint64_t* r2_full = stg_full + 1;          // [3] chunk c of r2 is in tensor memory (fp16, A operand of GEMM3)
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   float* be_s = g_s + 128;                                 // [128]
   float* red_s = be_s + 128;                               // [ET_GROUPS][128] LayerNorm partial means of the worker groups
   float* red_q = red_s + ET_GROUPS * 128;                  // [ET_GROUPS][128] partial sums of squared deviations
+  float* mk_s = red_q + ET_GROUPS * 128;                   // [2][128] pair mask of the tile's rows (prefetched with the epilogue vectors)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long per = (a.tiles + gridDim.x - 1) / gridDim.x;
@@ -121,6 +124,9 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     mbar_init(ds_full, 1);
     mbar_init(ds_empty, ET_WORKERS);
     mbar_init(d2_full, 1);
+    mbar_init(sb_full, 1);
+    mbar_init(sb_empty, ET_WORKERS);
+    mbar_init(an_empty, 1);
     mbar_init(stg_full, ET_WORKERS);
     for (int c = 0; c < 3; ++c) mbar_init(&r2_full[c], ET_WORKERS);
     for (int s = 0; s < 2; ++s) {
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t D2 = tmem_base, DS = tmem_base + 384;
+  const uint32_t D2 = tmem_base, DS = tmem_base + 384, SB = tmem_base + 256;
 
   // tile -> (b*N+i, jb); the n_j image changes when (b, jb) changes. Tiles are ordered (b, jb, i) with i fastest.
   auto tile_bjb = [&](long long t) -> long long { return (long long)((unsigned)t / (unsigned)a.N); };  // b*JB + jb (tiles < 2^31)
@@ -185,19 +191,22 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       load_n(t_begin);
       for (long long t = t_begin; t < t_end; ++t) {
         // weight stream in the exact order the MMA warp consumes it
-        for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 0, kb);                                   // G1(0)
-        for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 128, kb);                                 // G1(1)
+        for (int c = 0; c < 3; ++c)
+          for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, c * 128, kb);                           // G1(0), G1(1), G1(2)
         for (int n = 0; n < 3; ++n) for (int kb = 0; kb < 2; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(0)
-        for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, 256, kb);                                 // G1(2)
+        for (int kb = 6; kb < 8; ++kb) stage(a.W3cat, 128, 0, kb);                                   // G3 static, z part
         for (int n = 0; n < 3; ++n) for (int kb = 2; kb < 4; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(1)
-        for (int n = 0; n < 3; ++n) for (int kb = 4; kb < 6; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(2)
-        for (int kb = 6; kb < 10; ++kb) stage(a.W3cat, 128, 0, kb);                                  // G3 static ([z | n_j])
-        for (int kb = 0; kb < 6; ++kb) stage(a.W3cat, 128, 0, kb);                                   // G3 partials
         if (t + 1 < t_end) {
-          // tile t's last reader of z and n_j (G3 static) has completed: fetch the next tile's z (and the n_j image if it changes)
+          // tile t's last reader of z (G3 static, z part) precedes G2(1) in the tensor pipe: fetch the next tile's z now
           mbar_wait(&az_empty[0], (uint32_t)(t - t_begin) & 1);
           load_z(t + 1);
-          if (tile_bjb(t + 1) != tile_bjb(t)) load_n(t + 1);
+        }
+        for (int n = 0; n < 3; ++n) for (int kb = 4; kb < 6; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(2)
+        for (int kb = 8; kb < 10; ++kb) stage(a.W3cat, 128, 0, kb);                                  // G3 static, n_j part
+        for (int kb = 0; kb < 6; ++kb) stage(a.W3cat, 128, 0, kb);                                   // G3 partials
+        if (t + 1 < t_end && tile_bjb(t + 1) != tile_bjb(t)) {
+          mbar_wait(an_empty, (uint32_t)(t - t_begin) & 1);  // the n_j image changes: its last reader (G3 static, n_j part) has completed
+          load_n(t + 1);
         }
       }
     }
@@ -206,10 +215,15 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     for (long long t = t_begin; t < t_end; ++t) {
       const uint32_t n = (uint32_t)(t - t_begin), buf = n & 1;
       mbar_wait(&vec_free[buf], ((n >> 1) & 1) ^ 1);
-      int jb;
-      const long long m = tile_m(t, jb);
+      int jb, bsamp;
+      const long long m = tile_mb(t, jb, bsamp);
       for (int k = lane; k < 384; k += 32) Ui_s[buf * 384 + k] = a.Ui[m * 384 + k];
       for (int k = lane; k < 128; k += 32) Pf_s[buf * 128 + k] = a.Pf[m * 128 + k];
+      const float mi = a.mask[m];
+      for (int k = lane; k < 128; k += 32) {
+        const int j = jb * 128 + k;
+        mk_s[buf * 128 + k] = j < a.N ? mi * a.mask[(long long)bsamp * a.N + j] : 0.f;
+      }
       mbar_arrive(&vec_full[buf]);
     }
   } else if (warp == ET_WW) {
@@ -240,42 +254,53 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         const uint32_t az = smem_u32(A0z), an = smem_u32(A0n);
         const uint32_t bufa[2] = {smem_u32(BUF), smem_u32(BUF + ET_TILE_BYTES)};
         auto a0_kb = [&](int kb) { return kb < 2 ? az + kb * 16384 : an + (kb - 2) * 16384; };
-        auto G1 = [&](int c) {
-          (void)c;
+        auto wait_sa = [&]() {  // DS drained by the workers (E1(0) / E1(2) / E3 hold its content in registers)
           mbar_wait(ds_empty, (ds_e & 1) ^ 1);
           ++ds_e;
           tc_fence_after();
-          for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
-          umma_commit(ds_full);
         };
         auto G2 = [&](int c) {
           const int b = c & 1;
           mbar_wait(&buf_full[b], bf[b] & 1);
           ++bf[b];
           tc_fence_after();
-          for (int n = 0; n < 3; ++n)
+          for (int n = 0; n < 3; ++n) {
+            if (c == 0 && n == 2) {  // D2[256,384) staged G1(1)'s output: wait until E1(1) has drained it
+              mbar_wait(sb_empty, (uint32_t)(t - t_begin) & 1);
+              tc_fence_after();
+            }
             for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, D2 + n * 128, c == 0 && kb == 0);
+          }
           umma_commit(&buf_free[b]);
           if (c == 2) umma_commit(d2_full);
         };
-        G1(0);
+        // All three chunks of GEMM 1 are issued back to back: chunk 0 into DS, chunk 1 into D2's columns [256,384) -- idle between the
+        // previous tile's G3 partial products (in order in the tensor pipe, so no barrier) and this tile's G2(0) -- chunk 2 into DS again
+        // once E1(0) holds chunk 0 in registers.  Chunks 0 and 1 therefore run while the workers are still in the previous tile's E3.
+        wait_sa();
+        for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
+        umma_commit(ds_full);
         ET_TS(1);
-        G1(1);
+        for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), SB, kb == 0);
+        umma_commit(sb_full);
         ET_TS(2);
+        wait_sa();
+        for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
+        umma_commit(ds_full);
+        ET_TS(4);
         G2(0);
         ET_TS(3);
-        G1(2);
-        ET_TS(4);
+        // G3 static, z part: z . W3cat[:, 384:512]^T -> DS (E1(2) holds chunk 2 in registers); releases the z tile for the next fetch
+        wait_sa();
+        for (int kb = 0; kb < 2; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
+        umma_commit(&az_empty[0]);
         G2(1);
         ET_TS(5);
         G2(2);
         ET_TS(6);
-        // G3 static part: [z | n_j] . W3cat[:, 384:640]^T  -> DS (after E1(2) has drained it)
-        mbar_wait(ds_empty, (ds_e & 1) ^ 1);
-        ++ds_e;
-        tc_fence_after();
-        for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
-        umma_commit(&az_empty[0]);
+        // G3 static, n_j part (fills the tensor pipe while E2(0) runs)
+        for (int kb = 2; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, false);
+        umma_commit(an_empty);
         ET_TS(7);
         // G3 partial products: A = r2 chunk c straight from tensor memory (the workers wrote it in place over D2: the 16 K-elements of
         // k-step j of the chunk sit packed in the 8 columns D2 + 128 c + ET_GC (16 j / ET_GC) + (16 j % ET_GC) / 2), B = W3cat k-block
@@ -330,14 +355,12 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     for (long long t = t_begin; t < t_end; ++t) {
       int jb, bsamp;
       const long long m = tile_mb(t, jb, bsamp);
-      const int j = jb * 128 + row;
       // per-tile epilogue vectors (same i for the whole tile), prefetched by the vector warp
       const uint32_t vn = (uint32_t)(t - t_begin), vbuf = vn & 1;
       const float* Ui_t = Ui_s + vbuf * 384;
       const float* Pf_t = Pf_s + vbuf * 128;
-      float mk = 0.f;
-      if (j < a.N) mk = a.mask[m] * a.mask[(long long)bsamp * a.N + j];
       mbar_wait(&vec_full[vbuf], (vn >> 1) & 1);
+      const float mk = mk_s[vbuf * 128 + row];
       float v[ET_GC];
       if (threadIdx.x == 0) ET_TS(16);
       // ---- E1: three chunks of h1
@@ -346,13 +369,22 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive(&buf_free[1]);
         }
-        mbar_wait(ds_full, ds_f & 1);
-        ++ds_f;
-        tc_fence_after();
-        if (threadIdx.x == 0) ET_TS(17 + 3 * c);
-        load_part(DS, v);
-        tc_fence_before();
-        mbar_arrive(ds_empty);
+        if (c == 1) {
+          mbar_wait(sb_full, vn & 1);
+          tc_fence_after();
+          if (threadIdx.x == 0) ET_TS(17 + 3 * c);
+          load_part(SB, v);
+          tc_fence_before();
+          mbar_arrive(sb_empty);
+        } else {
+          mbar_wait(ds_full, ds_f & 1);
+          ++ds_f;
+          tc_fence_after();
+          if (threadIdx.x == 0) ET_TS(17 + 3 * c);
+          load_part(DS, v);
+          tc_fence_before();
+          mbar_arrive(ds_empty);
+        }
 #pragma unroll
         for (int n = 0; n < ET_GC; ++n) v[n] = fmaxf(v[n] + Ui_t[c * 128 + cg + n], 0.f);
         if (threadIdx.x == 0) ET_TS(18 + 3 * c);
@@ -447,7 +479,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
 }
 
 inline size_t et_smem_bytes() {
-  return 1024 + 4 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 44 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 2 * ET_GROUPS * 128) * 4 + 64 + 32;
+  return 1024 + 4 * (size_t)ET_TILE_BYTES + ET_WSTAGES * ET_STAGE_BYTES + 44 * 8 + 16 + (2 * 384 + 2 * 128 + 384 + 128 + 128 + 2 * ET_GROUPS * 128 + 256) * 4 + 64 + 32;
 }
 
 // ---- layout helpers --------------------------------------------------------------------------------------------------
