@@ -34,6 +34,10 @@ namespace tc {
 constexpr int ET_TILE_BYTES = 32768;    // 128 rows x 128 halfs (two k-blocks)
 constexpr int ET_WSTAGES = 5;
 constexpr int ET_STAGE_BYTES = 16384;   // 128 weight rows x one k-block
+constexpr int ET_KB_PER_TILE = 40;      // weight k-blocks streamed per tile (G1 12 + G2 18 + G3 10)
+// every tile starts at ring stage 0 with an even number of uses per stage, so stage index and barrier parity of each of the 40 uses
+// are compile-time constants in the fully unrolled issue sequence (no modulo / phase arithmetic on the issuing thread's critical path)
+static_assert(ET_KB_PER_TILE % ET_WSTAGES == 0 && (ET_KB_PER_TILE / ET_WSTAGES) % 2 == 0, "ring depth must divide the per-tile stream evenly");
 
 struct EtArgs {
   int B, N, JB;                 // JB = ceil(N/128) j-blocks
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   if (warp == ET_WW + 1) {
     // ============================ loader ============================
     if (elect_one() && t_begin < t_end) {
-      uint32_t wit = 0;      // weight stage counter
+      uint32_t wit = 0;      // weight stage counter of the tile
       auto load_z = [&](long long t) {
         mbar_arrive_expect_tx(&az_full[0], ET_TILE_BYTES);
         int jb;
@@ -191,18 +195,33 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       load_n(t_begin);
       for (long long t = t_begin; t < t_end; ++t) {
         // weight stream in the exact order the MMA warp consumes it
+        wit = 0;
+#pragma unroll
         for (int c = 0; c < 3; ++c)
+#pragma unroll
           for (int kb = 0; kb < 4; ++kb) stage(a.W1cat, 384, c * 128, kb);                           // G1(0), G1(1), G1(2)
-        for (int n = 0; n < 3; ++n) for (int kb = 0; kb < 2; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(0)
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) stage(a.W2, 384, n * 128, kb);                              // G2(0)
+#pragma unroll
         for (int kb = 6; kb < 8; ++kb) stage(a.W3cat, 128, 0, kb);                                   // G3 static, z part
-        for (int n = 0; n < 3; ++n) for (int kb = 2; kb < 4; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(1)
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+#pragma unroll
+          for (int kb = 2; kb < 4; ++kb) stage(a.W2, 384, n * 128, kb);                              // G2(1)
         if (t + 1 < t_end) {
           // tile t's last reader of z (G3 static, z part) precedes G2(1) in the tensor pipe: fetch the next tile's z now
           mbar_wait(&az_empty[0], (uint32_t)(t - t_begin) & 1);
           load_z(t + 1);
         }
-        for (int n = 0; n < 3; ++n) for (int kb = 4; kb < 6; ++kb) stage(a.W2, 384, n * 128, kb);      // G2(2)
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+#pragma unroll
+          for (int kb = 4; kb < 6; ++kb) stage(a.W2, 384, n * 128, kb);                              // G2(2)
+#pragma unroll
         for (int kb = 8; kb < 10; ++kb) stage(a.W3cat, 128, 0, kb);                                  // G3 static, n_j part
+#pragma unroll
         for (int kb = 0; kb < 6; ++kb) stage(a.W3cat, 128, 0, kb);                                   // G3 partials
         if (t + 1 < t_end && tile_bjb(t + 1) != tile_bjb(t)) {
           mbar_wait(an_empty, (uint32_t)(t - t_begin) & 1);  // the n_j image changes: its last reader (G3 static, n_j part) has completed
@@ -230,7 +249,8 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     // ============================ MMA issuer ============================
     if (elect_one()) {
       const uint32_t idesc = (a.exp & 2) ? make_idesc_f16(128, 16) : make_idesc_f16(128, 128);
-      uint32_t wit = 0, ds_e = 0, bf[2] = {0, 0}, an_f = 0;
+      uint32_t ds_e = 0, bf[2] = {0, 0}, an_f = 0;
+      uint32_t wit = 0;  // weight stage counter of the tile (see ET_KB_PER_TILE: stage index and parity of every use are compile-time constants)
       auto gemm_kb = [&](uint32_t a_addr, uint32_t d_col, bool first_acc) {
         // one k-block: wait the weight stage, 4 x (128x128x16) MMAs, release the stage
         const int s = wit % ET_WSTAGES;
@@ -244,6 +264,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         ++wit;
       };
       for (long long t = t_begin; t < t_end; ++t) {
+        wit = 0;
         mbar_wait(&az_full[0], (uint32_t)(t - t_begin) & 1);
         if (t == t_begin || tile_bjb(t) != tile_bjb(t - 1)) {
           mbar_wait(an_full, an_f & 1);
@@ -264,11 +285,13 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
           mbar_wait(&buf_full[b], bf[b] & 1);
           ++bf[b];
           tc_fence_after();
+#pragma unroll
           for (int n = 0; n < 3; ++n) {
             if (c == 0 && n == 2) {  // D2[256,384) staged G1(1)'s output: wait until E1(1) has drained it
               mbar_wait(sb_empty, (uint32_t)(t - t_begin) & 1);
               tc_fence_after();
             }
+#pragma unroll
             for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, D2 + n * 128, c == 0 && kb == 0);
           }
           umma_commit(&buf_free[b]);
@@ -278,13 +301,16 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         // previous tile's G3 partial products (in order in the tensor pipe, so no barrier) and this tile's G2(0) -- chunk 2 into DS again
         // once E1(0) holds chunk 0 in registers.  Chunks 0 and 1 therefore run while the workers are still in the previous tile's E3.
         wait_sa();
+#pragma unroll
         for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
         umma_commit(ds_full);
         ET_TS(1);
+#pragma unroll
         for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), SB, kb == 0);
         umma_commit(sb_full);
         ET_TS(2);
         wait_sa();
+#pragma unroll
         for (int kb = 0; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
         umma_commit(ds_full);
         ET_TS(4);
@@ -292,6 +318,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         ET_TS(3);
         // G3 static, z part: z . W3cat[:, 384:512]^T -> DS (E1(2) holds chunk 2 in registers); releases the z tile for the next fetch
         wait_sa();
+#pragma unroll
         for (int kb = 0; kb < 2; ++kb) gemm_kb(a0_kb(kb), DS, kb == 0);
         umma_commit(&az_empty[0]);
         G2(1);
@@ -299,16 +326,19 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         G2(2);
         ET_TS(6);
         // G3 static, n_j part (fills the tensor pipe while E2(0) runs)
+#pragma unroll
         for (int kb = 2; kb < 4; ++kb) gemm_kb(a0_kb(kb), DS, false);
         umma_commit(an_empty);
         ET_TS(7);
         // G3 partial products: A = r2 chunk c straight from tensor memory (the workers wrote it in place over D2: the 16 K-elements of
         // k-step j of the chunk sit packed in the 8 columns D2 + 128 c + ET_GC (16 j / ET_GC) + (16 j % ET_GC) / 2), B = W3cat k-block
         // 2c + kb from the weight ring
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
           mbar_wait(&r2_full[c], (uint32_t)(t - t_begin) & 1);
           tc_fence_after();
           ET_TS(11 + c);
+#pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
             const int s = wit % ET_WSTAGES;
             mbar_wait(&w_full[s], (wit / ET_WSTAGES) & 1);
