@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
   uint64_t* ds_empty = ds_full + 1;          // [1]
   uint64_t* buf_full = ds_empty + 1;         // [2]
   uint64_t* buf_free = buf_full + 2;         // [2]
-  uint64_t* d2_full = buf_free + 2;          // [1]
-  uint64_t* sb_full = d2_full + 1;           // [1] G1(1)'s output is in the second staging buffer (D2's idle columns [256,384))
+  uint64_t* d2_full = buf_free + 2;          // [3] output chunk n of GEMM 2 is complete (committed after each n-block of G2(2))
+  uint64_t* sb_full = d2_full + 3;           // [1] G1(1)'s output is in the second staging buffer (D2's idle columns [256,384))
   uint64_t* sb_empty = sb_full + 1;          // [1] ... and the workers have drained it
   uint64_t* an_empty = sb_empty + 1;         // [1] the tile's last reader of the n_j image has completed
   uint64_t* vec_full = an_empty + 1;         // [2]
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     mbar_init(an_full, 1);
     mbar_init(ds_full, 1);
     mbar_init(ds_empty, ET_WORKERS);
-    mbar_init(d2_full, 1);
+    for (int c = 0; c < 3; ++c) mbar_init(&d2_full[c], 1);
     mbar_init(sb_full, 1);
     mbar_init(sb_empty, ET_WORKERS);
     mbar_init(an_empty, 1);
@@ -230,21 +230,43 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       }
     }
   } else if (warp == ET_WW + 2) {
-    // ============================ epilogue-vector prefetcher ============================
-    for (long long t = t_begin; t < t_end; ++t) {
-      const uint32_t n = (uint32_t)(t - t_begin), buf = n & 1;
-      mbar_wait(&vec_free[buf], ((n >> 1) & 1) ^ 1);
-      int jb, bsamp;
-      const long long m = tile_mb(t, jb, bsamp);
-      for (int k = lane; k < 384; k += 32) Ui_s[buf * 384 + k] = a.Ui[m * 384 + k];
-      for (int k = lane; k < 128; k += 32) Pf_s[buf * 128 + k] = a.Pf[m * 128 + k];
-      const float mi = a.mask[m];
-      for (int k = lane; k < 128; k += 32) {
-        const int j = jb * 128 + k;
-        mk_s[buf * 128 + k] = j < a.N ? mi * a.mask[(long long)bsamp * a.N + j] : 0.f;
+    // ============================ epilogue-vector prefetcher + output store ============================
+    // iteration n: fetch the vectors of tile n (one tile ahead of the workers), then wait until the workers have staged tile n-1's
+    // output in BUF[1], bulk-store it and hand BUF[1] back once the copy engine has read it
+    const long long ntl = t_end - t_begin;
+    for (long long n = 0; n <= ntl && ntl > 0; ++n) {
+      if (n < ntl) {
+        const long long t = t_begin + n;
+        const uint32_t buf = (uint32_t)n & 1;
+        mbar_wait(&vec_free[buf], (((uint32_t)n >> 1) & 1) ^ 1);
+        int jb, bsamp;
+        const long long m = tile_mb(t, jb, bsamp);
+        for (int k = lane; k < 384; k += 32) Ui_s[buf * 384 + k] = a.Ui[m * 384 + k];
+        for (int k = lane; k < 128; k += 32) Pf_s[buf * 128 + k] = a.Pf[m * 128 + k];
+        const float mi = a.mask[m];
+        for (int k = lane; k < 128; k += 32) {
+          const int j = jb * 128 + k;
+          mk_s[buf * 128 + k] = j < a.N ? mi * a.mask[(long long)bsamp * a.N + j] : 0.f;
+        }
+        mbar_arrive(&vec_full[buf]);
       }
-      mbar_arrive(&vec_full[buf]);
+      if (n >= 1) {
+        const long long t = t_begin + n - 1;
+        mbar_wait(stg_full, (uint32_t)(n - 1) & 1);
+        if (lane == 0) {
+          int jb;
+          const long long m = tile_m(t, jb);
+          uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * (long long)ET_TILE_BYTES);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(BUF + ET_TILE_BYTES)), "r"(ET_TILE_BYTES)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&buf_free[1]);
+        }
+        __syncwarp();
+      }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp == ET_WW) {
     // ============================ MMA issuer ============================
     if (elect_one()) {
@@ -293,9 +315,9 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
             }
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) gemm_kb(bufa[b] + kb * 16384, D2 + n * 128, c == 0 && kb == 0);
+            if (c == 2) umma_commit(&d2_full[n]);  // E2(n) starts while the later output chunks are still accumulating
           }
           umma_commit(&buf_free[b]);
-          if (c == 2) umma_commit(d2_full);
         };
         // All three chunks of GEMM 1 are issued back to back: chunk 0 into DS, chunk 1 into D2's columns [256,384) -- idle between the
         // previous tile's G3 partial products (in order in the tensor pipe, so no barrier) and this tile's G2(0) -- chunk 2 into DS again
@@ -364,7 +386,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
     const int row = (warp & 3) * 32 + lane;
     const int cg = wg * ET_GC;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t ds_f = 0, fr[2] = {0, 0}, d2_f = 0;
+    uint32_t ds_f = 0, fr[2] = {0, 0};
     auto wait_free = [&](int b) {
       mbar_wait(&buf_free[b], (fr[b] & 1) ^ 1);
       ++fr[b];
@@ -395,10 +417,6 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       if (threadIdx.x == 0) ET_TS(16);
       // ---- E1: three chunks of h1
       for (int c = 0; c < 3; ++c) {
-        if (c == 1 && threadIdx.x == 0 && t != t_begin) {  // BUF[1] staged the previous tile's output: its bulk store has finished reading by now
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(&buf_free[1]);
-        }
         if (c == 1) {
           mbar_wait(sb_full, vn & 1);
           tc_fence_after();
@@ -425,11 +443,10 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
         if (threadIdx.x == 0) ET_TS(19 + 3 * c);
       }
       // ---- E2: three chunks of r2, written back in place (this thread's 32 fp32 columns become 16 packed fp16 columns)
-      mbar_wait(d2_full, d2_f & 1);
-      ++d2_f;
-      tc_fence_after();
-      if (threadIdx.x == 0) ET_TS(26);
       for (int c = 0; c < 3; ++c) {
+        mbar_wait(&d2_full[c], vn & 1);
+        tc_fence_after();
+        if (threadIdx.x == 0 && c == 0) ET_TS(26);
         load_part(D2 + c * 128, v);
         uint32_t pk[ET_GC / 2];
 #pragma unroll
@@ -491,17 +508,9 @@ __global__ void __launch_bounds__(ET_THREADS, 1) et_fused_kernel(EtArgs a) {
       wait_free(1);  // BUF[1]'s last reader was G2(1) (h1 chunk 1); its release is consumed here (already complete: D3 is)
       if (!(a.exp & 4)) store_part(BUF + ET_TILE_BYTES, v);
       fence_proxy_async();
-      mbar_arrive(stg_full);
-      if (threadIdx.x == 0) {
-        mbar_wait(stg_full, vn & 1);
-        uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * (long long)ET_TILE_BYTES);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(BUF + ET_TILE_BYTES)), "r"(ET_TILE_BYTES)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        ET_TS(32);
-      }
+      mbar_arrive(stg_full);  // the vector warp issues the bulk store of the staged tile
+      if (threadIdx.x == 0) ET_TS(32);
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
