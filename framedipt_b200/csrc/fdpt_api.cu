@@ -482,11 +482,11 @@ struct Lin {
         a.units = std::min(8, (int)((ctx->max_smem_optin - tc::lin_tc_fixed_bytes(pw.nkb, a.stg_cols)) / tc::LT_UNIT_BYTES));
         a.bias = bias; a.relu = relu; a.rowmask = rowmask; a.residual = residual; a.ldr = ldr; a.Y = y; a.ldy = ldc;
         a.dbg_flags = ctx->dbg_flags;
-        a.dbg = (ctx->dbg_flags & 512) ? ctx->et_dbg : nullptr;
+        a.dbg = (ctx->dbg_flags & (512 | (1 << 19))) ? ctx->et_dbg : nullptr;  // bit 19: stamps inside the weight-resident variant
         if (y_img) a.dbg = reinterpret_cast<long long*>(y_img);  // lin_tc_kernel<*, YIMG = true> writes the output image through this field
         if (x_img) a.X = reinterpret_cast<const float*>(x_img);  // lin_tc_kernel<XIMG = true> reads X as the operand image
         a.x_vec = tc::aligned16(x, lda, 0, 0);
-        a.y_vec = 0;
+        a.y_vec = (y && tc::aligned16(y, ldc, 0, 0) && (!residual || tc::aligned16(residual, ldr, 0, 0)) && N % 4 == 0) ? 1 : 0;
         dim3 grid(m_tiles, (pw.n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int m0 = blockIdx.x * 128;
   const int nt = blockIdx.y;  // this CTA's n-tile
+  if (tid == 0) LT_TS(0);
 
   if (tid == 0) {
     for (int k = 0; k < LT_MAX_KB; ++k) mbar_init(&w_full[k], 1);
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
+  if (tid == 0) LT_TS(1);
 
   if (warp == 9) {
     // ============================ weight loader: the whole panel, before the predecessor kernel has finished ============================
@@ -65,7 +67,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
       for (int kb = 0; kb < a.nkb; ++kb) {
         const int s = kb & 1;
         mbar_wait(&w_full[kb], 0);
+        if (kb == 0) LT_TS(7);
         mbar_wait(&a_full[s], (kb >> 1) & 1);
+        if (kb == 0) LT_TS(6);
         tc_fence_after();
         const uint32_t ah = smem_u32(Aring + (size_t)s * LT_STAGE_BYTES), al = ah + 16384;
         const uint32_t bh = smem_u32(Wst + (size_t)kb * LT_STAGE_BYTES), bl = bh + 16384;
@@ -81,10 +85,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
         umma_commit(&a_empty[s]);
       }
       umma_commit(acc_full);
+      LT_TS(8);
     }
   } else {
     // ============================ workers: feed the activation ring, then the epilogue ============================
     pdl_wait();  // X (and residual / Y) belong to the predecessor kernel until it has completed
+    if (tid == 0) LT_TS(2);
     if constexpr (XIMG) {
       if (tid == 0) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.X) + (size_t)blockIdx.x * a.nkb * LT_STAGE_BYTES;
@@ -114,10 +120,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
           store_tile(pa, Aring + (size_t)s * LT_STAGE_BYTES, ta[s]);
           fence_proxy_async();
           mbar_arrive(&a_full[s]);
+          if (tid == 0 && kb == 0) LT_TS(4);
           if (kb + 2 < a.nkb) load_tile(pa, kb + 2, ta[s]);
         }
       }
     }
+    if (tid == 0) LT_TS(5);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int c_half = (warp >> 2) * 64;
     const int mw = m0 + (warp & 3) * 32;
@@ -127,7 +135,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
     ep.ldr = a.ldr; ep.accumulate = 0; ep.Y = a.Y; ep.ldy = a.ldy;
     mbar_wait(acc_full, 0);  // every MMA has completed: the activation ring is idle and becomes the transposition patches
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(Aring) + warp * 32 * 17;
+    if (tid == 0) LT_TS(9);
+    // private transposition patch of the warp (the vectorised path needs 32 x 36 floats, the scalar fallback 32 x 17)
+    float* stg = reinterpret_cast<float*>(Aring) + warp * ST4_PATCH_FLOATS;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int cb = c_half + q * 32;
@@ -135,6 +145,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
       tmem_ld32(tmem_base + lane_base + cb, v);
       tmem_ld32(tmem_base + lane_base + 128 + cb, x2);
       tmem_ld_wait();
+      if (tid == 0 && q == 1) LT_TS(10);
       if (n0 + cb >= a.N) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
@@ -165,12 +176,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
         }
         if (!a.Y) continue;
       }
-      store_transposed<16>(ep, v, stg, lane, mw, n0 + cb);
+      if (a.y_vec) store_transposed_v4(ep, v, stg, lane, mw, n0 + cb);
+      else store_transposed<16>(ep, v, stg, lane, mw, n0 + cb);
     }
+    if (tid == 0) LT_TS(11);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, 256);
+  if (tid == 0) LT_TS(12);
 }
 
 inline size_t lin_tcw_smem_bytes(int nkb) { return 1024 + (size_t)(2 + nkb) * LT_STAGE_BYTES + (LT_MAX_KB + 5) * 8 + 64; }

@@ -9,7 +9,7 @@ names = ["kernel start", "setup done (barriers, TMEM)", "W pdl_wait done", "W fi
          "M a_full[0] seen", "M first weights seen", "M tile 0 MMAs issued", "W acc_full seen", "W TMEM loaded", "W stores issued", "all warps done"]
 for name, M, N, K in [("256x256", 2800, 256, 256), ("320x320", 2800, 320, 320), ("in_proj 960", 2800, 960, 320), ("N=128 K=256", 2800, 128, 256)]:
     x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda"); b = torch.randn(N, device="cuda")
-    ctx.set_option(3, 512)
+    ctx.set_option(3, int(os.environ.get("LT_FLAG", "512")))
     us = ctx.bench_linear(x, w, b)
     ts = ctx.debug_read(16)
     ctx.set_option(3, 0)
