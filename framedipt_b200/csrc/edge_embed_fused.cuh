@@ -11,9 +11,9 @@
 //   GEMM1  D1 = h1 . W2^T                                                        E1: h2 = relu(D1 + b2)              -> fp16 A2
 //   GEMM2  D2 = h2 . W4^T                                                        E2: z0 = LN(D2 + b4) * m_i m_j      -> fp16 tile image
 //
-// All three weight matrices (96 KB as fp16 swizzled images) stay resident in shared memory.  Warps 0-7: workers in two groups of 128
-// (thread <-> pair row <-> TMEM lane; group g owns columns [64g, 64g+64) = k-block g of every buffer it writes; group 0 builds the
-// idx_emb half of the per-tile feature block, group 1 the distogram half), warp 8: MMA issuer + TMEM owner, warp 9: loader.  MMA issue order G1(t), G2(t), G0(t+1): the first GEMM
+// All three weight matrices (96 KB as fp16 swizzled images) stay resident in shared memory.  Warps 0-15: workers in four groups of 128
+// (thread <-> pair row <-> TMEM lane; group g owns columns [32g, 32g+32) of every buffer it writes; groups 0, 1 build the idx_emb
+// half of the per-tile feature block, groups 2, 3 the distogram half), warp 16: MMA issuer + TMEM owner, warp 17: loader.  MMA issue order G1(t), G2(t), G0(t+1): the first GEMM
 // of the next tile runs under the LayerNorm epilogue of this one and is done when the workers get there.  fp16 operands (10-bit mantissa = TF32 class, which the pair side
 // tolerates: SURVEY §7 hard part 1), fp32 accumulate, positional tables evaluated on the host and gathered here.
 #pragma once
@@ -47,7 +47,10 @@ struct EeArgs {
   } while (0)
 
 constexpr int EE_W_BYTES = 32768;
-constexpr int EE_WORKERS = 256;
+constexpr int EE_GROUPS = 4;                      // worker groups of 128 threads (thread <-> pair row <-> TMEM lane)
+constexpr int EE_GC = 128 / EE_GROUPS;            // columns of every 128-column buffer owned by one group
+constexpr int EE_WORKERS = 128 * EE_GROUPS;
+constexpr int EE_WW = EE_WORKERS / 32;            // worker warps; then the MMA warp and the loader warp
 constexpr int EE_THREADS = EE_WORKERS + 64;
 
 __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
@@ -70,7 +73,9 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
   uint64_t* d1_full = bars + 7;     // [1]
   uint64_t* a2_full = bars + 8;     // [1]
   uint64_t* d2_full = bars + 9;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* stg_full = bars + 10;   // [1] every worker has written its part of the output tile into A1
+  uint64_t* a1_free = bars + 11;    // [1] the bulk store of the staged tile has finished reading A1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float* PA_s = reinterpret_cast<float*>(tmem_slot + 4);  // [128]
   float* b2_s = PA_s + 128;
   float* b4_s = b2_s + 128;
@@ -78,6 +83,8 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
   float* be_s = g_s + 128;
   float* lower_s = be_s + 128;  // [24]
   float* PA_s2 = lower_s + 24;  // [128] second PA buffer (tiles alternate between PA_s and PA_s2)
+  float* red_s = PA_s2 + 128;   // [EE_GROUPS][128] LayerNorm partial means of the worker groups
+  float* red_q = red_s + EE_GROUPS * 128;  // [EE_GROUPS][128] partial sums of squared deviations
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long per = (a.tiles + gridDim.x - 1) / gridDim.x;
@@ -95,6 +102,8 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
     mbar_init(d1_full, 1);
     mbar_init(a2_full, EE_WORKERS);
     mbar_init(d2_full, 1);
+    mbar_init(stg_full, EE_WORKERS);
+    mbar_init(a1_free, 1);
     fence_barrier_init();
   }
   for (int k = threadIdx.x; k < 128; k += blockDim.x) {
@@ -104,7 +113,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
     be_s[k] = a.ln_b[k];
   }
   if (threadIdx.x < 24) lower_s[threadIdx.x] = threadIdx.x < NBINS ? a.bin_lower[threadIdx.x] : 1e8f;  // [22] = top edge 1e8
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == EE_WW) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
     return (long long)b * a.N + i;
   };
 
-  if (warp == 9) {
+  if (warp == EE_WW + 1) {
     // ============================ loader ============================
     if (elect_one() && t_begin < t_end) {
       mbar_arrive_expect_tx(w_full, 3 * EE_W_BYTES);
@@ -136,15 +145,25 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
       };
       load_f(t_begin);
       uint32_t nfree = 0;
-      for (long long t = t_begin; t + 1 < t_end; ++t) {
-        if (tile_bjb(t + 1) != tile_bjb(t)) {
+      for (long long t = t_begin; t < t_end; ++t) {
+        if (t + 1 < t_end && tile_bjb(t + 1) != tile_bjb(t)) {
           mbar_wait(an_free, nfree & 1);  // GEMM0 of tile t (last reader of the old image) has completed
           ++nfree;
           load_f(t + 1);
         }
+        // output tile t is staged in A1: bulk-store it and hand A1 back once the copy engine has read it
+        mbar_wait(stg_full, (uint32_t)(t - t_begin) & 1);
+        int jb, b;
+        const long long m = tile_m(t, jb, b);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * 32768LL);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(A1)), "r"(32768) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(a1_free);
       }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-  } else if (warp == 8) {
+  } else if (warp == EE_WW) {
     // ============================ MMA issuer ============================
     if (elect_one() && t_begin < t_end) {
       const uint32_t idesc = make_idesc_f16(128, 128);
@@ -186,77 +205,103 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
       }
     }
   } else {
-    // ============================ workers (2 groups x 128 threads) ============================
+    // ============================ workers (EE_GROUPS groups x 128 threads) ============================
     const int wg = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
-    const int cg = wg * 64;
+    const int cg = wg * EE_GC;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    auto store_half = [&](uint8_t* buf, const float* v /*[64]*/) {  // fp16, swizzled, k-block `wg`, 8 chunks of row `row`
+    auto store_part = [&](uint8_t* buf, const float* v /*[32]*/) {  // fp16, swizzled: columns [cg, cg + 32) of row `row`
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const float* p = v + c * 8;
         const uint4 u = make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
-        *reinterpret_cast<uint4*>(buf + wg * 16384 + sw128_chunk_off(row, c)) = u;
+        *reinterpret_cast<uint4*>(buf + (wg >> 1) * 16384 + sw128_chunk_off(row, (wg & 1) * 4 + c)) = u;
       }
     };
-    auto load_half = [&](uint32_t taddr, float* v /*[64]*/) {
+    auto load_part = [&](uint32_t taddr, float* v /*[32]*/) {
       tmem_ld32(taddr + lane_base + cg, v);
-      tmem_ld32(taddr + lane_base + cg + 32, v + 32);
       tmem_ld_wait();
     };
-    // per-tile k-block [emb(rel) 32 | onehot(bin) 22 | 0 x 10] of row `row`: group 0 writes chunks 0-3, group 1 chunks 4-7
-    auto build_a0 = [&](long long t) {
+    // per-tile k-block [emb(rel) 32 | onehot(bin) 22 | 0 x 10] of row `row`: group g writes chunks 2g, 2g + 1 (groups 0, 1: the two
+    // halves of the embedding row; groups 2, 3: bins 0-15 / bins 16-21 + padding of the distogram one-hot)
+    // phases, so that the global-memory latencies do not sit on the workers' critical path: prep_a0 (top of the previous tile) only
+    // ISSUES the loads of the residue indices / CA coordinates; after E0, code_a0 reduces them to one small code (groups 0, 1: row of
+    // the relative-position table; groups 2, 3: distogram bin; -1: padding row) and emit_a0 gathers the table row and writes the chunks
+    struct A0Raw {  // what prep_a0 leaves in registers (loads issued, nothing consumed)
+      int si, sj, valid;
+      float ci[3], cj[3];
+    };
+    auto prep_a0 = [&](long long t) -> A0Raw {
+      A0Raw r;
+      r.si = r.sj = 0;
+      r.ci[0] = r.ci[1] = r.ci[2] = r.cj[0] = r.cj[1] = r.cj[2] = 0.f;
       int jb, b;
       const long long m = tile_m(t, jb, b);
       const int j = jb * 128 + row;
-      uint8_t* dst = A0t + ((t - t_begin) & 1) * 16384;
-      uint4 ch[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) ch[c] = make_uint4(0, 0, 0, 0);
-      if (j < a.N) {
+      r.valid = j < a.N;
+      if (r.valid) {
         const long long mj = (long long)b * a.N + j;
-        if (wg == 0) {
-          int rel = a.seq_idx[m] - a.seq_idx[mj] - a.rel_min;
-          rel = min(max(rel, 0), a.rel_count - 1);
-          const uint4* e = reinterpret_cast<const uint4*>(a.rel_tab + (long long)rel * EMB);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) ch[c] = __ldg(e + c);
+        if (wg < 2) {
+          r.si = a.seq_idx[m];
+          r.sj = a.seq_idx[mj];
         } else {
-          const float dx = a.sc_ca[m * 3 + 0] - a.sc_ca[mj * 3 + 0];
-          const float dy = a.sc_ca[m * 3 + 1] - a.sc_ca[mj * 3 + 1];
-          const float dz = a.sc_ca[m * 3 + 2] - a.sc_ca[mj * 3 + 2];
-          const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-          int bin = -1;
 #pragma unroll
-          for (int k = 0; k < NBINS; ++k)
-            if (d > lower_s[k] && d < lower_s[k + 1]) bin = k;  // strict on both sides (data/utils.py:547-549)
-          if (bin >= 0) {
-            const uint32_t one = (bin & 1) ? 0x3C000000u : 0x00003C00u;  // fp16 1.0 in the high / low half
-            uint32_t w[12];
+          for (int e = 0; e < 3; ++e) {
+            r.ci[e] = a.sc_ca[m * 3 + e];
+            r.cj[e] = a.sc_ca[mj * 3 + e];
+          }
+        }
+      }
+      return r;
+    };
+    auto code_a0 = [&](const A0Raw& r) -> int {
+      if (!r.valid) return -1;
+      if (wg < 2) return min(max(r.si - r.sj - a.rel_min, 0), a.rel_count - 1);
+      const float dx = r.ci[0] - r.cj[0], dy = r.ci[1] - r.cj[1], dz = r.ci[2] - r.cj[2];
+      const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      int bin = -1;
 #pragma unroll
-            for (int k = 0; k < 12; ++k) w[k] = (k == (bin >> 1)) ? one : 0u;
+      for (int k = 0; k < NBINS; ++k)
+        if (d > lower_s[k] && d < lower_s[k + 1]) bin = k;  // strict on both sides (data/utils.py:547-549)
+      return bin;
+    };
+    auto emit_a0 = [&](long long t, int code) {
+      uint8_t* dst = A0t + ((t - t_begin) & 1) * 16384;
+      uint4 ch[2];
+      ch[0] = ch[1] = make_uint4(0, 0, 0, 0);
+      if (code >= 0) {
+        if (wg < 2) {
+          const uint4* e = reinterpret_cast<const uint4*>(a.rel_tab + (long long)code * EMB) + 2 * wg;
+          ch[0] = __ldg(e);
+          ch[1] = __ldg(e + 1);
+        } else {
+          const int w0 = (wg - 2) * 8;  // first 32-bit word (= bin pair) of this group's two chunks
+          if ((code >> 1) >= w0 && (code >> 1) < w0 + 8) {
+            const uint32_t one = (code & 1) ? 0x3C000000u : 0x00003C00u;  // fp16 1.0 in the high / low half
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = (w0 + k == (code >> 1)) ? one : 0u;
             ch[0] = make_uint4(w[0], w[1], w[2], w[3]);
             ch[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            ch[2] = make_uint4(w[8], w[9], w[10], w[11]);
           }
         }
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + sw128_chunk_off(row, wg * 4 + c)) = ch[c];
+      for (int c = 0; c < 2; ++c) *reinterpret_cast<uint4*>(dst + sw128_chunk_off(row, wg * 2 + c)) = ch[c];
       fence_proxy_async();
       mbar_arrive(&a0_full[(t - t_begin) & 1]);
     };
 
-    // Two CTA-wide barriers per tile (none with a global-memory latency behind it): the per-tile vector PA_i is double buffered and
-    // fetched one tile ahead, the LayerNorm statistics need no exchange between the two groups (each thread re-reads the other half
-    // of its row from TMEM), and the wait for the asynchronous store of tile t sits in front of the first write into its staging
-    // buffer in tile t+1.
+    // CTA-wide (worker) barriers per tile, none with a global-memory latency behind it: the per-tile vector PA_i is double buffered
+    // and fetched one tile ahead, the pair mask is loaded at the top of the tile, the LayerNorm statistics of the four column groups
+    // are combined through shared memory, and the wait for the asynchronous store of tile t sits in front of the first write into its
+    // staging buffer in tile t+1.
     if (t_begin < t_end) {
-      build_a0(t_begin);
+      emit_a0(t_begin, code_a0(prep_a0(t_begin)));
       int jb0, b0;
       const long long m0 = tile_m(t_begin, jb0, b0);
       if (threadIdx.x < 128) PA_s[threadIdx.x] = a.PA[m0 * 128 + threadIdx.x];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EE_WORKERS) : "memory");
     }
     for (long long t = t_begin; t < t_end; ++t) {
       const uint32_t ph = (uint32_t)(t - t_begin) & 1;
@@ -270,105 +315,103 @@ __global__ void __launch_bounds__(EE_THREADS, 1) ee_fused_kernel(EeArgs a) {
         const long long mn = tile_m(t + 1, jbn, bn);
         pa_next = a.PA[mn * 128 + threadIdx.x];  // consumed at the end of this iteration
       }
-      float v[64];
+      float mk_i = 0.f, mk_j = 0.f;  // consumed in E2 (loaded here, multiplied there: no scoreboard wait at the top of the tile)
+      if (j < a.N) {
+        mk_i = a.mask[m];
+        mk_j = a.mask[(long long)b * a.N + j];
+      }
+      A0Raw raw_next;
+      raw_next.valid = 0;
+      if (t + 1 < t_end) raw_next = prep_a0(t + 1);
+      float v[EE_GC];
       EE_TS(0);
       // ---- E0
       mbar_wait(d0_full, ph);
       tc_fence_after();
       EE_TS(1);
-      load_half(D0, v);
+      load_part(D0, v);
       tc_fence_before();
 #pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + PA_t[cg + n], 0.f);
-      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tile t-1's store has left A1
+      for (int n = 0; n < EE_GC; ++n) v[n] = fmaxf(v[n] + PA_t[cg + n], 0.f);
       EE_TS(2);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (t != t_begin) mbar_wait(a1_free, (uint32_t)(t - t_begin - 1) & 1);  // tile t-1's store has left A1
       EE_TS(3);
-      store_half(A1, v);
+      store_part(A1, v);
       fence_proxy_async();
       mbar_arrive(a1_full);
       EE_TS(4);
       // the next tile's feature block is gathered here: its two dependent global loads (seq_idx -> rel_tab row) hide under GEMM 1 of
       // this tile, which the workers would otherwise just wait for; GEMM 0 of the next tile is issued after GEMM 1 anyway
-      if (t + 1 < t_end) build_a0(t + 1);
+      if (t + 1 < t_end) emit_a0(t + 1, code_a0(raw_next));
       EE_TS(5);
       // ---- E1
       mbar_wait(d1_full, ph);
       tc_fence_after();
       EE_TS(6);
-      load_half(D1, v);
+      load_part(D1, v);
       tc_fence_before();
 #pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = fmaxf(v[n] + b2_s[cg + n], 0.f);
-      store_half(A2, v);
+      for (int n = 0; n < EE_GC; ++n) v[n] = fmaxf(v[n] + b2_s[cg + n], 0.f);
+      store_part(A2, v);
       fence_proxy_async();
       mbar_arrive(a2_full);
       EE_TS(7);
       // ---- E2: LayerNorm + mask -> fp16 tile image (staged in A1, free since GEMM1 of this tile has completed) -> bulk store.
-      //      Statistics of the whole row per thread: own 64 columns + the other group's 64 re-read from TMEM, single pass with the
-      //      own-half mean as shift (as in et_fused.cuh)
+      //      Each thread reduces its 32 columns (two-pass); the groups exchange (mean, sum of squared deviations) through shared
+      //      memory and combine them with the pairwise update (as in et_fused.cuh)
       mbar_wait(d2_full, ph);
       tc_fence_after();
       EE_TS(8);
-      load_half(D2, v);
-      float s0 = 0.f;
-#pragma unroll
-      for (int n = 0; n < 64; ++n) {
-        v[n] += b4_s[cg + n];
-        s0 += v[n];
-      }
-      const float shift = s0 * (1.f / 64.f);
-      float sd = 0.f, sq = 0.f;
-#pragma unroll
-      for (int n = 0; n < 64; ++n) {
-        const float d = v[n] - shift;
-        sd += d;
-        sq += d * d;
-      }
-      const int og = 64 - cg;
-      {
-        float w[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          tmem_ld32(D2 + lane_base + og + 32 * h, w);
-          tmem_ld_wait();
-#pragma unroll
-          for (int n = 0; n < 32; ++n) {
-            const float d = w[n] + b4_s[og + 32 * h + n] - shift;
-            sd += d;
-            sq += d * d;
-          }
-        }
-      }
+      load_part(D2, v);
       tc_fence_before();
-      EE_TS(9);
-      const float dm = sd * (1.f / 128.f);
-      const float mean = shift + dm;
-      const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - dm * dm, 0.f) + 1e-5f);
-      float mk = 0.f;
-      if (j < a.N) mk = a.mask[m] * a.mask[(long long)b * a.N + j];
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int n = 0; n < 64; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
-      store_half(A1, v);
-      fence_proxy_async();
-      if (threadIdx.x < 128 && t + 1 < t_end) (ph ? PA_s : PA_s2)[threadIdx.x] = pa_next;
-      EE_TS(10);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      EE_TS(11);
-      if (threadIdx.x == 0) {
-        uint8_t* dst = reinterpret_cast<uint8_t*>(a.z_out) + ((m * a.JB + jb) * 32768LL);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(A1)), "r"(32768) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      for (int n = 0; n < EE_GC; n += 2) {
+        v[n] += b4_s[cg + n];
+        v[n + 1] += b4_s[cg + n + 1];
+        s0 += v[n];
+        s1 += v[n + 1];
       }
+      const float mh = (s0 + s1) * (1.f / EE_GC);
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int n = 0; n < EE_GC; n += 2) {
+        const float d0 = v[n] - mh, d1 = v[n + 1] - mh;
+        q0 += d0 * d0;
+        q1 += d1 * d1;
+      }
+      red_s[wg * 128 + row] = mh;
+      red_q[wg * 128 + row] = q0 + q1;
+      // the other PA buffer was last read in E0 of the previous tile; the barrier below orders this write before E0 of the next one
+      if (threadIdx.x < 128 && t + 1 < t_end) (ph ? PA_s : PA_s2)[threadIdx.x] = pa_next;
+      asm volatile("bar.sync 1, %0;" ::"n"(EE_WORKERS) : "memory");
+      float mean = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int g = 0; g < EE_GROUPS; ++g) mean += red_s[g * 128 + row];
+      mean *= (1.f / EE_GROUPS);
+#pragma unroll
+      for (int g = 0; g < EE_GROUPS; ++g) {
+        const float dg = red_s[g * 128 + row] - mean;
+        m2 += red_q[g * 128 + row] + (float)EE_GC * dg * dg;
+      }
+      EE_TS(9);
+      const float rstd = rsqrtf(m2 * (1.f / 128.f) + 1e-5f);
+      const float mk = mk_i * mk_j;
+#pragma unroll
+      for (int n = 0; n < EE_GC; ++n) v[n] = ((v[n] - mean) * rstd * g_s[cg + n] + be_s[cg + n]) * mk;
+      store_part(A1, v);
+      fence_proxy_async();
+      EE_TS(10);
+      mbar_arrive(stg_full);  // the loader warp issues the bulk store
+      EE_TS(11);
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == EE_WW) tmem_dealloc(tmem_base, 512);
 }
 
-inline size_t ee_smem_bytes() { return 1024 + 3 * (size_t)EE_W_BYTES + 3 * 16384 + 2 * 32768 + 10 * 8 + 16 + (5 * 128 + 24 + 512) * 4 + 64; }
+inline size_t ee_smem_bytes() { return 1024 + 3 * (size_t)EE_W_BYTES + 3 * 16384 + 2 * 32768 + 12 * 8 + 16 + (5 * 128 + 24 + 512 + 2 * EE_GROUPS * 128) * 4 + 64; }
 
 // per-residue features feat1d [B*N, F1] fp32 -> per-(b, j-block) fp16 k-block images [B][JB][128 rows][128 B] (columns >= F1 and rows >= N zero)
 __global__ void f_to_image_kernel(int B, int N, int JB, int F1, const float* __restrict__ feat1d, __half* __restrict__ img) {
