@@ -213,18 +213,23 @@ def eager_gpu_rate(wl, B: int, steps: int, warmup: int, dev):
     with torch.no_grad(), torch.device(dev):
         for s in range(warmup + steps):
             if s == warmup:
-                torch.cuda.synchronize(dev)
+                if torch.device(dev).type == "cuda":
+                    torch.cuda.synchronize(dev)
                 t_start = time.perf_counter()
             t = float(sched_t[s])
             feats["t"] = t * torch.ones(B)
             out = orc.score_network_forward(sd, feats, inpainting=not wl.de_novo, input_aatype=not wl.de_novo)
             rig = out["rigids"].float()
             feats["sc_ca_t"] = rig[..., 4:]
-            R1, T1 = orc.reverse_step(feats["rigids_t"].float().cpu().numpy(), out["rot_score"].cpu().numpy().astype(np.float64),
-                                      out["trans_score"].float().cpu().numpy(), dm, t, dt, noise[s, 0], noise[s, 1], noise_scale=wl.noise_scale)
-            q1 = orc.rot_to_quat_np(R1.astype(np.float64)).astype(np.float32)
-            feats["rigids_t"] = torch.tensor(np.concatenate([q1, T1], -1))
-        torch.cuda.synchronize(dev)
+            with torch.device("cpu"):  # the reverse step is host numpy in the reference (its torch helpers must not land on the GPU)
+                R1, T1 = orc.reverse_step(feats["rigids_t"].float().cpu().numpy(), out["rot_score"].cpu().numpy().astype(np.float64),
+                                          out["trans_score"].float().cpu().numpy(), dm, t, dt, noise[s, 0], noise[s, 1],
+                                          noise_scale=wl.noise_scale)
+                q1 = orc.rot_to_quat_np(R1.astype(np.float64)).astype(np.float32)
+                nxt = torch.tensor(np.concatenate([q1, T1], -1))
+            feats["rigids_t"] = nxt.to(dev)
+        if torch.device(dev).type == "cuda":
+            torch.cuda.synchronize(dev)
     el = time.perf_counter() - t_start
     return B * n * steps / el, el / steps
 
