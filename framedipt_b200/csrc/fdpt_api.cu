@@ -675,9 +675,12 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
     if (plan.rz < 1) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs more shared memory than available in ipa_core", N);
     IpaCoreArgs a;
     a.B = B; a.N = N; a.JB = w.JB; a.ldS = w.ldS; a.S = w.S; a.z = z; a.Wb_img = p.imgWb; a.bb = p.bb;
-    a.Wd = p.Wd; a.bd = p.bd; a.cat = w.cat; a.rz = plan.rz; a.tmem_cols = plan.tmem_cols; a.rows = (int)M; a.Pg = img ? w.pimg : nullptr; a.mn_swap = ctx->mn_swap; a.dbg = (ctx->dbg_flags & 4) ? ctx->et_dbg : nullptr;
+    a.Wd = p.Wd; a.single_pass = plan.single_pass; a.bd = p.bd; a.cat = w.cat; a.rz = plan.rz; a.tmem_cols = plan.tmem_cols; a.rows = (int)M; a.Pg = img ? w.pimg : nullptr; a.mn_swap = ctx->mn_swap; a.dbg = (ctx->dbg_flags & 4) ? ctx->et_dbg : nullptr;
     ProfScope pc(ctx, FDPT_PROF_IPA_CORE, st);
-    ipa_core_kernel<<<(unsigned)std::min<long long>((long long)ctx->num_sms * plan.ctas_per_sm, M), 192, plan.bytes, st>>>(a);
+    if (plan.single_pass)
+      ipa_core_kernel<true><<<(unsigned)std::min<long long>((long long)ctx->num_sms, M), IPA_THREADS, plan.bytes, st>>>(a);
+    else
+      ipa_core_kernel<false><<<(unsigned)std::min<long long>((long long)ctx->num_sms * plan.ctas_per_sm, M), IPA_THREADS, plan.bytes, st>>>(a);
     LAUNCH_CHECK();
   }
   if (img) {  // [o | o_pt (global frame)][b,:,h,:] = P_h V'_h  -> cat'[:, h*292 : (h+1)*292]   (V' rows = j: MN-major B)
@@ -1015,7 +1018,8 @@ int fdpt_create(const fdpt_config* cfg, int device, fdpt_ctx** out) {
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&ctx->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
-  cudaFuncSetAttribute(ipa_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(ipa_core_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
+  cudaFuncSetAttribute(ipa_core_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin);
   cudaFuncSetAttribute(tc::et_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::et_smem_bytes());
   cudaFuncSetAttribute(tc::ee_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::ee_smem_bytes());
   cudaFuncSetAttribute(tc::tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::tc_linear_smem_bytes(512));

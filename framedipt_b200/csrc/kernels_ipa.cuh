@@ -269,6 +269,8 @@ struct IpaCoreArgs {
   const float* bd;       // [32]
   float* cat;            // [B*N, CAT] (cat' order)
   int rz, tmem_cols;     // z ring slots; TMEM columns to allocate (two D1 buffers + D2)
+  int single_pass;       // 1: the ring holds two whole rows (rz = 2 JB): GEMM-o re-uses the tiles GEMM-b left in shared memory, every z
+                         //    tile is fetched once; 0: the tiles of a row are fetched a second time for GEMM-o (L2 hits)
   int rows;              // B*N
   uint8_t* Pg;           // optional: probabilities as fp16 hi | lo operand images [b, h][i-tile][2 JB k-blocks][32 KB] for the A.V GEMM
                          // (gemm_img.cuh); S then keeps the logits (the fp32 probabilities are not written)
@@ -285,25 +287,38 @@ constexpr int IPA_TILE_BYTES = 32768;
 constexpr int IPA_PIMG_TILE = 4096;   // [2 kb][16 rows][128 B]
 constexpr int IPA_OZ_LD = 132;
 constexpr int IPA_MAX_RZ = 6, IPA_MAX_JB = 8;
+constexpr int IPA_EPI = 256;                 // epilogue threads (logits / softmax / down_z): two groups of 128
+constexpr int IPA_THREADS = IPA_EPI + 64;    // + MMA issuer warp, loader warp
 
 struct IpaSmemPlan {
-  int rz, ctas_per_sm, tmem_cols;
+  int rz, ctas_per_sm, tmem_cols, single_pass;
   size_t bytes;
 };
 __host__ __device__ inline size_t ipa_pimg_bytes(int JB) {  // probability images; the region doubles as ozs [H][132] fp32 once GEMM-o has read it
   const size_t p = (size_t)JB * IPA_PIMG_TILE, o = (size_t)NH * IPA_OZ_LD * 4;
   return ((p > o ? p : o) + 1023) / 1024 * 1024;
 }
-// Shared-memory / TMEM plan.  The kernel is latency-bound per row (load -> GEMM-b -> logits -> softmax -> GEMM-o -> down_z), so two
-// CTAs per SM are preferred whenever they fit (2-slot z ring, <= 256 TMEM columns each); otherwise one CTA with the deepest ring.
+// Shared-memory / TMEM plan.  N <= 384: the ring holds two whole rows, so the tiles GEMM-b consumed are still there when the softmax of
+// the row has produced P and GEMM-o runs without a second fetch (single pass over z, one CTA per SM).  Larger N: the tiles of a row
+// are fetched twice (the second time from L2); the kernel is then latency-bound per row, so two CTAs per SM are preferred whenever
+// they fit (2-slot z ring, <= 256 TMEM columns each), otherwise one CTA with the deepest ring.
 inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
   const int JB = (N + 127) / 128;
-  const size_t other = ipa_pimg_bytes(JB) + 4096 + (size_t)NH * JB * 128 * 4 + C_Z * (C_Z / 4) * 4 + 512 + 1024;
+  const size_t other_sp = ipa_pimg_bytes(JB) + 4096 + (size_t)NH * JB * 128 * 4 + 512 + 1024;  // single pass: down_z.weight in registers
+  const size_t other = other_sp + C_Z * (C_Z / 4) * 4;                                          // else: staged in shared memory
   const int need_cols = 2 * JB * 16 + 16;  // two D1 buffers + D2
   IpaSmemPlan p;
   p.tmem_cols = need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512);
+  p.single_pass = 0;
   const size_t two = other + 2 * (size_t)IPA_TILE_BYTES;
-  if (2 * (two + 1024) <= (size_t)max_smem_per_sm && p.tmem_cols <= 256) {
+  if (2 * JB <= IPA_MAX_RZ && other_sp + 2 * (size_t)JB * IPA_TILE_BYTES <= (size_t)max_smem) {
+    // two whole rows resident (N <= 384): one CTA per SM, every z tile crosses HBM / L2 once
+    p.rz = 2 * JB;
+    p.ctas_per_sm = 1;
+    p.single_pass = 1;
+    p.bytes = other_sp + (size_t)p.rz * IPA_TILE_BYTES;
+    return p;
+  } else if (2 * (two + 1024) <= (size_t)max_smem_per_sm && p.tmem_cols <= 256) {
     p.rz = 2;
     p.ctas_per_sm = 2;
   } else {
@@ -321,7 +336,9 @@ inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
 //   epilogue order:           logits(0), { softmax(it), logits(it+1), down_z(it) }
 // so the HBM loads and GEMM-b of the next rows run under the softmax of the current one, and the logits of the next row are computed
 // while the tensor core does GEMM-o.
-__global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
+// SP (single pass): one CTA per SM, so a thread may keep its whole row of down_z.weight (128 floats) in registers
+template <bool SP>
+__global__ void __launch_bounds__(IPA_THREADS, SP ? 1 : 2) ipa_core_kernel(IpaCoreArgs a) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
@@ -331,8 +348,8 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
   float* ozs = reinterpret_cast<float*>(Pimg);               // [H][132], aliases Pimg (dead once GEMM-o has completed)
   uint8_t* Wbs = Pimg + ipa_pimg_bytes(JB);                  // 4 KB
   float* L = reinterpret_cast<float*>(Wbs + 4096);           // [H][ldL] logits / exp
-  float* Wd4 = L + NH * ldL;                                 // [32 channel groups][32 d][4] down_z.weight
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Wd4 + C_Z * (C_Z / 4));
+  float* Wd4 = L + NH * ldL;                                 // !SP: [32 channel groups][32 d][4] down_z.weight
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Wd4 + (SP ? 0 : C_Z * (C_Z / 4)));
   uint64_t* zfull = bars;                        // [IPA_MAX_RZ]
   uint64_t* zfree = zfull + IPA_MAX_RZ;          // [IPA_MAX_RZ]
   uint64_t* d1_full = zfree + IPA_MAX_RZ;        // [2][IPA_MAX_JB]
@@ -351,25 +368,27 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
       mbar_init(&zfree[s], 1);
     }
     for (int t = 0; t < 2 * IPA_MAX_JB; ++t) mbar_init(&d1_full[t], 1);
-    mbar_init(&d1_free[0], 128);
-    mbar_init(&d1_free[1], 128);
-    mbar_init(p_full, 128);
+    mbar_init(&d1_free[0], IPA_EPI);
+    mbar_init(&d1_free[1], IPA_EPI);
+    mbar_init(p_full, IPA_EPI);
     mbar_init(d2_full, 1);
     mbar_init(wb_full, 1);
     fence_barrier_init();
   }
-  for (int k = tid; k < C_Z * (C_Z / 4); k += blockDim.x) {
-    const int d = k / C_Z, c = k % C_Z;
-    Wd4[((c >> 2) * (C_Z / 4) + d) * 4 + (c & 3)] = a.Wd[k];
+  if constexpr (!SP) {
+    for (int k = tid; k < C_Z * (C_Z / 4); k += blockDim.x) {
+      const int d = k / C_Z, c = k % C_Z;
+      Wd4[((c >> 2) * (C_Z / 4) + d) * 4 + (c & 3)] = a.Wd[k];
+    }
   }
-  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  if (warp == IPA_EPI / 32) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t D1 = tmem_base, D2 = tmem_base + 2 * JB * 16;  // D1 buffer b at D1 + b*JB*16
 
-  if (warp == 5) {
+  if (warp == IPA_EPI / 32 + 1) {
     // ============================ loader ============================
     if (elect_one() && nrows > 0) {
       mbar_arrive_expect_tx(wb_full, 4096);
@@ -386,14 +405,18 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
           ++cnt;
         }
       };
-      load_row(0);
-      if (nrows > 1) load_row(1);
-      for (int it = 0; it < nrows; ++it) {
-        load_row(it);                        // second pass of row it (GEMM-o): L2 hits
-        if (it + 2 < nrows) load_row(it + 2);
+      if (a.single_pass) {
+        for (int it = 0; it < nrows; ++it) load_row(it);  // a slot is released by GEMM-o of its tile
+      } else {
+        load_row(0);
+        if (nrows > 1) load_row(1);
+        for (int it = 0; it < nrows; ++it) {
+          load_row(it);                        // second pass of row it (GEMM-o): L2 hits
+          if (it + 2 < nrows) load_row(it + 2);
+        }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == IPA_EPI / 32) {
     // ============================ MMA issuer ============================
     if (elect_one() && nrows > 0) {
       mbar_wait(wb_full, 0);
@@ -403,6 +426,16 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
       const uint32_t wb = smem_u32(Wbs), pimg = smem_u32(Pimg), ring_u = smem_u32(ring);
       const uint32_t lbo = a.mn_swap ? 1024u : 16384u, sbo = a.mn_swap ? 16384u : 1024u;
       uint32_t cnt = 0;
+      auto gemm_b_tile = [&](int it, int t, uint32_t s) {  // tile t of row iteration it (landed in ring slot s): D1[it & 1][t] = z_tile . Wb^T
+        const uint32_t zt = ring_u + s * IPA_TILE_BYTES;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(D1 + ((it & 1) * JB + t) * 16, make_sw128_desc(zt + kb * 16384 + k * 32), make_sw128_desc(wb + kb * 2048 + k * 32), idesc_b,
+                     (kb | k) ? 1u : 0u);
+        umma_commit(&d1_full[(it & 1) * IPA_MAX_JB + t]);
+      };
       // GEMM-b of row iteration `it`: D1[it & 1][t] = z_tile . Wb^T
       auto issue_b = [&](int it) {
         const int buf = it & 1;
@@ -411,59 +444,100 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
           tc_fence_after();
         }
         for (int t = 0; t < JB; ++t) {
-          const uint32_t s = cnt % a.rz;
-          mbar_wait(&zfull[s], (cnt / a.rz) & 1);
+          const uint32_t c_use = a.single_pass ? (uint32_t)(it * JB + t) : cnt;  // single pass: tile (it, t) lives in slot (it JB + t) % rz
+          const uint32_t s = c_use % a.rz;
+          mbar_wait(&zfull[s], (c_use / a.rz) & 1);
           tc_fence_after();
-          const uint32_t zt = ring_u + s * IPA_TILE_BYTES;
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(D1 + (buf * JB + t) * 16, make_sw128_desc(zt + kb * 16384 + k * 32), make_sw128_desc(wb + kb * 2048 + k * 32), idesc_b,
-                       (kb | k) ? 1u : 0u);
-          umma_commit(&d1_full[buf * IPA_MAX_JB + t]);
-          umma_commit(&zfree[s]);
+          gemm_b_tile(it, t, s);
+          if (!a.single_pass) umma_commit(&zfree[s]);  // single pass: the tile stays for GEMM-o
           ++cnt;
           if (t == 0) IPA_TS(1);
         }
       };
       // GEMM-o of row iteration `it`: D2 += z_tile^T . P^T  (after the softmax of this row has written the probability images)
       auto issue_o = [&](int it) {
-        mbar_wait(p_full, it & 1);
+        if (!SP) mbar_wait(p_full, it & 1);  // SP: the caller has polled it
         tc_fence_after();
         IPA_TS(9);
         for (int t = 0; t < JB; ++t) {
-          const uint32_t s = cnt % a.rz;
-          mbar_wait(&zfull[s], (cnt / a.rz) & 1);
-          tc_fence_after();
+          const uint32_t c_use = a.single_pass ? (uint32_t)(it * JB + t) : cnt;
+          const uint32_t s = c_use % a.rz;
+          if (!a.single_pass) {  // (single pass: GEMM-b of this tile has already waited for it)
+            mbar_wait(&zfull[s], (c_use / a.rz) & 1);
+            tc_fence_after();
+          }
           const uint32_t zt = ring_u + s * IPA_TILE_BYTES;
+          // one descriptor pair per tile; the 8 steps advance the start-address fields by compile-time constants (the 14-bit field
+          // holds address >> 4 and shared-memory addresses stay below 256 KB, so the additions never carry out of it)
+          const uint64_t dz0 = make_sw128_desc_ls(zt, lbo, sbo), dp0 = make_sw128_desc(pimg + t * IPA_PIMG_TILE);
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // 16 j-rows per step
-            umma_f16(D2, make_sw128_desc_ls(zt + k * 2048, lbo, sbo),
-                     make_sw128_desc(pimg + t * IPA_PIMG_TILE + (k >> 2) * 2048 + (k & 3) * 32), idesc_o, (t | k) ? 1u : 0u);
+            umma_f16(D2, dz0 + (uint64_t)((k * 2048) >> 4), dp0 + (uint64_t)(((k >> 2) * 2048 + (k & 3) * 32) >> 4), idesc_o, (t | k) ? 1u : 0u);
           umma_commit(&zfree[s]);
           ++cnt;
         }
         umma_commit(d2_full);
         IPA_TS(10);
       };
-      issue_b(0);
-      if (nrows > 1) issue_b(1);
-      for (int it = 0; it < nrows; ++it) {
-        issue_o(it);
-        if (it + 2 < nrows) issue_b(it + 2);
+      if constexpr (SP) {
+        // event loop: GEMM-o of the oldest row as soon as its probabilities are there (the epilogue's critical path), otherwise the next
+        // GEMM-b tile that has landed -- a blocking wait for an HBM tile would delay GEMM-o by a whole memory latency
+        int io = 0, bt = 0;
+        const int total_b = nrows * JB;
+        while (io < nrows) {
+          if (mbar_try_wait(p_full, io & 1)) {
+            issue_o(io);
+            ++io;
+            continue;
+          }
+          if (bt < total_b) {
+            const int it_b = bt / JB, t = bt - it_b * JB;
+            if (t == 0 && it_b >= 2 && !mbar_try_wait(&d1_free[it_b & 1], ((it_b - 2) >> 1) & 1)) continue;  // logits of row it_b - 2 not read yet
+            const uint32_t s = (uint32_t)bt % a.rz;
+            if (mbar_try_wait(&zfull[s], ((uint32_t)bt / a.rz) & 1)) {
+              tc_fence_after();
+              gemm_b_tile(it_b, t, s);
+              if (t == 0) {
+                const int it = it_b;
+                IPA_TS(1);
+              }
+              ++bt;
+            }
+          }
+        }
+      } else {
+        issue_b(0);
+        if (nrows > 1) issue_b(1);
+        for (int it = 0; it < nrows; ++it) {
+          issue_o(it);
+          if (it + 2 < nrows) issue_b(it + 2);
+        }
       }
     }
   } else {
-    // ============================ logits / softmax / down_z (128 threads) ============================
-    const int r = tid;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ============================ logits / softmax / down_z (256 threads) ============================
+    // two groups of 128 threads: thread r of either group <-> TMEM lane r (key j of a tile in D1, channel c in D2); group eg owns heads
+    // 4 eg .. 4 eg + 3 wherever the work splits by head (logits, o_pair read-out), warp w owns head w in the softmax, and down_z has
+    // one output per thread
+    const int r = tid & 127, eg = tid >> 7;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float s_b = sqrtf(1.0f / 3.f);
-    float bbv[NH];
+    float bbv[4];
 #pragma unroll
-    for (int h = 0; h < NH; ++h) bbv[h] = a.bb[h];
-    const int hh_out = r >> 4, dq = r & 15;
-    const float bd0 = a.bd[dq], bd1 = a.bd[dq + 16];
+    for (int h = 0; h < 4; ++h) bbv[h] = a.bb[4 * eg + h];
+    const int hh_out = tid >> 5, dq = tid & 31;
+    const float bd0 = a.bd[dq];
+    // SP: down_z from registers.  Warp w: outputs d in [16 (w & 1), +16) of heads 2 (w >> 1), 2 (w >> 1) + 1; lane: d = that range +
+    // (lane & 15), channel half lane >> 4 (64 weights in registers), the two halves are added with one shuffle
+    const int sp_d = 16 * (warp & 1) + (lane & 15), sp_half = lane >> 4, sp_h0 = 2 * (warp >> 1);
+    float wdr[SP ? C_Z / 2 : 1];
+    if constexpr (SP) {
+#pragma unroll
+      for (int c = 0; c < C_Z / 2; c += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(a.Wd + sp_d * C_Z + sp_half * (C_Z / 2) + c);
+        wdr[c] = w.x; wdr[c + 1] = w.y; wdr[c + 2] = w.z; wdr[c + 3] = w.w;
+      }
+    }
     const long long hs = (long long)N * a.ldS;
     // S row of iteration `it` (8 heads x ldS floats) -> L, asynchronously (cp.async, 16 bytes per request)
     auto prefetch_S = [&](int it) {
@@ -471,17 +545,51 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
       const int b = row / N, i = row - b * N;
       const float* Srow0 = a.S + (((long long)b * NH) * N + i) * a.ldS;
       const int cpr = a.ldS >> 2;  // 16-byte chunks per head
-      for (int k = tid; k < NH * cpr; k += 128) {
+      for (int k = tid; k < NH * cpr; k += IPA_EPI) {
         const int h = k / cpr, c = k - h * cpr;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(L + h * ldL + 4 * c)), "l"(Srow0 + h * hs + 4 * c) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // SP: the S values a thread adds its bias to (4 heads x JB keys) are loaded into registers one row ahead (issued before the softmax
+    // of the previous row, consumed after it): no cp.async into L, whose single buffer is busy until that softmax has finished
+    float sreg[SP ? 3 : 1][4];
+    auto prefetch_S_regs = [&](int it) {
+      if constexpr (SP) {
+        const int row = (int)blockIdx.x + it * (int)gridDim.x;
+        const int b = row / N, i = row - b * N;
+        const float* Srow0 = a.S + (((long long)b * NH + 4 * eg) * N + i) * a.ldS;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int j = t * 128 + r;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) sreg[t][h] = (t < JB && j < N) ? Srow0[h * hs + j] : 0.f;
+        }
+      }
+    };
     // logits of row iteration `it`: L[h][j] = S'[h][j] + sqrt(1/3) (b_ij,h + b_b,h), -inf beyond N
     auto logits = [&](int it) {
       const int buf = it & 1;
+      if constexpr (SP) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          if (t >= JB) break;
+          const int j = t * 128 + r;
+          mbar_wait(&d1_full[buf * IPA_MAX_JB + t], (it >> 1) & 1);
+          tc_fence_after();
+          float bv[16];
+          tmem_ld16(D1 + lane_base + (buf * JB + t) * 16, bv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            L[(4 * eg + h) * ldL + j] = j < N ? sreg[t][h] + s_b * ((eg ? bv[4 + h] + bv[12 + h] : bv[h] + bv[8 + h]) + bbv[h]) : -INFINITY;
+        }
+        tc_fence_before();
+        mbar_arrive(&d1_free[buf]);
+        return;
+      }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // every thread's part of the S row has landed
+      asm volatile("bar.sync 1, %0;" ::"n"(IPA_EPI) : "memory");  // every thread's part of the S row has landed
       for (int t = 0; t < JB; ++t) {
         const int j = t * 128 + r;
         mbar_wait(&d1_full[buf * IPA_MAX_JB + t], (it >> 1) & 1);
@@ -491,27 +599,31 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
         tmem_ld_wait();
         if (j < N) {
 #pragma unroll
-          for (int h = 0; h < NH; ++h) L[h * ldL + j] += s_b * (bv[h] + bv[h + 8] + bbv[h]);
+          for (int h = 0; h < 4; ++h)  // constant register indices (a runtime index would put bv on the stack)
+            L[(4 * eg + h) * ldL + j] += s_b * ((eg ? bv[4 + h] + bv[12 + h] : bv[h] + bv[8 + h]) + bbv[h]);
         } else {
 #pragma unroll
-          for (int h = 0; h < NH; ++h) L[h * ldL + j] = -INFINITY;
+          for (int h = 0; h < 4; ++h) L[(4 * eg + h) * ldL + j] = -INFINITY;
         }
       }
       tc_fence_before();
       mbar_arrive(&d1_free[buf]);
     };
-    if (nrows > 0) prefetch_S(0);
-    if (nrows > 0) logits(0);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (nrows > 0) {
+      if constexpr (SP) prefetch_S_regs(0);
+      else prefetch_S(0);
+      logits(0);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(IPA_EPI) : "memory");
     for (int it = 0; it < nrows; ++it) {
       const int row = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = row / N, i = row - b * N;
       float* Srow0 = a.S + (((long long)b * NH) * N + i) * a.ldS;
       if (tid == 0) IPA_TS(20);
-      // ---- softmax over j: warp w owns heads 2w, 2w+1; a lane owns 4 consecutive j per 128-column tile
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int h = 2 * warp + hh;
+      if (SP && it + 1 < nrows) prefetch_S_regs(it + 1);  // loads in flight under the softmax
+      // ---- softmax over j: warp w owns head w; a lane owns 4 consecutive j per 128-column tile
+      {
+        const int h = warp;
         const float4* L4 = reinterpret_cast<const float4*>(L + h * ldL);
         float4 v[IPA_MAX_JB];
         float mx = -INFINITY;
@@ -564,9 +676,9 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
       fence_proxy_async();
       mbar_arrive(p_full);
       if (tid == 0) IPA_TS(31);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // every warp is done with L
+      asm volatile("bar.sync 1, %0;" ::"n"(IPA_EPI) : "memory");  // every warp is done with L
       if (it + 1 < nrows) {                            // overlaps GEMM-o of this row
-        prefetch_S(it + 1);
+        if constexpr (!SP) prefetch_S(it + 1);
         logits(it + 1);
       }
       if (tid == 0) IPA_TS(30);
@@ -579,36 +691,48 @@ __global__ void __launch_bounds__(192, 2) ipa_core_kernel(IpaCoreArgs a) {
         tmem_ld16(D2 + lane_base, ov);
         tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < NH; ++h) ozs[h * IPA_OZ_LD + r] = ov[h] + ov[h + 8];
+        for (int h = 0; h < 4; ++h) ozs[(4 * eg + h) * IPA_OZ_LD + r] = eg ? ov[4 + h] + ov[12 + h] : ov[h] + ov[8 + h];
       }
       tc_fence_before();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      {
-        float acc0 = bd0, acc1 = bd1, acc2 = 0.f, acc3 = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(IPA_EPI) : "memory");
+      if constexpr (SP) {
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const float4* o4 = reinterpret_cast<const float4*>(ozs + (sp_h0 + hh) * IPA_OZ_LD + sp_half * (C_Z / 2));
+#pragma unroll
+          for (int cgp = 0; cgp < C_Z / 8; ++cgp) {
+            const float4 x = o4[cgp];  // two distinct addresses per warp (one per channel half): broadcasts
+            acc[hh][0] = fmaf(wdr[4 * cgp], x.x, fmaf(wdr[4 * cgp + 1], x.y, acc[hh][0]));
+            acc[hh][1] = fmaf(wdr[4 * cgp + 2], x.z, fmaf(wdr[4 * cgp + 3], x.w, acc[hh][1]));
+          }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float v = acc[hh][0] + acc[hh][1];
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (sp_half == hh) a.cat[(long long)row * CAT + CATP_PAIR + (sp_h0 + hh) * (C_Z / 4) + sp_d] = v + a.bd[sp_d];
+        }
+      } else {
+        float acc0 = bd0, acc2 = 0.f;
         const float4* o4 = reinterpret_cast<const float4*>(ozs + hh_out * IPA_OZ_LD);
         const float4* w4 = reinterpret_cast<const float4*>(Wd4);
 #pragma unroll 8
         for (int cgp = 0; cgp < C_Z / 4; ++cgp) {
           const float4 x = o4[cgp];
-          const float4 w0 = w4[cgp * (C_Z / 4) + dq], w1 = w4[cgp * (C_Z / 4) + dq + 16];
+          const float4 w0 = w4[cgp * (C_Z / 4) + dq];
           acc0 = fmaf(w0.x, x.x, fmaf(w0.y, x.y, acc0));
           acc2 = fmaf(w0.z, x.z, fmaf(w0.w, x.w, acc2));
-          acc1 = fmaf(w1.x, x.x, fmaf(w1.y, x.y, acc1));
-          acc3 = fmaf(w1.z, x.z, fmaf(w1.w, x.w, acc3));
         }
-        acc0 += acc2;
-        acc1 += acc3;
-        float* dst = a.cat + (long long)row * CAT + CATP_PAIR + hh_out * (C_Z / 4);
-        dst[dq] = acc0;
-        dst[dq + 16] = acc1;
+        a.cat[(long long)row * CAT + CATP_PAIR + hh_out * (C_Z / 4) + dq] = acc0 + acc2;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // ozs aliases the probability images: the next softmax may not start earlier
+      asm volatile("bar.sync 1, %0;" ::"n"(IPA_EPI) : "memory");  // ozs aliases the probability images: the next softmax may not start earlier
       if (tid == 0) IPA_TS(33);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  if (warp == IPA_EPI / 32) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 }  // namespace fdpt

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python tools/ee_timeline.py 2>&1 | tail -16
+python tools/ipa_timeline.py 2>&1 | tail -12
 tools/gpu_r2_quick.sh
