@@ -336,6 +336,9 @@ inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
 //   epilogue order:           logits(0), { softmax(it), logits(it+1), down_z(it) }
 // so the HBM loads and GEMM-b of the next rows run under the softmax of the current one, and the logits of the next row are computed
 // while the tensor core does GEMM-o.
+// SP = true (N <= 384, ring = 2 JB tiles, one CTA per SM): tile (it, t) stays in slot (it JB + t) % rz from its load until GEMM-o of
+// row it has read it, so there is no second pass; the MMA warp runs an event loop (GEMM-o of the oldest row whenever its
+// probabilities are there, else the next landed GEMM-b tile) and the epilogue keeps the down_z weights and the next S row in registers.
 // SP (single pass): one CTA per SM, so a thread may keep its whole row of down_z.weight (128 floats) in registers
 template <bool SP>
 __global__ void __launch_bounds__(IPA_THREADS, SP ? 1 : 2) ipa_core_kernel(IpaCoreArgs a) {
