@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(GI_THREADS, 1) gemm_img_kernel(const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + smem_align_pad(smem_raw);  // offset arithmetic on the __shared__ symbol: accesses stay LDS / STS
   uint8_t* ring = smem;                                                     // GI_STAGES x 64 KB
-  float* Stg = reinterpret_cast<float*>(ring + (size_t)GI_STAGES * GI_STAGE_BYTES);  // 8 warps x 32 rows x 17 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Stg + 8 * 32 * 17);
+  float* Stg = reinterpret_cast<float*>(ring + (size_t)GI_STAGES * GI_STAGE_BYTES);  // 8 warps x 32 rows x 20 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Stg + 8 * 32 * 20);
   uint64_t* s_full = bars;                     // [GI_STAGES]
   uint64_t* s_empty = s_full + GI_STAGES;      // [GI_STAGES]
   uint64_t* acc_full = s_empty + GI_STAGES;    // [2]
@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(GI_THREADS, 1) gemm_img_kernel(const __grid_co
     // ============================ epilogue workers ============================
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int c_half = (warp >> 2) * 64;
-    float* stg = Stg + warp * 32 * 17;
+    float* stg = Stg + warp * 32 * 20;
+    const bool c_vec = ((reinterpret_cast<uintptr_t>(a.C) | (uintptr_t)(a.ldc * 4) | (uintptr_t)(a.sC1 * 4) | (uintptr_t)(a.sC2 * 4)) & 15) == 0;  // (N need not be a multiple of 4: the straddling float4 is stored by element; gemm_img has no residual / accumulate)
     uint32_t tl = 0;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
       int mt, nt, z;
@@ -181,7 +182,12 @@ __global__ void __launch_bounds__(GI_THREADS, 1) gemm_img_kernel(const __grid_co
         if (n0 + cb >= a.N) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(x2[j], 1.0f / GT_LO_SCALE, v[j]);
-        store_transposed<16>(ep, v, stg, lane, mw, n0 + cb);
+        if (c_vec) {  // 16-byte accesses through a [32][20] patch, two 16-column passes
+          store_transposed_v4<16>(ep, v, stg, lane, mw, n0 + cb);
+          store_transposed_v4<16>(ep, v + 16, stg, lane, mw, n0 + cb + 16);
+        } else {
+          store_transposed<16>(ep, v, stg, lane, mw, n0 + cb);
+        }
       }
     }
   }
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) gemm_img_kernel(const __grid_co
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-inline size_t gemm_img_smem_bytes() { return 1024 + (size_t)GI_STAGES * GI_STAGE_BYTES + (size_t)8 * 32 * 17 * 4 + (2 * GI_STAGES + 4) * 8 + 64; }
+inline size_t gemm_img_smem_bytes() { return 1024 + (size_t)GI_STAGES * GI_STAGE_BYTES + (size_t)8 * 32 * 20 * 4 + (2 * GI_STAGES + 4) * 8 + 64; }
 
 }  // namespace tc
 }  // namespace fdpt

@@ -79,58 +79,76 @@ struct EpiArgs {
 // 8 LDS.128 + 8 STG.128 per thread instead of 32 + 32 + 32 scalar ones.  Needs 16-byte aligned rows of Y / residual (ldy, ldr, c0
 // multiples of 4) and N a multiple of 4; stg must be 16-byte aligned.
 constexpr int ST4_PATCH_FLOATS = 32 * 36;
-FDPT_DEVINL void store_transposed_v4(const EpiArgs& a, const float (&v)[32], float* stg, int lane, int mw, int c0) {
-  constexpr int SLD = 36;
+// COLS = 32: patch [32][36]; COLS = 16: patch [32][20] (both row strides keep the 16-byte accesses of a quarter warp on distinct banks),
+// v holds the COLS columns starting at v[0]
+template <int COLS = 32>
+FDPT_DEVINL void store_transposed_v4(const EpiArgs& a, const float* v, float* stg, int lane, int mw, int c0) {
+  constexpr int SLD = COLS + 4, LPR = COLS / 4, RPI = 32 / LPR, NIT = 32 / RPI;  // lanes per row, rows per instruction, instructions
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stg + lane * SLD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  for (int j = 0; j < COLS / 4; ++j) *reinterpret_cast<float4*>(stg + lane * SLD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
-  const int lrow = lane >> 3, lc = (lane & 7) * 4;
+  const int lrow = lane / LPR, lc = (lane % LPR) * 4;
   const int col = c0 + lc;
   const bool cok = col < a.N;
   float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (a.bias && cok) bs = make_float4(__ldg(a.bias + col), __ldg(a.bias + col + 1), __ldg(a.bias + col + 2), __ldg(a.bias + col + 3));
-  float4 x[8];
+  if (a.bias && cok)
+    bs = make_float4(__ldg(a.bias + col), col + 1 < a.N ? __ldg(a.bias + col + 1) : 0.f, col + 2 < a.N ? __ldg(a.bias + col + 2) : 0.f,
+                     col + 3 < a.N ? __ldg(a.bias + col + 3) : 0.f);
+  float4 x[NIT];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const float4 t = *reinterpret_cast<const float4*>(stg + (it * 4 + lrow) * SLD + lc);
+  for (int it = 0; it < NIT; ++it) {
+    const float4 t = *reinterpret_cast<const float4*>(stg + (it * RPI + lrow) * SLD + lc);
     x[it] = make_float4(fmaf(a.alpha, t.x, bs.x), fmaf(a.alpha, t.y, bs.y), fmaf(a.alpha, t.z, bs.z), fmaf(a.alpha, t.w, bs.w));
   }
   if (a.relu) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) x[it] = make_float4(fmaxf(x[it].x, 0.f), fmaxf(x[it].y, 0.f), fmaxf(x[it].z, 0.f), fmaxf(x[it].w, 0.f));
+    for (int it = 0; it < NIT; ++it) x[it] = make_float4(fmaxf(x[it].x, 0.f), fmaxf(x[it].y, 0.f), fmaxf(x[it].z, 0.f), fmaxf(x[it].w, 0.f));
   }
   if (a.rowmask) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int m = mw + it * 4 + lrow;
+    for (int it = 0; it < NIT; ++it) {
+      const int m = mw + it * RPI + lrow;
       const float rm = (m < a.M) ? __ldg(a.rowmask + m) : 0.f;
       x[it] = make_float4(x[it].x * rm, x[it].y * rm, x[it].z * rm, x[it].w * rm);
     }
   }
   if (a.residual) {
-    float4 rr[8];
+    float4 rr[NIT];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int m = mw + it * 4 + lrow;
+    for (int it = 0; it < NIT; ++it) {
+      const int m = mw + it * RPI + lrow;
       rr[it] = (cok && m < a.M) ? *reinterpret_cast<const float4*>(a.residual + (long long)m * a.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int it = 0; it < 8; ++it) x[it] = make_float4(x[it].x + rr[it].x, x[it].y + rr[it].y, x[it].z + rr[it].z, x[it].w + rr[it].w);
+    for (int it = 0; it < NIT; ++it) x[it] = make_float4(x[it].x + rr[it].x, x[it].y + rr[it].y, x[it].z + rr[it].z, x[it].w + rr[it].w);
   }
   if (a.accumulate) {
-    float4 rr[8];
+    float4 rr[NIT];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int m = mw + it * 4 + lrow;
+    for (int it = 0; it < NIT; ++it) {
+      const int m = mw + it * RPI + lrow;
       rr[it] = (cok && m < a.M) ? *reinterpret_cast<const float4*>(a.Y + (long long)m * a.ldy + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int it = 0; it < 8; ++it) x[it] = make_float4(x[it].x + rr[it].x, x[it].y + rr[it].y, x[it].z + rr[it].z, x[it].w + rr[it].w);
+    for (int it = 0; it < NIT; ++it) x[it] = make_float4(x[it].x + rr[it].x, x[it].y + rr[it].y, x[it].z + rr[it].z, x[it].w + rr[it].w);
+  }
+  if (cok && col + 3 >= a.N) {  // the float4 straddles N (N not a multiple of 4): element stores, columns >= N stay untouched
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int m = mw + it * RPI + lrow;
+      if (m >= a.M) continue;
+      float* yp = a.Y + (long long)m * a.ldy + col;
+      const float e[4] = {x[it].x, x[it].y, x[it].z, x[it].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (col + q < a.N) yp[q] = e[q];
+    }
+    return;
   }
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int m = mw + it * 4 + lrow;
+  for (int it = 0; it < NIT; ++it) {
+    const int m = mw + it * RPI + lrow;
     if (cok && m < a.M) *reinterpret_cast<float4*>(a.Y + (long long)m * a.ldy + col) = x[it];
   }
 }

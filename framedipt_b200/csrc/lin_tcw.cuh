@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lin_tcw_kernel(LinTcArgs a) {
         }
         if (!a.Y) continue;
       }
-      if (a.y_vec) store_transposed_v4(ep, v, stg, lane, mw, n0 + cb);
+      if (a.y_vec) store_transposed_v4<32>(ep, v, stg, lane, mw, n0 + cb);
       else store_transposed<16>(ep, v, stg, lane, mw, n0 + cb);
     }
     if (tid == 0) LT_TS(11);
