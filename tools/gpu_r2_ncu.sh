@@ -13,8 +13,6 @@ cap ipa_core_kernel ipa_core_kernel 6 ""
 cap ee_fused_kernel ee_fused_kernel 2 ""
 cap gemm_img_kernel gemm_img_kernel 6 ""
 cap gemm_tc_kernel gemm_tc_kernel 6 ""
-cap lin_tc_ipa_projection "lin_tc_kernel<.*, .*, 1>" 4 ""
-cap lin_tc_plain "lin_tc_kernel<.*, .*, 0>" 40 ""
 cap softmax_rows_kernel softmax_rows_kernel 6 ""
 cap rot_score_kernel rot_score_kernel 2 ""
 cap reverse_kernel reverse_kernel 2 ""
