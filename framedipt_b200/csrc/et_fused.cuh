@@ -16,13 +16,19 @@
 //                                                     W3cat = [Wf | Wf[:, 0:128] | Wf[:, 256:384]]
 //   E3     z' = LN(D3 + Pf_i) * mask                -> fp16 tile image, bulk store
 //
-// TMEM: columns [0,384) = D2 (then r2, packed fp16, in place), [384,512) = D1 chunk stage / D3.   Shared memory (216 KB): A0z (32 KB,
-// bulk-copied; the next tile's z is fetched while G3's partial products and E3 run), A0n (32 KB), two 32 KB chunk buffers (h1 / output
-// staging), 5-stage weight ring (80 KB: the ring depth, not the tensor pipe, paced this kernel with 3 stages).
+// TMEM: columns [0,384) = D2 (then r2, packed fp16, in place), [384,512) = DS: staging of GEMM 1's chunks 0 and 2, then D3; D2's columns
+// [256,384) double as the staging buffer of chunk 1 (they are idle between the previous tile's last partial product and the tile's own
+// G2(0), and the tensor pipe executes in order), so chunks 0 and 1 of the next tile are issued while the workers are still in E3.
+// Issue order per tile: G1(0) G1(1) G1(2) G2(0) G3[z] G2(1) G2(2) G3[n_j] G3[r2 chunks]; GEMM 2's output chunks are handed to E2 one by one.
+// Shared memory (216 KB): A0z (32 KB, bulk-copied; the next tile's z is fetched as soon as G3[z] has read this one), A0n (32 KB), two
+// 32 KB chunk buffers (h1 / output staging), 5-stage weight ring (80 KB: the ring depth, not the tensor pipe, paced this kernel with 3
+// stages).  The 40 weight k-blocks of a tile are 8 full turns of the ring, so the issue sequence is fully unrolled with compile-time
+// stage indices and barrier parities.
 // Warps 0-15: epilogue workers in four groups of 128 (thread <-> tile row <-> TMEM lane; group g owns columns [32g, 32g+32) of every
 // 128-column chunk: four warps per scheduler hide the TMEM-load / shared-memory latencies of each other); warp 16: MMA issuer (one
-// elect.sync lane) + TMEM owner; warp 17: weight / z / n_j loader; warp 18: prefetches the per-tile epilogue vectors (U_i, Pf_i) of
-// the next tile into a double-buffered shared-memory slot so that the workers never wait on a global load between tiles.
+// elect.sync lane) + TMEM owner; warp 17: weight / z / n_j loader; warp 18: prefetches the per-tile epilogue vectors (U_i, Pf_i, pair
+// mask) of the next tile into a double-buffered shared-memory slot so that the workers never wait on a global load between tiles,
+// and issues the bulk store of the finished tile.
 // All operands fp16 (10-bit mantissa = TF32 precision, which the pair side tolerates: SURVEY §7 hard part 1), fp32 accumulate.
 #pragma once
 #include "tc_common.cuh"
