@@ -487,12 +487,15 @@ __global__ void __launch_bounds__(IPA_THREADS, SP ? 1 : 2) ipa_core_kernel(IpaCo
         // GEMM-b tile that has landed -- a blocking wait for an HBM tile would delay GEMM-o by a whole memory latency
         int io = 0, bt = 0;
         const int total_b = nrows * JB;
+        long long t_idle = clock64();  // bounded like mbar_wait: a protocol bug must trap instead of hanging the GPU
         while (io < nrows) {
           if (mbar_try_wait(p_full, io & 1)) {
             issue_o(io);
             ++io;
+            t_idle = clock64();
             continue;
           }
+          if (clock64() - t_idle > 4000000000LL) __trap();
           if (bt < total_b) {
             const int it_b = bt / JB, t = bt - it_b * JB;
             if (t == 0 && it_b >= 2 && !mbar_try_wait(&d1_free[it_b & 1], ((it_b - 2) >> 1) & 1)) continue;  // logits of row it_b - 2 not read yet
@@ -500,6 +503,7 @@ __global__ void __launch_bounds__(IPA_THREADS, SP ? 1 : 2) ipa_core_kernel(IpaCo
             if (mbar_try_wait(&zfull[s], ((uint32_t)bt / a.rz) & 1)) {
               tc_fence_after();
               gemm_b_tile(it_b, t, s);
+              t_idle = clock64();
               if (t == 0) {
                 const int it = it_b;
                 IPA_TS(1);

@@ -239,7 +239,11 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *    512  lin_tc: write the clock64 timeline of CTA (0,0)   1024  lin_tc: 32-column epilogue staging passes
  *   8192  edge embedder: write the clock64 timeline of worker thread 0 of CTA 0
  *  16384  IPA linear_out: 2-way instead of 3-way split-K
- *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition) */
+ *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition)
+ * 1 << 19  clock64 stamps inside the weight-resident Linear kernel (tools/lin_timeline.py with LT_FLAG=524288)
+ * 15 << 20 TIMING EXPERIMENTS of the fused EdgeTransition kernel, RESULTS ARE WRONG while any of them is set (tools/gpu_et_exp.sh):
+ *           1 << 20 no weight bulk copies, 2 << 20 MMAs shrunk to N = 16, 4 << 20 no shared-memory stores in the epilogues,
+ *           8 << 20 the timeline samples CTA 77, tiles 40-47 instead of CTA 0, tiles 0-7 (this one leaves the results intact) */
 enum { FDPT_OPT_GEMM_TC = 0, FDPT_OPT_MN_SWAP = 1, FDPT_OPT_ET_TIMELINE = 2, FDPT_OPT_DEBUG_FLAGS = 3, FDPT_OPT_GRAPH = 4 /* 1 (default): replay one captured CUDA graph per timestep in fdpt_sample */,
        FDPT_OPT_ET_PAIR = 5 /* retired: the cta_group::2 EdgeTransition variant of round 1 was slower (1.3 vs 1.0 ms) and has been removed */,
        FDPT_OPT_ET_R2_TMEM = 10 /* retired switch: the fused EdgeTransition kernel always hands r2 to its third GEMM through tensor memory
