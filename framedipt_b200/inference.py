@@ -52,8 +52,9 @@ class _TrajReader:
     backbone trajectories are expanded to the reference's [T,B,N,37,3] layout on the way; only 5 of the 37 atom slots are ever
     non-zero).  The reference materialises the same arrays with np.stack at the end (experiments/utils.py:610-626)."""
 
-    def __init__(self, ctx, out: dict, T: int, chunk: int, keys: list[str]):
+    def __init__(self, ctx, out: dict, T: int, chunk: int, keys: list[str], event_every: int | None = None):
         self.ctx, self.out, self.T, self.chunk, self.keys = ctx, out, T, chunk, keys
+        self.event_every = event_every or chunk  # device-side progress events are recorded every this many timesteps
         self.side = torch.cuda.Stream(device=ctx.device)
         self.host = {}
         for k in keys:
@@ -79,8 +80,17 @@ class _TrajReader:
 
     def run(self) -> dict[str, np.ndarray]:
         T, c = self.T, self.chunk
-        for s0 in range(0, T, c):
-            s1 = min(s0 + c, T)
+        # read-back groups: whole chunks while the trajectory is long, then single events: whatever is read after the last
+        # timestep has finished is exposed time, so the final group is as small as the event granularity allows
+        ev = self.event_every
+        bounds = list(range(0, max(T - c, 0), c))
+        b = bounds[-1] + c if bounds else 0
+        while b < T:
+            bounds.append(b)
+            b += ev
+        bounds.append(T)
+        bounds = sorted(set(bounds))
+        for s0, s1 in zip(bounds[:-1], bounds[1:]):
             self.ctx.wait_step(s1 - 1)
             lo, hi = T - s1, T - s0  # step s writes slot T-1-s (index 0 = final sample)
             for k in self.keys:
@@ -131,10 +141,11 @@ def inference_fn(model: ScoreNetwork, diffuser, data_init: dict, num_t: int, min
         seed = int(np.random.randint(0, 2 ** 31 - 1)) if philox_seed is None else int(philox_seed)
     flags = (1 if (embed_self_conditioning and self_condition) else 0) | (0 if embed_self_conditioning else 2)
     chunk = max(1, min(int(readback_chunk), num_t))
+    ev = 5 if chunk % 5 == 0 else chunk  # progress events every 5 timesteps: the last read-back group covers 5 steps, not `chunk`
     out = ctx.sample(pf, sched, t_emb_tab, noise_d, self_condition=flags, center=center, diffuse_rot=diffuser._diffuse_rot,
-                     diffuse_trans=diffuser._diffuse_trans, final_only=False, philox_seed=seed, progress_chunk=chunk)
+                     diffuse_trans=diffuser._diffuse_trans, final_only=False, philox_seed=seed, progress_chunk=ev)
     keys = ["prot_traj"] + (["rigid_traj", "trans_traj", "rigid_0_traj"] if aux_traj else [])
-    host = _TrajReader(ctx, out, num_t, chunk, keys).run()
+    host = _TrajReader(ctx, out, num_t, chunk, keys, event_every=ev).run()
     torch.cuda.current_stream(dev).synchronize()
     ret = {"prot_traj": host["prot_traj"]}
     if aux_traj:
