@@ -479,6 +479,7 @@ struct Lin {
           a.tiles_per_cta = best;
         }
         a.stg_cols = (ctx->dbg_flags & 1024) ? 32 : 16;  // 16-column staging patches: measured faster than 32 for every layer shape (profiles/r01_bench_lin_ablation.txt)
+        if (ipa) a.stg_cols = -1;  // the image-writing epilogues (IPA projection, transformer in_proj) need no transposition patches: 17 KB more for the weight ring
         a.units = std::min(8, (int)((ctx->max_smem_optin - tc::lin_tc_fixed_bytes(pw.nkb, a.stg_cols)) / tc::LT_UNIT_BYTES));
         a.bias = bias; a.relu = relu; a.rowmask = rowmask; a.residual = residual; a.ldr = ldr; a.Y = y; a.ldy = ldc;
         a.dbg_flags = ctx->dbg_flags;
