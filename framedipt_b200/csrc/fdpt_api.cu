@@ -672,7 +672,7 @@ int run_ipa(fdpt_ctx* ctx, int blk, int B, int N, const float* s, const __half* 
   }
   }
   {
-    const IpaSmemPlan plan = ipa_core_plan(N, ctx->max_smem_optin, ctx->max_smem_sm);
+    const IpaSmemPlan plan = ipa_core_plan(N, ctx->max_smem_optin, ctx->max_smem_sm, (ctx->dbg_flags & 65536) != 0);  // debug flag 65536: two-pass kernel also for N <= 384
     if (plan.rz < 1) return fail(ctx, FDPT_ERR_INVALID, "N=%d needs more shared memory than available in ipa_core", N);
     IpaCoreArgs a;
     a.B = B; a.N = N; a.JB = w.JB; a.ldS = w.ldS; a.S = w.S; a.z = z; a.Wb_img = p.imgWb; a.bb = p.bb;

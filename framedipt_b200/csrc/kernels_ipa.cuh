@@ -302,7 +302,7 @@ __host__ __device__ inline size_t ipa_pimg_bytes(int JB) {  // probability image
 // the row has produced P and GEMM-o runs without a second fetch (single pass over z, one CTA per SM).  Larger N: the tiles of a row
 // are fetched twice (the second time from L2); the kernel is then latency-bound per row, so two CTAs per SM are preferred whenever
 // they fit (2-slot z ring, <= 256 TMEM columns each), otherwise one CTA with the deepest ring.
-inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
+inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm, bool force_two_pass = false) {
   const int JB = (N + 127) / 128;
   const size_t other_sp = ipa_pimg_bytes(JB) + 4096 + (size_t)NH * JB * 128 * 4 + 512 + 1024;  // single pass: down_z.weight in registers
   const size_t other = other_sp + C_Z * (C_Z / 4) * 4;                                          // else: staged in shared memory
@@ -311,7 +311,7 @@ inline IpaSmemPlan ipa_core_plan(int N, int max_smem, int max_smem_per_sm) {
   p.tmem_cols = need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512);
   p.single_pass = 0;
   const size_t two = other + 2 * (size_t)IPA_TILE_BYTES;
-  if (2 * JB <= IPA_MAX_RZ && other_sp + 2 * (size_t)JB * IPA_TILE_BYTES <= (size_t)max_smem) {
+  if (!force_two_pass && 2 * JB <= IPA_MAX_RZ && other_sp + 2 * (size_t)JB * IPA_TILE_BYTES <= (size_t)max_smem) {
     // two whole rows resident (N <= 384): one CTA per SM, every z tile crosses HBM / L2 once
     p.rz = 2 * JB;
     p.ctas_per_sm = 1;

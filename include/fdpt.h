@@ -240,6 +240,7 @@ int fdpt_bench_linear(fdpt_ctx* ctx, int M, int N, int K, const float* x, const 
  *   8192  edge embedder: write the clock64 timeline of worker thread 0 of CTA 0
  *  16384  IPA linear_out: 2-way instead of 3-way split-K
  *  32768  no operand-image chaining between consecutive Linear layers (transformer FFN, node transition)
+ *  65536  IPA core: the two-pass kernel (z rows fetched twice, two CTAs per SM) also for N <= 384 (A/B switch and test hook)
  * 1 << 19  clock64 stamps inside the weight-resident Linear kernel (tools/lin_timeline.py with LT_FLAG=524288)
  * 15 << 20 TIMING EXPERIMENTS of the fused EdgeTransition kernel, RESULTS ARE WRONG while any of them is set (tools/gpu_et_exp.sh):
  *           1 << 20 no weight bulk copies, 2 << 20 MMAs shrunk to N = 16, 4 << 20 no shared-memory stores in the epilogues,

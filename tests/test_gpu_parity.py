@@ -447,11 +447,15 @@ def test_ipa_operand_image_modes_agree(model):
         ctx.set_option(7, 1)
         ctx.set_option(8, 0)  # sequence-transformer attention on the fp32-operand GEMM path (FDPT_OPT_TF_IMG = 0)
         outs["tf0"] = {k: v.cpu().numpy() for k, v in m(feats).items()}
+        ctx.set_option(8, 1)
+        ctx.set_option(3, 65536)  # IPA core: the two-pass kernel (N > 384 path) instead of the single-pass one
+        outs["two_pass"] = {k: v.cpu().numpy() for k, v in m(feats).items()}
     finally:
         ctx.set_option(7, 1)
         ctx.set_option(8, 1)
+        ctx.set_option(3, 0)
     valid = feats["res_mask"].cpu().numpy().astype(bool)
-    for mode in (2, 0, "tf0"):
+    for mode in (2, 0, "tf0", "two_pass"):
         d = np.abs(outs[mode]["rigids"][..., 4:] - outs[1]["rigids"][..., 4:])[valid].max()
         da = rot_angle_between(outs[mode]["rigids"][..., :4], outs[1]["rigids"][..., :4])[valid].max()
         print(f"IPA image mode {mode} vs 1: |dtrans| {d:.2e} A, rot {da:.2e} rad")
